@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the 2D TM+PML time-stepping hot path (BASELINE.json metric: Mcell-updates/s and HBM GB/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full FDTD time step (D, E, Hx, Hy and both PML integrals of every cell).  Workload at
+N GPUs: BASELINE config 5 weak-scaled -- every GPU owns a 32768 x 32768 fp32 row slab of an
+(N*32768) x 32768 grid with npml=80 and the point sinusoid of program 3_2, ghost rows exchanged over
+NVLink every time block.  One JSON line on stdout (rank 0).
+
+--impl reference times the REFERENCE's own C/OpenMP step functions (oracle/_ref, compiled from
+/root/reference/fd2d/clang/test_3_2.c; falls back to the numpy oracle port when absent) on all host cores,
+on a bounded sample of the same workload.  The oracle is used only there and in the cpu_baseline leg --
+never on the measured GPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FULL = 32768
+NPML = 80
+BYTES_PER_CELL_UPDATE = 48          # dz,hx,hy,ihx,ihy R+W; naz R; ez W (fp32) -- SURVEY.md 8(d)
+METRIC = "Mcell-updates/s, 2D TM+PML fp32"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/bench_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------ CPU legs
+def cpu_numpy_port(n, steps):
+    """The numpy oracle (bit-identical restatement of fd2d/program/fd2d_3_2.py) on one core."""
+    from oracle import fdtd_oracle as orc
+    g = orc.Grid2D(n, n, NPML, np.float32, point=(n // 2 - 5, n // 2 - 5))
+    src = orc.source_table("sine", steps + 1, freq=1500e6)
+    orc.step_2d(g, np.int32(1), src[0])                       # warm-up (page faults, temporaries)
+    t0 = time.perf_counter()
+    for k in range(1, steps + 1):
+        orc.step_2d(g, np.int32(k + 1), src[k])
+    dt = time.perf_counter() - t0
+    return n * n * steps / dt / 1e6, dt
+
+
+def cpu_reference_c(nx, ny, steps, warm=1):
+    """The reference's own C/OpenMP dfield/efield/hfield (oracle/_ref/libref_fd2d_3_2.so), all host threads."""
+    import ctypes as C
+    from oracle import fdtd_oracle as orc
+    from oracle import ref_c
+    lib = ref_c.load("3_2")
+    g = orc.Grid2D(nx, ny, NPML, np.float32, point=(nx // 2 - 5, ny // 2 - 5))
+    ps = ref_c.pml_struct(g.pml)
+    p = ref_c._p
+
+    def one(t):
+        lib.dfield(C.c_int(t), nx, ny, C.byref(ps), p(g.dz), p(g.hx), p(g.hy))
+        lib.efield(nx, ny, p(g.naz), p(g.dz), p(g.ez))
+        lib.hfield(nx, ny, C.byref(ps), p(g.ez), p(g.ihx), p(g.ihy), p(g.hx), p(g.hy))
+    for t in range(1, warm + 1):
+        one(t)
+    t0 = time.perf_counter()
+    for t in range(warm + 1, warm + steps + 1):
+        one(t)
+    dt = time.perf_counter() - t0
+    return nx * ny * steps / dt / 1e6, dt
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only; a bounded sample (8192 x 8192 of the 32768 x 32768 workload) per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_c
+    cores = os.cpu_count() or 1
+    n = 8192
+    steps, warm = max(1, args.steps), max(1, args.warmup)
+    # keep the whole run within a few minutes whatever K the driver asks for
+    steps, warm = min(steps, 40), min(warm, 3)
+    if ref_c.available("3_2"):
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        v, dt = cpu_reference_c(n, n, steps, warm)
+        kind, how = "reference", "reference C/OpenMP step functions (fd2d/clang/test_3_2.c) via oracle/_ref"
+    else:
+        n, steps = 4096, min(steps, 10)
+        v, dt = cpu_numpy_port(n, steps)
+        cores, kind, how = 1, "port", "numpy oracle port (oracle/_ref not built)"
+    sample = f"{n}x{n} fp32 sub-grid of the {N_FULL}x{N_FULL} workload, {steps} steps after {warm} warm-up; {how}"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mcell-updates/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fd2d TM+PML {N_FULL}x{N_FULL} fp32 npml={NPML} point sinusoid (BASELINE config 5)",
+                       "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "Mcell-updates/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from simulation_b200 import fd2d, surface
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    n, K, W, T = args.size, args.steps, args.warmup, args.tblock
+    nx_global = n * world                       # weak scaling: one n x n slab per GPU
+    wave = surface.Sinusoid(1500e6)
+    src = fd2d.PointSource(nx_global // 2 - 5, n // 2 - 5, wave, hard=True)
+
+    if world > 1:
+        from simulation_b200 import slab
+        sim = slab.SlabFdtd2D(nx_global, n, NPML, np.float32, source=src, tblock=T)
+        barrier = dist.barrier
+    else:
+        sim = fd2d.Fdtd2D(n, n, NPML, np.float32, source=src, tblock=T)
+        barrier = lambda: None
+
+    def sync():
+        barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K steps, inputs already in HBM
+    sim.advance(W)
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    sim.advance(K)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = (K + T - 1) // T
+    cells = float(nx_global) * n
+    value = cells * K / (ms * 1e-3) / 1e6
+    peak, peak_src = peaks()
+    per_gpu_cells = float(n) * n
+    achieved = BYTES_PER_CELL_UPDATE * per_gpu_cells * K / (ms * 1e-3) / 1e9      # per GPU, algorithmic GB/s
+    traffic = measured_traffic()
+
+    # ---- end to end through the public API with HOST buffers: naz up (pinned), K steps, ez down (pinned)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(sim, world, rank, n, nx_global, K, T, src, sync)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nn, ss = 4096, 10
+        v, dt = cpu_numpy_port(nn, ss)
+        cpu = {"value": v, "unit": "Mcell-updates/s", "cores": 1, "kind": "port",
+               "sample": f"{nn}x{nn} fp32 npml={NPML}, {ss} steps after 1 warm-up ({dt:.1f} s); numpy oracle == "
+                         f"fd2d/program/fd2d_3_2.py statements (single-threaded numpy), host has {os.cpu_count()} cores"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"fd2d TM+PML {nx_global}x{n} fp32 npml={NPML} point sinusoid 1500 MHz "
+                                       f"(BASELINE config 5{'' if world == 1 else ', weak-scaled row slabs'})",
+                           "grid_per_gpu": [n, n], "tblock": T, "parallelism": f"slab{world}",
+                           "l2": "inputs (52 GB per GPU) far exceed the 126 MB L2; no flush needed",
+                           "timing": "CUDA events on the launch stream, barrier+sync both sides, max over ranks"},
+                "gpu_launches": launches * (1 if world == 1 else 1),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
+                             "kernel": f"k_march<float,V=4,T={T}>", "launches": launches,
+                             "avg_launch_ms": ms / launches,
+                             "algorithmic_bytes_per_launch": BYTES_PER_CELL_UPDATE * per_gpu_cells * T,
+                             "peak_source": peak_src,
+                             "note": "achieved = 48 B x cells x steps / time; a T-step pass moves ~48 B per cell once, "
+                                     "so frac may exceed 1 (traffic = real DRAM bytes per launch from ncu)"},
+                "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync):
+    """Same metric through the user-facing call with host buffers: upload the medium (naz) from pinned host
+    memory, run K steps, read Ez back into pinned host memory; all inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    rows = sim.row_hi - sim.row_lo
+    host_naz = torch.ones((rows, n), dtype=torch.float32).pin_memory()
+    host_ez = torch.empty((rows, n), dtype=torch.float32).pin_memory()
+    for name in ("dz", "hx", "hy", "ihx", "ihy", "ez"):            # fresh problem: fields start at zero
+        sim.tensor(name, stored=True).zero_()
+    sim.t = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    o = sim.row_lo - sim.row_base
+    sim.naz[o:o + rows].copy_(host_naz, non_blocking=True)
+    sim.advance(K)
+    host_ez.copy_(sim.tensor("ez"), non_blocking=True)
+    e1.record()
+    sync()
+    dt = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    nbytes = rows * n * 4
+    return {"value": float(nx_global) * n * K / dt / 1e6, "unit": "Mcell-updates/s",
+            "h2d_bytes_per_step": nbytes / K, "d2h_bytes_per_step": nbytes / K,
+            "what": f"pinned naz H2D ({nbytes / 2**30:.1f} GiB/GPU) + advance({K}) + pinned Ez D2H, CUDA events on the launch stream, max over ranks"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=N_FULL, help="rows and columns per GPU (default: BASELINE config 5)")
+    ap.add_argument("--tblock", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+/* fdtd_b200.h -- C ABI of libfdtd_b200.so: B200 (sm_100a) kernels for the Yee time-stepping hot path of
+ * dsarvan/simulation (fd1d/: Ex/Hy; fd2d/: TM Dz/Ez/Hx/Hy + PML + TFSF + lossy medium).
+ *
+ * The reference has no FFI; its operator interface is the module-level step-function protocol shared by
+ * all of its language variants, and -- for a Python host driving GPU kernels -- the PyCUDA idiom
+ *     fn = SourceModule(src).get_function("dfield"); fn(t, nx, ny, pml, ezi, dz, hx, hy, grid=, block=)
+ * (reference fd2d/pycuda/test_3_3.py:247-270, fd2d/cuda/test_3_4.cu:20-36,333-343).  This header keeps those
+ * function names, argument order and in-place/caller-owns-everything semantics, on raw device pointers.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, a negative FDTD_E* code on failure; fdtd_last_error()
+ *     returns a thread-local message.  The reference has no error reporting at all.
+ *   - `dtype` is FDTD_F32 or FDTD_F64; every array of one call has that element type.
+ *   - all array arguments are DEVICE pointers (16-byte aligned); 2D arrays are C-order (nx rows, ny
+ *     columns, j fastest), exactly the reference layout n = i*ny + j (fd2d/cuda/test_3_4.cu:80).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous.
+ *   - source waveforms are evaluated on the HOST in float64 (the reference hard-codes them inside
+ *     dfield/exfield/dxfield): a hard source overwrites, a soft source is added in float64 and rounded
+ *     once -- the numpy semantics of `ex[1] += np.float64`.
+ *   - arithmetic is evaluated in the reference's left-to-right order with no FMA contraction, so results
+ *     are bit-identical to the reference numpy programs.
+ */
+#ifndef FDTD_B200_H
+#define FDTD_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDTD_F32 0
+#define FDTD_F64 1
+
+#define FDTD_OK            0
+#define FDTD_EINVAL       -1   /* bad argument (size, alignment, dtype, null pointer) */
+#define FDTD_ECUDA        -2   /* a CUDA runtime call or kernel launch failed */
+#define FDTD_EUNSUPPORTED -3   /* valid request this build has no kernel for */
+
+/* problem feature flags */
+#define FDTD_TFSF   1          /* incident line + total-field/scattered-field corrections (programs 3_3, 3_4) */
+#define FDTD_LOSSY  2          /* conduction-current integral iz / nbz (program 3_4) */
+#define FDTD_ABC    4          /* 1D two-step-delay absorbing boundaries (programs 1_2 ..) */
+#define FDTD_FLUX   8          /* 1D flux form Dx/Ex/Ix (programs 2_1, 2_2) */
+#define FDTD_DEBYE 16          /* 1D Debye medium Sx (program 2_3) */
+
+/* structs of device pointers, in the reference's declaration order
+ * (fd2d/cuda/test_3_4.cu:20-36, fd1d/cuda/test_2_3.cu:17-27) */
+typedef struct { const void *fx1, *fx2, *fx3, *fy1, *fy2, *fy3, *gx2, *gx3, *gy2, *gy3; } fdtd_pmlayer;
+typedef struct { const void *naz, *nbz; } fdtd_medium2d;             /* nbz may be NULL (lossless) */
+typedef struct { const void *nax, *nbx, *ncx, *ndx; } fdtd_medium1d; /* ncx/ndx may be NULL */
+typedef struct { void *r_pt, *i_pt, *r_in, *i_in; } fdtd_ftrans;
+
+/* one source sample: target[index] = value (hard) or target[index] += value (soft, float64 add).
+ * target == NULL: no source. */
+typedef struct { void *target; long long index; int hard; double value; } fdtd_source;
+
+/* ------------------------------------------------------------------------------------------ misc */
+const char *fdtd_last_error(void);
+int fdtd_version(void);
+/* device facts used by the host for sizing: SM count, free / total bytes of the current device */
+int fdtd_device_info(int *sm_count, size_t *free_bytes, size_t *total_bytes);
+/* optional allocator / copies for hosts that do not bring their own device memory */
+int fdtd_malloc(void **dptr, size_t bytes);
+int fdtd_free(void *dptr);
+int fdtd_memset0(void *dptr, size_t bytes, void *stream);
+int fdtd_upload(void *dptr, const void *hptr, size_t bytes, void *stream);
+int fdtd_download(void *hptr, const void *dptr, size_t bytes, void *stream);
+int fdtd_stream_sync(void *stream);
+
+/* ------------------------------------------------------------- 1D: reference-named step functions */
+/* ex[1:nx] = ca*ex + cb*(hy[i-1]-hy[i]); then the source.  ca == NULL means 1, cb == NULL means 0.5.
+ * replaces exfield of fd1d/cuda/test_1_1.cu:22-29, test_1_3.cu:22-30, test_1_5.cu:30-37
+ * (numpy: fd1d/program/fd1d_1_5.py:65-67) */
+int fdtd1d_exfield(int dtype, int nx, const void *ca, const void *cb, void *ex, const void *hy,
+                   const fdtd_source *src, void *stream);
+/* ABC (if abc != 0) then hy[0:nx-1] += 0.5*(ex[i]-ex[i+1]).
+ * replaces hyfield of fd1d/cuda/test_1_2.cu:32-40 (numpy: fd1d/program/fd1d_2_1.py:56-61) */
+int fdtd1d_hyfield(int dtype, int nx, void *ex, void *hy, void *bc, int abc, void *stream);
+/* dx[1:nx] += 0.5*(hy[i-1]-hy[i]); then the source.  replaces dxfield of fd1d/cuda/test_2_3.cu:51-58 */
+int fdtd1d_dxfield(int dtype, int nx, void *dx, const void *hy, const fdtd_source *src, void *stream);
+/* ex = nax*(dx-ix[-ncx*sx]); ix += nbx*ex; [sx = ncx*sx + ndx*ex]   (sx == NULL: no Debye term).
+ * replaces exfield of fd1d/cuda/test_2_1.cu:39-47 and test_2_3.cu:61-69 */
+int fdtd1d_exfield_flux(int dtype, int nx, const fdtd_medium1d *md, const void *dx, void *ix, void *sx,
+                        void *ex, void *stream);
+
+/* --------------------------------------------------------------------- 1D: fused time-blocked path */
+typedef struct {
+    int dtype, nx, flags;              /* FDTD_ABC | FDTD_FLUX | FDTD_DEBYE */
+    const void *ca, *cb;               /* FDTD form (NULL = 1 / 0.5) */
+    fdtd_medium1d md;                  /* flux form */
+    void *state[2][5];                 /* two ping-pong sets of ex, hy, dx, ix, sx (unused: NULL) */
+    void *bc[2];                       /* two ping-pong copies of bc[4] */
+    int src_field;                     /* 0: ex, 1: dx */
+    int src_index, src_hard;           /* src_index < 0: no source */
+} fdtd1d_problem;
+/* advance nsteps steps starting from state set `cur`; src[k] is the float64 waveform sample of the k-th of
+ * these steps (HOST pointer, may be NULL without a source).  *cur_out = set holding the result. */
+int fdtd1d_advance(const fdtd1d_problem *p, int cur, int nsteps, const double *src, int tblock,
+                   void *stream, int *cur_out);
+
+/* ------------------------------------------------------------- 2D: reference-named step functions */
+/* replaces ezinct of fd2d/cuda/test_3_4.cu:63-72 (numpy fd2d/program/fd2d_3_3.py:60-65) */
+int fdtd2d_ezinct(int dtype, int ny, void *ezi, const void *hxi, void *bc, void *stream);
+/* replaces dfield of fd2d/cuda/test_3_4.cu:75-86, test_3_2.cu:34-48 (numpy fd2d_3_3.py:68-72);
+ * the embedded source assignment (ezi[3] = pulse / dz[src] = pulse) is `src` */
+int fdtd2d_dfield(int dtype, int nx, int ny, const fdtd_pmlayer *pml, void *dz, const void *hx,
+                  const void *hy, const fdtd_source *src, void *stream);
+/* replaces inctdz of fd2d/cuda/test_3_4.cu:89-96 (numpy fd2d_3_3.py:75-78) */
+int fdtd2d_inctdz(int dtype, int nx, int ny, int npml, const void *hxi, void *dz, void *stream);
+/* replaces efield of fd2d/cuda/test_3_4.cu:99-109 / test_3_3.cu:69-78; iz == NULL: ez = naz*dz */
+int fdtd2d_efield(int dtype, int nx, int ny, const fdtd_medium2d *md, const void *dz, void *iz, void *ez,
+                  void *stream);
+/* replaces hxinct of fd2d/cuda/test_3_4.cu:112-118 */
+int fdtd2d_hxinct(int dtype, int ny, const void *ezi, void *hxi, void *stream);
+/* replaces hfield of fd2d/cuda/test_3_4.cu:121-133 (numpy fd2d_3_3.py:91-98) */
+int fdtd2d_hfield(int dtype, int nx, int ny, const fdtd_pmlayer *pml, const void *ez, void *ihx, void *ihy,
+                  void *hx, void *hy, void *stream);
+/* replace incthx / incthy of fd2d/cuda/test_3_4.cu:136-153 (numpy fd2d_3_3.py:101-110) */
+int fdtd2d_incthx(int dtype, int nx, int ny, int npml, const void *ezi, void *hx, void *stream);
+int fdtd2d_incthy(int dtype, int nx, int ny, int npml, const void *ezi, void *hy, void *stream);
+
+/* --------------------------------------------------------------------- 2D: fused time-blocked path */
+enum { FDTD2D_DZ = 0, FDTD2D_EZ, FDTD2D_HX, FDTD2D_HY, FDTD2D_IHX, FDTD2D_IHY, FDTD2D_IZ, FDTD2D_NFIELDS };
+
+typedef struct {
+    int dtype;
+    int nx, ny;                 /* GLOBAL grid size */
+    int row_lo, row_hi;         /* global rows this device owns and must produce: [row_lo, row_hi) */
+    int row_base, rows_alloc;   /* global row index of array row 0, and rows stored per array (owned + ghosts) */
+    int npml, flags;            /* FDTD_TFSF | FDTD_LOSSY */
+    fdtd_pmlayer pml;           /* x-vectors: GLOBAL length nx; y-vectors: length ny */
+    fdtd_medium2d md;           /* local layout (rows_alloc x ny) */
+    void *state[2][FDTD2D_NFIELDS];  /* two ping-pong sets, local layout; IZ may be NULL without FDTD_LOSSY */
+    void *ezi, *hxi, *bc;       /* incident line, length ny / ny / 4 (FDTD_TFSF) */
+    void *ezi_hist, *hxi_hist;  /* scratch: tblock*ny and tblock*2 elements (FDTD_TFSF) */
+    int src_i, src_j, src_hard; /* point source on dz at GLOBAL (src_i, src_j); src_i < 0: none.
+                                   With FDTD_TFSF the table drives ezi[3] instead (hard). */
+} fdtd2d_problem;
+
+/* Advance nsteps full time steps (reference order: ezinct, dfield+source, inctdz, efield, hxinct, hfield,
+ * incthx, incthy -- fd2d/python/fd2d_3_4.py:268-277) from state set `cur`, tblock steps per kernel pass.
+ * Rows [row_lo-g, row_hi+g) with g = nsteps must be present and current in set `cur` (clipped to the
+ * grid); single device: row_lo=row_base=0, row_hi=rows_alloc=nx and any nsteps is allowed.
+ * src: HOST float64 table, one sample per step.  *cur_out = set holding the result. */
+int fdtd2d_advance(const fdtd2d_problem *p, int cur, int nsteps, const double *src, int tblock,
+                   void *stream, int *cur_out);
+/* largest supported tblock for a dtype / ny (0 if unsupported) */
+int fdtd2d_max_tblock(int dtype, int ny);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDTD_B200_H */

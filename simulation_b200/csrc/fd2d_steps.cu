@@ -1,0 +1,218 @@
+// 2D TM step functions under the reference's names, one kernel per reference function, on raw device
+// pointers.  This is the drop-in / parity / debug path (the benchmarked path is fd2d_march.cu); the
+// arithmetic, index ranges and evaluation order are those of the reference numpy programs
+// (fd2d/program/fd2d_3_3.py:60-110, fd2d/python/fd2d_3_4.py:131-136), so the results are bit-identical.
+#include "common.cuh"
+
+namespace {
+
+using fdtd::inject;
+
+constexpr int BX = 64, BY = 4;   // 64 consecutive j per warp-pair row: coalesced along the fast axis
+
+template <typename real>
+struct Pml {
+    const real *fx1, *fx2, *fx3, *fy1, *fy2, *fy3, *gx2, *gx3, *gy2, *gy3;
+    explicit Pml(const fdtd_pmlayer &p)
+        : fx1((const real *)p.fx1), fx2((const real *)p.fx2), fx3((const real *)p.fx3),
+          fy1((const real *)p.fy1), fy2((const real *)p.fy2), fy3((const real *)p.fy3),
+          gx2((const real *)p.gx2), gx3((const real *)p.gx3), gy2((const real *)p.gy2),
+          gy3((const real *)p.gy3) {}
+};
+
+template <typename real>
+__global__ void k_source(real *target, long long index, int hard, double value) {
+    target[index] = inject<real>(target[index], value, hard);
+}
+
+// ezi[1:ny] += 0.5*(hxi[j-1]-hxi[j]); then the two-step-delay ABC on both ends.  Single CTA: the ABC
+// reads ezi[1] / ezi[ny-2] AFTER the stencil, which needs a barrier (the reference CUDA kernel races here).
+template <typename real>
+__global__ void k_ezinct(int ny, real *ezi, const real *hxi, real *bc) {
+    for (int j = 1 + threadIdx.x; j < ny; j += blockDim.x) ezi[j] = ezi[j] + real(0.5) * (hxi[j - 1] - hxi[j]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        real e1 = ezi[1], b0 = bc[0], b1 = bc[1];
+        ezi[0] = b0; bc[0] = b1; bc[1] = e1;
+        real e2 = ezi[ny - 2], b3 = bc[3], b2 = bc[2];
+        ezi[ny - 1] = b3; bc[3] = b2; bc[2] = e2;
+    }
+}
+
+template <typename real>
+__global__ void k_hxinct(int ny, const real *ezi, real *hxi) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < ny - 1) hxi[j] = hxi[j] + real(0.5) * (ezi[j] - ezi[j + 1]);
+}
+
+template <typename real>
+__global__ void k_dfield(int nx, int ny, Pml<real> p, real *dz, const real *hx, const real *hy) {
+    int j = blockIdx.x * BX + threadIdx.x;
+    int i = blockIdx.y * BY + threadIdx.y;
+    if (i < 1 || i >= nx || j < 1 || j >= ny) return;
+    size_t n = (size_t)i * ny + j;
+    real curl = ((hy[n] - hy[n - ny]) - hx[n]) + hx[n - 1];
+    dz[n] = ((p.gx3[i] * p.gy3[j]) * dz[n]) + (((p.gx2[i] * p.gy2[j]) * real(0.5)) * curl);
+}
+
+template <typename real>
+__global__ void k_inctdz(int nx, int ny, int npml, const real *hxi, real *dz) {
+    int i = npml - 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nx - npml) return;
+    size_t a = (size_t)i * ny + (npml - 1), b = (size_t)i * ny + (ny - npml);
+    dz[a] = dz[a] + real(0.5) * hxi[npml - 2];
+    dz[b] = dz[b] - real(0.5) * hxi[ny - npml];
+}
+
+template <typename real, bool LOSSY>
+__global__ void k_efield(int nx, int ny, const real *naz, const real *nbz, const real *dz, real *iz, real *ez) {
+    int j = blockIdx.x * BX + threadIdx.x;
+    int i = blockIdx.y * BY + threadIdx.y;
+    if (i >= nx || j >= ny) return;
+    size_t n = (size_t)i * ny + j;
+    if (LOSSY) {
+        real e = naz[n] * (dz[n] - iz[n]);
+        ez[n] = e;
+        iz[n] = iz[n] + nbz[n] * e;
+    } else {
+        ez[n] = naz[n] * dz[n];
+    }
+}
+
+template <typename real>
+__global__ void k_hfield(int nx, int ny, Pml<real> p, const real *ez, real *ihx, real *ihy, real *hx, real *hy) {
+    int j = blockIdx.x * BX + threadIdx.x;
+    int i = blockIdx.y * BY + threadIdx.y;
+    if (i >= nx - 1 || j >= ny - 1) return;
+    size_t n = (size_t)i * ny + j;
+    real e = ez[n];
+    real cm = e - ez[n + 1];
+    real cn = e - ez[n + ny];
+    real ax = ihx[n] + cm;
+    real ay = ihy[n] + cn;
+    ihx[n] = ax;
+    ihy[n] = ay;
+    hx[n] = (p.fy3[j] * hx[n]) + (p.fy2[j] * ((real(0.5) * cm) + (p.fx1[i] * ax)));
+    hy[n] = (p.fx3[i] * hy[n]) - (p.fx2[i] * ((real(0.5) * cn) + (p.fy1[j] * ay)));
+}
+
+template <typename real>
+__global__ void k_incthx(int nx, int ny, int npml, const real *ezi, real *hx) {
+    int i = npml - 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nx - npml) return;
+    size_t a = (size_t)i * ny + (npml - 2), b = (size_t)i * ny + (ny - npml);
+    hx[a] = hx[a] + real(0.5) * ezi[npml - 1];
+    hx[b] = hx[b] - real(0.5) * ezi[ny - npml];
+}
+
+template <typename real>
+__global__ void k_incthy(int nx, int ny, int npml, const real *ezi, real *hy) {
+    int j = npml - 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > ny - npml) return;
+    size_t a = (size_t)(npml - 2) * ny + j, b = (size_t)(nx - npml) * ny + j;
+    real h = real(0.5) * ezi[j];
+    if (a == b) {            // degenerate geometry: both corrections hit the same cell, in reference order
+        hy[a] = (hy[a] - h) + h;
+    } else {
+        hy[a] = hy[a] - h;
+        hy[b] = hy[b] + h;
+    }
+}
+
+inline dim3 grid2d(int nx, int ny) { return dim3((ny + BX - 1) / BX, (nx + BY - 1) / BY); }
+
+template <typename real>
+int apply_source(const fdtd_source *src, cudaStream_t st) {
+    if (src == nullptr || src->target == nullptr) return FDTD_OK;
+    FDTD_REQUIRE(src->index >= 0, "source index %lld < 0", src->index);
+    k_source<real><<<1, 1, 0, st>>>((real *)src->target, src->index, src->hard, src->value);
+    FDTD_LAUNCH_CHECK("k_source");
+    return FDTD_OK;
+}
+
+bool tfsf_geometry_ok(int nx, int ny, int npml) { return npml >= 2 && 2 * npml <= nx && 2 * npml <= ny; }
+
+}  // namespace
+
+namespace fdtd {
+int launch_source(int dtype, const fdtd_source *src, cudaStream_t st) {
+    return dtype == FDTD_F32 ? apply_source<float>(src, st) : apply_source<double>(src, st);
+}
+}  // namespace fdtd
+
+#define DISPATCH(dtype, CALL)                                                     \
+    if ((dtype) == FDTD_F32) { using real = float; CALL; }                        \
+    else if ((dtype) == FDTD_F64) { using real = double; CALL; }                  \
+    else { fdtd::set_error("unknown dtype %d", (int)(dtype)); return FDTD_EINVAL; }
+
+extern "C" {
+
+int fdtd2d_ezinct(int dtype, int ny, void *ezi, const void *hxi, void *bc, void *stream) {
+    FDTD_REQUIRE(ny >= 3 && ezi && hxi && bc, "fdtd2d_ezinct: bad arguments (ny=%d)", ny);
+    DISPATCH(dtype, (k_ezinct<real><<<1, 1024, 0, fdtd::as_stream(stream)>>>(ny, (real *)ezi, (const real *)hxi, (real *)bc)));
+    FDTD_LAUNCH_CHECK("k_ezinct");
+    return FDTD_OK;
+}
+
+int fdtd2d_hxinct(int dtype, int ny, const void *ezi, void *hxi, void *stream) {
+    FDTD_REQUIRE(ny >= 2 && ezi && hxi, "fdtd2d_hxinct: bad arguments (ny=%d)", ny);
+    DISPATCH(dtype, (k_hxinct<real><<<(ny + 255) / 256, 256, 0, fdtd::as_stream(stream)>>>(ny, (const real *)ezi, (real *)hxi)));
+    FDTD_LAUNCH_CHECK("k_hxinct");
+    return FDTD_OK;
+}
+
+int fdtd2d_dfield(int dtype, int nx, int ny, const fdtd_pmlayer *pml, void *dz, const void *hx, const void *hy,
+                  const fdtd_source *src, void *stream) {
+    FDTD_REQUIRE(nx >= 2 && ny >= 2 && pml && dz && hx && hy, "fdtd2d_dfield: bad arguments (nx=%d ny=%d)", nx, ny);
+    cudaStream_t st = fdtd::as_stream(stream);
+    DISPATCH(dtype, (k_dfield<real><<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(nx, ny, Pml<real>(*pml), (real *)dz, (const real *)hx, (const real *)hy)));
+    FDTD_LAUNCH_CHECK("k_dfield");
+    return fdtd::launch_source(dtype, src, st);
+}
+
+int fdtd2d_inctdz(int dtype, int nx, int ny, int npml, const void *hxi, void *dz, void *stream) {
+    FDTD_REQUIRE(tfsf_geometry_ok(nx, ny, npml) && hxi && dz, "fdtd2d_inctdz: bad geometry nx=%d ny=%d npml=%d", nx, ny, npml);
+    int n = nx - 2 * npml + 2;
+    DISPATCH(dtype, (k_inctdz<real><<<(n + 255) / 256, 256, 0, fdtd::as_stream(stream)>>>(nx, ny, npml, (const real *)hxi, (real *)dz)));
+    FDTD_LAUNCH_CHECK("k_inctdz");
+    return FDTD_OK;
+}
+
+int fdtd2d_efield(int dtype, int nx, int ny, const fdtd_medium2d *md, const void *dz, void *iz, void *ez, void *stream) {
+    FDTD_REQUIRE(nx >= 1 && ny >= 1 && md && md->naz && dz && ez, "fdtd2d_efield: bad arguments");
+    FDTD_REQUIRE(iz == nullptr || md->nbz != nullptr, "fdtd2d_efield: iz given without nbz");
+    cudaStream_t st = fdtd::as_stream(stream);
+    if (iz) {
+        DISPATCH(dtype, (k_efield<real, true><<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(nx, ny, (const real *)md->naz, (const real *)md->nbz, (const real *)dz, (real *)iz, (real *)ez)));
+    } else {
+        DISPATCH(dtype, (k_efield<real, false><<<grid2d(nx, ny), dim3(BX, BY), 0, st>>>(nx, ny, (const real *)md->naz, nullptr, (const real *)dz, nullptr, (real *)ez)));
+    }
+    FDTD_LAUNCH_CHECK("k_efield");
+    return FDTD_OK;
+}
+
+int fdtd2d_hfield(int dtype, int nx, int ny, const fdtd_pmlayer *pml, const void *ez, void *ihx, void *ihy, void *hx,
+                  void *hy, void *stream) {
+    FDTD_REQUIRE(nx >= 2 && ny >= 2 && pml && ez && ihx && ihy && hx && hy, "fdtd2d_hfield: bad arguments");
+    DISPATCH(dtype, (k_hfield<real><<<grid2d(nx, ny), dim3(BX, BY), 0, fdtd::as_stream(stream)>>>(nx, ny, Pml<real>(*pml), (const real *)ez, (real *)ihx, (real *)ihy, (real *)hx, (real *)hy)));
+    FDTD_LAUNCH_CHECK("k_hfield");
+    return FDTD_OK;
+}
+
+int fdtd2d_incthx(int dtype, int nx, int ny, int npml, const void *ezi, void *hx, void *stream) {
+    FDTD_REQUIRE(tfsf_geometry_ok(nx, ny, npml) && ezi && hx, "fdtd2d_incthx: bad geometry nx=%d ny=%d npml=%d", nx, ny, npml);
+    int n = nx - 2 * npml + 2;
+    DISPATCH(dtype, (k_incthx<real><<<(n + 255) / 256, 256, 0, fdtd::as_stream(stream)>>>(nx, ny, npml, (const real *)ezi, (real *)hx)));
+    FDTD_LAUNCH_CHECK("k_incthx");
+    return FDTD_OK;
+}
+
+int fdtd2d_incthy(int dtype, int nx, int ny, int npml, const void *ezi, void *hy, void *stream) {
+    FDTD_REQUIRE(tfsf_geometry_ok(nx, ny, npml) && ezi && hy, "fdtd2d_incthy: bad geometry nx=%d ny=%d npml=%d", nx, ny, npml);
+    int n = ny - 2 * npml + 2;
+    DISPATCH(dtype, (k_incthy<real><<<(n + 255) / 256, 256, 0, fdtd::as_stream(stream)>>>(nx, ny, npml, (const real *)ezi, (real *)hy)));
+    FDTD_LAUNCH_CHECK("k_incthy");
+    return FDTD_OK;
+}
+
+}  // extern "C"

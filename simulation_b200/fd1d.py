@@ -1,0 +1,170 @@
+"""1D Ex/Hy host side: the reference's step functions under their own names (fd1d/program/fd1d_2_1.py:43-61,
+fd1d_2_3.py:73-94; programs 1_1-1_5 inline the same statements in ``main()``, fd1d_1_5.py:63-72) on CUDA
+tensors, and :class:`Fdtd1D`, which owns the arrays of one line and replaces the reference time loop by a
+fused, temporally blocked ``advance``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .fd2d import _TORCH_DT, _code, _ptr, _require_cuda, _stream
+
+
+class medium(NamedTuple):
+    nax: torch.Tensor
+    nbx: torch.Tensor
+    ncx: Optional[torch.Tensor] = None
+    ndx: Optional[torch.Tensor] = None
+
+
+@dataclass(frozen=True)
+class LineSource:
+    """``field[index] = w(t)`` (hard) or ``field[index] += w(t)`` (soft); field is 'ex' or 'dx'."""
+    index: int
+    waveform: object
+    hard: bool = False
+    field: str = "ex"
+
+
+def _src(target, source, t):
+    if source is None:
+        return None
+    return _lib.Source(target.data_ptr(), int(source.index), int(bool(source.hard)),
+                       float(source.waveform.table(int(t), 1)[0]))
+
+
+def exfield(t: int, nx: int, ex, hy, *, ca=None, cb=None, source: Optional[LineSource] = None) -> None:
+    """FDTD-form E update ``ex[1:nx] = ca*ex + cb*(hy[i-1]-hy[i])`` then the source of step ``t``."""
+    _require_cuda(ex, hy, ca, cb)
+    s = _src(ex, source, t)
+    check(lib().fdtd1d_exfield(_code(ex), nx, _ptr(ca), _ptr(cb), _ptr(ex), _ptr(hy),
+                               C.byref(s) if s is not None else None, _stream()), "exfield")
+
+
+def dxfield(t: int, nx: int, dx, hy, *, source: Optional[LineSource] = None) -> None:
+    _require_cuda(dx, hy)
+    s = _src(dx, source, t)
+    check(lib().fdtd1d_dxfield(_code(dx), nx, _ptr(dx), _ptr(hy), C.byref(s) if s is not None else None, _stream()),
+          "dxfield")
+
+
+def exfield_flux(nx: int, md: medium, dx, ix, ex, sx=None) -> None:
+    """Flux-form ``ex = nax*(dx-ix[-ncx*sx]); ix += nbx*ex; [sx = ncx*sx + ndx*ex]``."""
+    _require_cuda(dx, ix, ex, sx, md.nax, md.nbx, md.ncx, md.ndx)
+    ms = _lib.Medium1D(md.nax.data_ptr(), md.nbx.data_ptr(),
+                       None if md.ncx is None else md.ncx.data_ptr(), None if md.ndx is None else md.ndx.data_ptr())
+    check(lib().fdtd1d_exfield_flux(_code(ex), nx, C.byref(ms), _ptr(dx), _ptr(ix), _ptr(sx), _ptr(ex), _stream()),
+          "exfield_flux")
+
+
+def hyfield(nx: int, ex, hy, bc=None) -> None:
+    """ABC (when ``bc`` is given) then the H update."""
+    _require_cuda(ex, hy, bc)
+    check(lib().fdtd1d_hyfield(_code(ex), nx, _ptr(ex), _ptr(hy), _ptr(bc), int(bc is not None), _stream()), "hyfield")
+
+
+class Fdtd1D:
+    """One 1D line.  ``form='fdtd'`` (``ca``/``cb``; programs 1_1-1_5) or ``'flux'`` (``nax``..``ndx``; 2_1-2_3)."""
+
+    FIELDS = ("ex", "hy", "dx", "ix", "sx")
+
+    def __init__(self, nx: int, dtype=np.float32, *, form: str = "fdtd", abc: bool = True, source: Optional[LineSource] = None,
+                 ca=None, cb=None, nax=None, nbx=None, ncx=None, ndx=None, device=None, tblock: int = 32):
+        if not torch.cuda.is_available():
+            raise _lib.FdtdError("Fdtd1D needs a CUDA device: the product has no CPU path")
+        lib()
+        if form not in ("fdtd", "flux"):
+            raise ValueError(form)
+        self.nx, self.form, self.abc, self.source = int(nx), form, bool(abc), source
+        self.np_dtype = np.dtype(dtype)
+        self.dtype = _TORCH_DT[self.np_dtype]
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.tblock = int(tblock)
+        self.debye = form == "flux" and ncx is not None
+        self.t = 0
+        up = lambda a: None if a is None else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(a, dtype=self.np_dtype))).to(self.device)
+        self.ca, self.cb = up(ca), up(cb)
+        if form == "flux":
+            one = np.full(nx, 1.0, dtype=self.np_dtype)
+            zero = np.zeros(nx, dtype=self.np_dtype)
+            self.md = medium(up(one if nax is None else nax), up(zero if nbx is None else nbx), up(ncx), up(ndx))
+        else:
+            self.md = None
+        names = self.FIELDS[:2] if form == "fdtd" else (self.FIELDS if self.debye else self.FIELDS[:4])
+        z = lambda n: torch.zeros(n, dtype=self.dtype, device=self.device)
+        self._sets = [{n: z(self.nx) for n in names} for _ in range(2)]
+        self._bc = [z(4), z(4)]
+        self._cur = 0
+        if source is not None and source.field == "dx" and form != "flux":
+            raise _lib.FdtdError("a dx source needs the flux form")
+
+    def tensor(self, name: str) -> torch.Tensor:
+        return self._bc[self._cur] if name == "bc" else self._sets[self._cur][name]
+
+    def get(self, name: str) -> np.ndarray:
+        return self.tensor(name).cpu().numpy()
+
+    def set(self, name: str, host) -> None:
+        self.tensor(name).copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(host, dtype=self.np_dtype))))
+
+    def _problem(self) -> _lib.Problem1D:
+        p = _lib.Problem1D()
+        p.dtype, p.nx = _lib.dtype_code(self.np_dtype), self.nx
+        p.flags = (_lib.ABC if self.abc else 0) | (_lib.FLUX if self.form == "flux" else 0) | (_lib.DEBYE if self.debye else 0)
+        p.ca = None if self.ca is None else self.ca.data_ptr()
+        p.cb = None if self.cb is None else self.cb.data_ptr()
+        if self.md is not None:
+            p.md = _lib.Medium1D(self.md.nax.data_ptr(), self.md.nbx.data_ptr(),
+                                 None if self.md.ncx is None else self.md.ncx.data_ptr(),
+                                 None if self.md.ndx is None else self.md.ndx.data_ptr())
+        for s in range(2):
+            for k, n in enumerate(self.FIELDS):
+                t = self._sets[s].get(n)
+                p.state[s][k] = None if t is None else t.data_ptr()
+            p.bc[s] = self._bc[s].data_ptr()
+        if self.source is None:
+            p.src_field, p.src_index, p.src_hard = 0, -1, 0
+        else:
+            p.src_field = 1 if self.source.field == "dx" else 0
+            p.src_index, p.src_hard = int(self.source.index), int(self.source.hard)
+        return p
+
+    def advance(self, nsteps: int, tblock: Optional[int] = None) -> None:
+        if nsteps <= 0:
+            return
+        src = None
+        if self.source is not None:
+            src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)
+        p = self._problem()
+        out = C.c_int(-1)
+        with torch.cuda.device(self.device):
+            check(lib().fdtd1d_advance(C.byref(p), self._cur, int(nsteps),
+                                       None if src is None else src.ctypes.data_as(C.POINTER(C.c_double)),
+                                       int(tblock or self.tblock), _stream(), C.byref(out)), "fdtd1d_advance")
+        self._cur = out.value
+        self.t += int(nsteps)
+
+    def step(self) -> None:
+        """One step through the reference-named functions in the reference order."""
+        t = self.t + 1
+        s = self._sets[self._cur]
+        bc = self._bc[self._cur] if self.abc else None
+        with torch.cuda.device(self.device):
+            if self.form == "fdtd":
+                exfield(t, self.nx, s["ex"], s["hy"], ca=self.ca, cb=self.cb, source=self.source)
+            else:
+                dxfield(t, self.nx, s["dx"], s["hy"], source=self.source)
+                exfield_flux(self.nx, self.md, s["dx"], s["ix"], s["ex"], s.get("sx"))
+            hyfield(self.nx, s["ex"], s["hy"], bc)
+        self.t = t
+
+    def synchronize(self) -> None:
+        torch.cuda.synchronize(self.device)

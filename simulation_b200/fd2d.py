@@ -1,0 +1,313 @@
+"""2D TM (Dz/Ez/Hx/Hy + PML + TFSF + lossy medium) host side.
+
+Two layers, both calling the sm_100a kernels of ``csrc/libfdtd_b200.so`` through ctypes:
+
+* the reference's module-level step-function protocol, same names and argument order as
+  fd2d/program/fd2d_3_3.py:60-110 / fd2d/python/fd2d_3_4.py:104-170 -- ``ezinct, dfield, inctdz, efield,
+  hxinct, hfield, incthx, incthy`` -- on CUDA tensors the caller owns, mutated in place;
+* :class:`Fdtd2D`, which owns the arrays the reference's ``main()`` allocates (fd2d_3_3.py:132-161) and
+  replaces its ``for t in ...`` loop (:166-174) by ``advance(nsteps)``: the fused, temporally blocked kernel.
+
+torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, surface
+from ._lib import check, lib
+
+_TORCH_DT = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+FIELD_NAMES = ("dz", "ez", "hx", "hy", "ihx", "ihy", "iz")
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+            raise _lib.FdtdError("arguments must be contiguous CUDA tensors (there is no CPU path)")
+
+
+def _code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.float64:
+        return _lib.F64
+    raise _lib.FdtdError(f"unsupported tensor dtype {t.dtype}")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+class pmlayer(NamedTuple):
+    """Device-resident PML vectors, reference field order."""
+    fx1: torch.Tensor
+    fx2: torch.Tensor
+    fx3: torch.Tensor
+    fy1: torch.Tensor
+    fy2: torch.Tensor
+    fy3: torch.Tensor
+    gx2: torch.Tensor
+    gx3: torch.Tensor
+    gy2: torch.Tensor
+    gy3: torch.Tensor
+
+    def as_struct(self) -> _lib.PmlLayer:
+        return _lib.PmlLayer(*[t.data_ptr() for t in self])
+
+
+class medium(NamedTuple):
+    naz: torch.Tensor
+    nbz: Optional[torch.Tensor] = None
+
+
+def pmlparam(nx: int, ny: int, npml: int, dtype=np.float32, device=None) -> pmlayer:
+    """Host-evaluated reference formulas (surface.pmlparam), uploaded."""
+    host = surface.pmlparam(nx, ny, npml, dtype)
+    return pmlayer(*[torch.from_numpy(a).to(device or "cuda") for a in host])
+
+
+@dataclass(frozen=True)
+class PointSource:
+    """``dz[i, j] = waveform(t)`` (hard) or ``+=`` (soft) after the D update (fd2d_3_1.py:48, fd2d_3_2.py:66)."""
+    i: int
+    j: int
+    waveform: object
+    hard: bool = True
+
+
+@dataclass(frozen=True)
+class IncidentWave:
+    """TFSF plane wave: the waveform drives ``ezi[3]`` of the incident line (fd2d_3_3.py:72)."""
+    waveform: object
+
+
+# ------------------------------------------------------------- reference-named step functions (in place)
+def _src_struct(target, index, value, hard):
+    if target is None:
+        return None
+    return _lib.Source(target.data_ptr(), int(index), int(bool(hard)), float(value))
+
+
+def ezinct(ny: int, ezi, hxi, bc) -> None:
+    _require_cuda(ezi, hxi, bc)
+    check(lib().fdtd2d_ezinct(_code(ezi), ny, _ptr(ezi), _ptr(hxi), _ptr(bc), _stream()), "ezinct")
+
+
+def dfield(t: int, nx: int, ny: int, pml: pmlayer, dz, hx, hy, *, source=None, ezi=None) -> None:
+    """D update; then the source sample of step ``t``: an :class:`IncidentWave` sets ``ezi[3]``, a
+    :class:`PointSource` sets / adds to ``dz[i, j]``.  (The reference hard-codes the waveform here.)"""
+    _require_cuda(dz, hx, hy, ezi)
+    src = None
+    if isinstance(source, IncidentWave):
+        src = _src_struct(ezi, 3, source.waveform.table(int(t), 1)[0], True)
+    elif isinstance(source, PointSource):
+        src = _src_struct(dz, source.i * ny + source.j, source.waveform.table(int(t), 1)[0], source.hard)
+    ps = pml.as_struct()
+    check(lib().fdtd2d_dfield(_code(dz), nx, ny, C.byref(ps), _ptr(dz), _ptr(hx), _ptr(hy),
+                              C.byref(src) if src is not None else None, _stream()), "dfield")
+
+
+def inctdz(nx: int, ny: int, npml: int, hxi, dz) -> None:
+    _require_cuda(hxi, dz)
+    check(lib().fdtd2d_inctdz(_code(dz), nx, ny, npml, _ptr(hxi), _ptr(dz), _stream()), "inctdz")
+
+
+def efield(nx: int, ny: int, md, dz, ez, iz=None) -> None:
+    """``md`` is the ``naz`` tensor (programs 3_1-3_3) or a :class:`medium` (3_4, with ``iz``)."""
+    md = md if isinstance(md, medium) else medium(md)
+    _require_cuda(md.naz, md.nbz, dz, ez, iz)
+    ms = _lib.Medium2D(md.naz.data_ptr(), None if md.nbz is None else md.nbz.data_ptr())
+    check(lib().fdtd2d_efield(_code(dz), nx, ny, C.byref(ms), _ptr(dz), _ptr(iz), _ptr(ez), _stream()), "efield")
+
+
+def hxinct(ny: int, ezi, hxi) -> None:
+    _require_cuda(ezi, hxi)
+    check(lib().fdtd2d_hxinct(_code(ezi), ny, _ptr(ezi), _ptr(hxi), _stream()), "hxinct")
+
+
+def hfield(nx: int, ny: int, pml: pmlayer, ez, ihx, ihy, hx, hy) -> None:
+    _require_cuda(ez, ihx, ihy, hx, hy)
+    ps = pml.as_struct()
+    check(lib().fdtd2d_hfield(_code(ez), nx, ny, C.byref(ps), _ptr(ez), _ptr(ihx), _ptr(ihy), _ptr(hx), _ptr(hy),
+                              _stream()), "hfield")
+
+
+def incthx(nx: int, ny: int, npml: int, ezi, hx) -> None:
+    _require_cuda(ezi, hx)
+    check(lib().fdtd2d_incthx(_code(hx), nx, ny, npml, _ptr(ezi), _ptr(hx), _stream()), "incthx")
+
+
+def incthy(nx: int, ny: int, npml: int, ezi, hy) -> None:
+    _require_cuda(ezi, hy)
+    check(lib().fdtd2d_incthy(_code(hy), nx, ny, npml, _ptr(ezi), _ptr(hy), _stream()), "incthy")
+
+
+# ------------------------------------------------------------------------------------------ Fdtd2D
+class Fdtd2D:
+    """Owns the device arrays of one 2D TM problem and advances them.
+
+    ``rows=(lo, hi)`` with ``ghost=g`` makes this object one row slab of a larger grid (see slab.py): the
+    arrays then hold global rows ``[lo-g, hi+g)`` clipped to the grid and ``advance`` may take at most ``g``
+    steps between ghost exchanges.
+    """
+
+    def __init__(self, nx: int, ny: int, npml: int = 0, dtype=np.float32, *, source=None, naz=None, nbz=None,
+                 device=None, tblock: Optional[int] = None, rows=None, ghost: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.FdtdError("Fdtd2D needs a CUDA device: the product has no CPU path")
+        lib()
+        self.nx, self.ny, self.npml = int(nx), int(ny), int(npml)
+        self.np_dtype = np.dtype(dtype)
+        self.dtype = _TORCH_DT[self.np_dtype]
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.source = source
+        self.tfsf = isinstance(source, IncidentWave)
+        self.lossy = nbz is not None
+        self.row_lo, self.row_hi = (0, self.nx) if rows is None else (int(rows[0]), int(rows[1]))
+        self.ghost = int(ghost)
+        self.row_base = max(self.row_lo - self.ghost, 0)
+        self.rows_alloc = min(self.row_hi + self.ghost, self.nx) - self.row_base
+        self.t = 0                                        # steps taken so far (next step is t+1)
+        code = _lib.dtype_code(self.np_dtype)
+        self.tblock = int(tblock) if tblock else lib().fdtd2d_max_tblock(code, self.ny)
+
+        with torch.cuda.device(self.device):
+            shape = (self.rows_alloc, self.ny)
+            names = FIELD_NAMES if self.lossy else FIELD_NAMES[:-1]
+            self._sets = [{n: torch.zeros(shape, dtype=self.dtype, device=self.device) for n in names}
+                          for _ in range(2)]
+            self._cur = 0
+            self.naz = self._to_dev_rows(naz, fill=1.0)
+            self.nbz = self._to_dev_rows(nbz, fill=0.0) if self.lossy else None
+            self.pml = pmlparam(self.nx, self.ny, self.npml, self.np_dtype, self.device)
+            if self.tfsf:
+                z1 = lambda n: torch.zeros(n, dtype=self.dtype, device=self.device)
+                self.ezi, self.hxi, self.bc = z1(self.ny), z1(self.ny), z1(4)
+                self._ezi_hist = z1(max(self.tblock, 1) * self.ny)
+                self._hxi_hist = z1(max(self.tblock, 1) * 2)
+            else:
+                self.ezi = self.hxi = self.bc = self._ezi_hist = self._hxi_hist = None
+
+    # ---- array access -----------------------------------------------------------------------------
+    def _to_dev_rows(self, host, fill):
+        """Upload a coefficient array given for the whole grid, the owned rows, or the stored rows."""
+        if host is None:
+            return torch.full((self.rows_alloc, self.ny), fill, dtype=self.dtype, device=self.device)
+        if isinstance(host, torch.Tensor):
+            host = host.detach().cpu().numpy()
+        a = np.asarray(host, dtype=self.np_dtype)
+        if a.shape == (self.nx, self.ny):
+            a = a[self.row_base:self.row_base + self.rows_alloc]
+        if a.shape != (self.rows_alloc, self.ny):
+            raise _lib.FdtdError(f"coefficient array has shape {a.shape}, expected {(self.rows_alloc, self.ny)}")
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def _owned(self, t: torch.Tensor) -> torch.Tensor:
+        o = self.row_lo - self.row_base
+        return t[o:o + (self.row_hi - self.row_lo)]
+
+    def tensor(self, name: str, stored: bool = False) -> torch.Tensor:
+        """Current device tensor of a field (owned rows; ``stored=True`` includes ghost rows)."""
+        t = self._sets[self._cur][name]
+        return t if stored else self._owned(t)
+
+    def get(self, name: str) -> np.ndarray:
+        if name in ("ezi", "hxi", "bc"):
+            return getattr(self, name).cpu().numpy()
+        return self.tensor(name).cpu().numpy()
+
+    def set(self, name: str, host) -> None:
+        """Upload a field (owned-rows shape or whole-grid shape).  Ghost rows are filled from a whole-grid array."""
+        if name in ("ezi", "hxi", "bc"):
+            getattr(self, name).copy_(torch.as_tensor(np.asarray(host, dtype=self.np_dtype)))
+            return
+        a = np.asarray(host, dtype=self.np_dtype)
+        if a.shape == (self.nx, self.ny) and (self.rows_alloc != self.nx):
+            self.tensor(name, stored=True).copy_(torch.from_numpy(
+                np.ascontiguousarray(a[self.row_base:self.row_base + self.rows_alloc])))
+        else:
+            self.tensor(name).copy_(torch.from_numpy(np.ascontiguousarray(a)))
+
+    # ---- the fused path -----------------------------------------------------------------------------
+    def _problem(self) -> _lib.Problem2D:
+        p = _lib.Problem2D()
+        p.dtype = _lib.dtype_code(self.np_dtype)
+        p.nx, p.ny = self.nx, self.ny
+        p.row_lo, p.row_hi, p.row_base, p.rows_alloc = self.row_lo, self.row_hi, self.row_base, self.rows_alloc
+        p.npml = self.npml
+        p.flags = (_lib.TFSF if self.tfsf else 0) | (_lib.LOSSY if self.lossy else 0)
+        p.pml = self.pml.as_struct()
+        p.md = _lib.Medium2D(self.naz.data_ptr(), None if self.nbz is None else self.nbz.data_ptr())
+        for s in range(2):
+            for k, n in enumerate(FIELD_NAMES):
+                t = self._sets[s].get(n)
+                p.state[s][k] = None if t is None else t.data_ptr()
+        if self.tfsf:
+            p.ezi, p.hxi, p.bc = self.ezi.data_ptr(), self.hxi.data_ptr(), self.bc.data_ptr()
+            p.ezi_hist, p.hxi_hist = self._ezi_hist.data_ptr(), self._hxi_hist.data_ptr()
+        if isinstance(self.source, PointSource):
+            p.src_i, p.src_j, p.src_hard = self.source.i, self.source.j, int(self.source.hard)
+        else:
+            p.src_i, p.src_j, p.src_hard = -1, -1, 1
+        return p
+
+    def advance(self, nsteps: int, tblock: Optional[int] = None) -> None:
+        """``nsteps`` full time steps through the fused, temporally blocked kernel (asynchronous)."""
+        if nsteps <= 0:
+            return
+        tb = int(tblock or self.tblock)
+        if self.tfsf and tb > self.tblock:
+            raise _lib.FdtdError(f"tblock {tb} exceeds the incident-line scratch sized for {self.tblock}")
+        src = None
+        if self.source is not None:
+            src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)
+        p = self._problem()
+        out = C.c_int(-1)
+        with torch.cuda.device(self.device):
+            check(lib().fdtd2d_advance(C.byref(p), self._cur, int(nsteps),
+                                       None if src is None else src.ctypes.data_as(C.POINTER(C.c_double)),
+                                       tb, _stream(), C.byref(out)), "fdtd2d_advance")
+        self._cur = out.value
+        self.t += int(nsteps)
+
+    # ---- the unfused path: the reference loop body, one kernel per reference function ----------------
+    def step(self) -> None:
+        """One time step via the reference-named functions in the reference order (single device only)."""
+        if self.rows_alloc != self.nx:
+            raise _lib.FdtdError("step() runs the whole-grid reference functions; use advance() on a slab")
+        t = self.t + 1
+        nx, ny, n = self.nx, self.ny, self.npml
+        s = self._sets[self._cur]
+        with torch.cuda.device(self.device):
+            if self.tfsf:
+                ezinct(ny, self.ezi, self.hxi, self.bc)
+            dfield(t, nx, ny, self.pml, s["dz"], s["hx"], s["hy"], source=self.source, ezi=self.ezi)
+            if self.tfsf:
+                inctdz(nx, ny, n, self.hxi, s["dz"])
+            efield(nx, ny, medium(self.naz, self.nbz), s["dz"], s["ez"], s.get("iz"))
+            if self.tfsf:
+                hxinct(ny, self.ezi, self.hxi)
+            hfield(nx, ny, self.pml, s["ez"], s["ihx"], s["ihy"], s["hx"], s["hy"])
+            if self.tfsf:
+                incthx(nx, ny, n, self.ezi, s["hx"])
+                incthy(nx, ny, n, self.ezi, s["hy"])
+        self.t = t
+
+    def synchronize(self) -> None:
+        torch.cuda.synchronize(self.device)
+
+    def state_bytes(self) -> int:
+        per = self.rows_alloc * self.ny * self.np_dtype.itemsize
+        return per * (2 * len(self._sets[0]) + 1 + (1 if self.lossy else 0))

@@ -1,0 +1,152 @@
+"""Setup surface kept from the reference programs: source waveforms, PML vectors and medium coefficient
+arrays, evaluated on the host in float64 exactly as the reference does and rounded on store, so the
+arrays handed to the kernels are bit-identical to the reference's.
+
+Reference lines: waveforms fd1d/program/fd1d_1_1.py:27-28, fd1d_1_4.py:30-32; pmlparam
+fd2d/program/fd2d_3_3.py:113-122 (+ defaults :147-158); 1D media fd1d_1_3.py:31-34, fd1d_1_5.py:37-44,
+fd1d_2_1.py:64-72, fd1d_2_3.py:97-109; cylinder fd2d/python/fd2d_3_4.py:173-194.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import NamedTuple, Optional
+
+import numpy as np
+
+EPS0 = 8.854e-12          # F/m, the reference's literal
+DS = 0.01                 # spatial step (m)
+DT = DS / 6e8             # time step (s): Courant number 0.5
+
+
+def _steps(t_first: int, n: int) -> np.ndarray:
+    """Step counters as the reference loop produces them (np.int32)."""
+    return np.arange(t_first, t_first + n).astype(np.int32)
+
+
+@dataclass(frozen=True)
+class Gaussian:
+    """``exp(-0.5*((t - t0)/spread)**2)``"""
+    t0: int
+    spread: float
+
+    def table(self, t_first: int, n: int) -> np.ndarray:
+        t = _steps(t_first, n)
+        return np.array([np.exp(-0.5 * ((k - self.t0) / self.spread) ** 2) for k in t], dtype=np.float64)
+
+
+@dataclass(frozen=True)
+class Sinusoid:
+    """``sin(2*pi*freq*dt*t)`` with ``dt = ds/6e8``"""
+    freq: float
+    ds: float = DS
+
+    def table(self, t_first: int, n: int) -> np.ndarray:
+        dt = self.ds / 6e8
+        t = _steps(t_first, n)
+        return np.array([np.sin(2 * np.pi * self.freq * dt * k) for k in t], dtype=np.float64)
+
+
+@dataclass(frozen=True)
+class Samples:
+    """An explicit float64 waveform; entry k is the sample of step k+1."""
+    values: np.ndarray
+
+    def table(self, t_first: int, n: int) -> np.ndarray:
+        v = np.asarray(self.values, dtype=np.float64)
+        if t_first - 1 + n > v.size:
+            raise ValueError("waveform table too short")
+        return v[t_first - 1:t_first - 1 + n].copy()
+
+
+class PmlVectors(NamedTuple):
+    """Host arrays in the reference's ``pmlayer`` order."""
+    fx1: np.ndarray
+    fx2: np.ndarray
+    fx3: np.ndarray
+    fy1: np.ndarray
+    fy2: np.ndarray
+    fy3: np.ndarray
+    gx2: np.ndarray
+    gx3: np.ndarray
+    gy2: np.ndarray
+    gy3: np.ndarray
+
+
+def pmlparam(nx: int, ny: int, npml: int, dtype=np.float32) -> PmlVectors:
+    """The ten 1D PML vectors; ``npml = 0`` returns the identity set (free space)."""
+    if npml < 0 or 2 * npml > min(nx, ny):
+        raise ValueError(f"npml={npml} does not fit a {nx}x{ny} grid")
+    one = lambda n: np.full(n, 1.0, dtype=dtype)
+    p = PmlVectors(np.full(nx, 0.0, dtype=dtype), one(nx), one(nx),
+                   np.full(ny, 0.0, dtype=dtype), one(ny), one(ny),
+                   one(nx), one(nx), one(ny), one(ny))
+    for n in range(npml):
+        xm = 0.33 * ((npml - n) / npml) ** 3
+        xn = 0.33 * ((npml - n - 0.5) / npml) ** 3
+        for f1, f2, f3, g2, g3, size in ((p.fx1, p.fx2, p.fx3, p.gx2, p.gx3, nx),
+                                         (p.fy1, p.fy2, p.fy3, p.gy2, p.gy3, ny)):
+            m = size - 2 - n                      # H lives on the half cell: mirrored about N-2
+            f1[n] = f1[m] = xn
+            f2[n] = f2[m] = 1 / (1 + xn)
+            f3[n] = f3[m] = (1 - xn) / (1 + xn)
+            g2[n] = g2[m + 1] = 1 / (1 + xm)
+            g3[n] = g3[m + 1] = (1 - xm) / (1 + xm)
+    return p
+
+
+# ------------------------------------------------------------------------------------ 1D media
+def dielectric_fdtd(nx: int, dt: float, epsr: float, sigma: float = 0.0, dtype=np.float32,
+                    start: Optional[int] = None, stop: Optional[int] = None):
+    """``ca, cb`` of the FDTD form: half space from ``nx//2`` by default, or a slab ``[start, stop)``."""
+    start = nx // 2 if start is None else start
+    ca = 1.0 + np.zeros(nx, dtype=dtype)
+    cb = 0.5 + np.zeros(nx, dtype=dtype)
+    epsf = dt * sigma / (2 * EPS0 * epsr)
+    ca[start:stop] = (1 - epsf) / (1 + epsf)
+    cb[start:stop] = 0.5 / (epsr * (1 + epsf))
+    return ca, cb
+
+
+def dielectric_flux(nx: int, dt: float, epsr: float, sigma: float, dtype=np.float32, chi: Optional[float] = None,
+                    tau: Optional[float] = None, start: Optional[int] = None, stop: Optional[int] = None):
+    """``nax, nbx, ncx, ndx`` of the flux form; ``chi``/``tau`` add the Debye term."""
+    start = nx // 2 if start is None else start
+    nax = np.full(nx, 1.0, dtype=dtype)
+    nbx, ncx, ndx = (np.full(nx, 0.0, dtype=dtype) for _ in range(3))
+    nbx[start:stop] = sigma * dt / EPS0
+    if chi is None:
+        nax[start:stop] = 1 / (epsr + sigma * dt / EPS0)
+    else:
+        nax[start:stop] = 1 / (epsr + sigma * dt / EPS0 + chi * dt / tau)
+        ncx[start:stop] = np.exp(-dt / tau)
+        ndx[start:stop] = chi * dt / tau
+    return nax, nbx, ncx, ndx
+
+
+# ------------------------------------------------------------------------------------ 2D media
+def dielectric_cylinder(nx: int, ny: int, npml: int, rgrid: int, dt: float, epsr: float, sigma: float,
+                        dtype=np.float32, rows: Optional[slice] = None):
+    """``naz, nbz`` of a lossy dielectric cylinder centred at (nx/2-1, ny/2-1), averaged over 3x3
+    sub-cells.  Row-blocked so a 32768-row grid never materialises more than a band of float64 temporaries.
+    ``rows`` restricts the output to a slab (multi-GPU setup)."""
+    r0, r1 = (0, nx) if rows is None else (rows.start, rows.stop)
+    naz = np.full((r1 - r0, ny), 1.0, dtype=dtype)
+    nbz = np.full((r1 - r0, ny), 0.0, dtype=dtype)
+    jj = np.arange(npml, ny - npml, dtype=np.float64)[None, :]
+    lo, hi = max(r0, npml), min(r1, nx - npml)
+    band = 256
+    for b0 in range(lo, hi, band):
+        b1 = min(b0 + band, hi)
+        ii = np.arange(b0, b1, dtype=np.float64)[:, None]
+        epsn = np.full((b1 - b0, jj.shape[1]), 1.0)
+        cond = np.zeros_like(epsn)
+        for m in range(-1, 2):
+            for n in range(-1, 2):
+                x = nx / 2 - 1 - ii + m / 3
+                y = ny / 2 - 1 - jj + n / 3
+                inside = np.sqrt(x ** 2 + y ** 2) <= rgrid
+                epsn = np.where(inside, epsn + (epsr - 1) / 9, epsn)
+                cond = np.where(inside, cond + sigma / 9, cond)
+        naz[b0 - r0:b1 - r0, npml:ny - npml] = 1 / (epsn + cond * dt / EPS0)
+        nbz[b0 - r0:b1 - r0, npml:ny - npml] = cond * dt / EPS0
+    return naz, nbz

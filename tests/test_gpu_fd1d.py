@@ -1,0 +1,125 @@
+"""GPU parity tests of the 1D Ex/Hy path (reference-named functions and the fused time-blocked advance)
+against the numpy oracle and the reference-made goldens.  Bar: bit-exact, fp32 and fp64."""
+import numpy as np
+import pytest
+
+from oracle import fdtd_oracle as orc
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _sim_for(prog, nx, dtype, **kw):
+    from simulation_b200 import fd1d, surface
+    S, DT = fd1d.LineSource, surface.DT
+    if prog in ("1_1", "1_2"):
+        return fd1d.Fdtd1D(nx, dtype, abc=(prog == "1_2"), source=S(nx // 2, surface.Gaussian(40, 12.0), hard=True), **kw)
+    if prog in ("1_3", "1_4", "1_5"):
+        ca, cb = surface.dielectric_fdtd(nx, DT, 4.0, 0.04 if prog == "1_5" else 0.0, dtype)
+        w = surface.Gaussian(40, 12.0) if prog == "1_3" else surface.Sinusoid(700e6)
+        return fd1d.Fdtd1D(nx, dtype, source=S(1, w), ca=(ca if prog == "1_5" else None), cb=cb, **kw)
+    if prog == "2_1":
+        nax, nbx, _, _ = surface.dielectric_flux(nx, DT, 4.0, 0.04, dtype)
+        return fd1d.Fdtd1D(nx, dtype, form="flux", source=S(1, surface.Sinusoid(700e6), field="dx"), nax=nax, nbx=nbx, **kw)
+    if prog == "2_2":
+        nax, nbx, _, _ = surface.dielectric_flux(nx, DT, 4.0, 0.0, dtype)
+        return fd1d.Fdtd1D(nx, dtype, form="flux", source=S(1, surface.Gaussian(50, 10.0), field="dx"), nax=nax, nbx=nbx, **kw)
+    if prog == "2_3":
+        nax, nbx, ncx, ndx = surface.dielectric_flux(nx, DT, 2.0, 0.01, dtype, chi=2.0, tau=0.001e-6)
+        return fd1d.Fdtd1D(nx, dtype, form="flux", source=S(1, surface.Gaussian(50, 10.0), field="dx"),
+                           nax=nax, nbx=nbx, ncx=ncx, ndx=ndx, **kw)
+    raise KeyError(prog)
+
+
+def _oracle(prog, nx, ns, dtype):
+    p, src = cases.line_program(prog, nx, ns, dtype)
+    p.freqs = None                       # running DFT is a next-tier row; fields do not depend on it
+    orc.advance_1d(p, src)
+    return p
+
+
+def _assert_same(sim, p):
+    names = ["ex", "hy"] + (["dx", "ix"] if p.form == "flux" else [])
+    if p.form == "flux" and sim.debye:
+        names.append("sx")
+    if p.abc:
+        names.append("bc")
+    for n in names:
+        got, want = sim.get(n), getattr(p, n)
+        if got.tobytes() != want.tobytes():
+            bad = np.argwhere(got != want)
+            raise AssertionError(f"{n}: {len(bad)} cells differ, first {bad[:5].ravel().tolist()}")
+
+
+ALL = ["1_1", "1_2", "1_3", "1_4", "1_5", "2_1", "2_2", "2_3"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("prog", ALL)
+def test_step_functions_match_oracle(prog, dtype):
+    nx, ns = 300, 700
+    sim = _sim_for(prog, nx, dtype)
+    for _ in range(ns):
+        sim.step()
+    _assert_same(sim, _oracle(prog, nx, ns, dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("tblock", [1, 7, 32, 64])
+@pytest.mark.parametrize("prog", ALL)
+def test_advance_matches_oracle(prog, tblock, dtype):
+    nx, ns = 5000, 1203                  # three CTAs, ragged last segment, ns not a multiple of tblock
+    sim = _sim_for(prog, nx, dtype)
+    sim.advance(ns, tblock=tblock)
+    _assert_same(sim, _oracle(prog, nx, ns, dtype))
+
+
+@pytest.mark.parametrize("prog", ALL)
+def test_reference_main_goldens_fp64(prog):
+    nx, ns = cases.LINE_MAIN[prog]
+    sim = _sim_for(prog, nx, np.float64)
+    sim.advance(ns)
+    assert sim.get("ex").tobytes() == cases.golden(f"main_fd1d_{prog}")["ex"].tobytes()
+
+
+@pytest.mark.parametrize("prog", ALL)
+def test_reference_twin_goldens_fp32(prog):
+    g = cases.golden(f"twin_fd1d_{prog}")
+    sim = _sim_for(prog, int(g["nx"]), np.float32)
+    sim.advance(int(g["ns"]))
+    assert sim.get("ex").tobytes() == g["ex"].tobytes()
+
+
+def test_baseline_config_1_free_space_pulse():
+    """BASELINE config 1: ke=200, 100 steps, hard Gaussian in the middle (fd1d_1_1 rule), fp64."""
+    sim = _sim_for("1_1", 200, np.float64)
+    sim.advance(100)
+    _assert_same(sim, _oracle("1_1", 200, 100, np.float64))
+
+
+def test_baseline_config_2_long_lossy_line():
+    """BASELINE config 2 shape: 1e6 cells, lossy slab, sinusoid, ABC -- 600 steps vs the oracle, and the
+    fused path against the unfused reference-named functions."""
+    from simulation_b200 import fd1d, surface
+    nx, ns = 1_000_000, 600
+    ca, cb = surface.dielectric_fdtd(nx, surface.DT, 4.0, 0.04, np.float32, start=nx // 2, stop=nx // 2 + nx // 4)
+    mk = lambda: fd1d.Fdtd1D(nx, np.float32, source=fd1d.LineSource(1, surface.Sinusoid(700e6)), ca=ca, cb=cb)
+    a, b = mk(), mk()
+    a.advance(ns, tblock=64)
+    for _ in range(ns):
+        b.step()
+    oca, ocb = orc.lossy_halfspace_fdtd(nx, cases.DT, 4.0, 0.04, np.float32, start=nx // 2, stop=nx // 2 + nx // 4)
+    p = orc.Line1D(nx, np.float32, ca=oca, cb=ocb)
+    orc.advance_1d(p, orc.source_table("sine", ns, freq=700e6))
+    for n in ("ex", "hy", "bc"):
+        assert a.get(n).tobytes() == getattr(p, n).tobytes(), n
+        assert b.get(n).tobytes() == getattr(p, n).tobytes(), n
+
+
+def test_tiny_lines():
+    for nx in (3, 4, 17):
+        sim = _sim_for("1_2", nx, np.float64)
+        sim.advance(40, tblock=5)
+        _assert_same(sim, _oracle("1_2", nx, 40, np.float64))

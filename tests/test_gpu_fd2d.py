@@ -1,0 +1,243 @@
+"""GPU parity tests of the 2D TM path: the CUDA kernels (through the ctypes C ABI) against the numpy
+oracle on identical inputs.  Bar: BIT-EXACT for every state array, fp32 and fp64 (the kernels reproduce
+the reference's rounding sequence), which is far inside the north star's 1e-5-of-peak tolerance."""
+import numpy as np
+import pytest
+
+from oracle import fdtd_oracle as orc
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _sim_for(prog, nx, ny, dtype, npml=8, naz=None, radius=0.15, **kw):
+    from simulation_b200 import fd2d, surface
+    if prog == "3_1":
+        src = fd2d.PointSource(nx // 2, ny // 2, surface.Gaussian(20, 6.0), hard=True)
+        return fd2d.Fdtd2D(nx, ny, 0, dtype, source=src, naz=naz, **kw)
+    if prog == "3_2":
+        src = fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6), hard=True)
+        return fd2d.Fdtd2D(nx, ny, npml, dtype, source=src, naz=naz, **kw)
+    if prog == "3_3":
+        return fd2d.Fdtd2D(nx, ny, npml, dtype, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=naz, **kw)
+    if prog == "3_4":
+        rgrid = int(radius / 0.01 - 1)
+        mnaz, mnbz = surface.dielectric_cylinder(nx, ny, npml, rgrid, surface.DT, 30.0, 0.30, dtype)
+        return fd2d.Fdtd2D(nx, ny, npml, dtype, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)),
+                           naz=mnaz, nbz=mnbz, **kw)
+    raise KeyError(prog)
+
+
+def _fields(prog):
+    f = ["dz", "ez", "hx", "hy", "ihx", "ihy"]
+    if prog == "3_4":
+        f.append("iz")
+    if prog in ("3_3", "3_4"):
+        f += ["ezi", "hxi", "bc"]
+    return f
+
+
+def _assert_same(sim, g, prog, exact_zero_sign=True):
+    for name in _fields(prog):
+        got, want = sim.get(name), getattr(g, name)
+        assert got.dtype == want.dtype and got.shape == want.shape, name
+        if exact_zero_sign:
+            ok = got.tobytes() == want.tobytes()
+        else:
+            ok = np.array_equal(got, want)
+        if not ok:
+            bad = np.argwhere(got != want)
+            raise AssertionError(f"{name}: {len(bad)} cells differ, first {bad[:4].tolist()}, "
+                                 f"max|d|={np.abs(got.astype(np.float64) - want).max():.3e}")
+
+
+# ------------------------------------------------------------------ reference-named (unfused) functions
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("prog,nx,ny,npml,ns", [("3_1", 40, 56, 0, 60), ("3_2", 56, 72, 8, 90),
+                                                ("3_3", 64, 48, 7, 100), ("3_4", 60, 72, 8, 90)])
+def test_step_functions_match_oracle(prog, nx, ny, npml, ns, dtype):
+    sim = _sim_for(prog, nx, ny, dtype, npml=npml, radius=0.12)
+    for _ in range(ns):
+        sim.step()
+    g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=0.12, dft=False)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, prog)
+
+
+# ------------------------------------------------------------------ fused, temporally blocked advance
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("tblock", [1, 2, 3, 4])
+@pytest.mark.parametrize("prog,nx,ny,npml,ns", [("3_2", 56, 72, 8, 61), ("3_3", 64, 48, 7, 75),
+                                                ("3_4", 60, 72, 8, 66), ("3_1", 40, 56, 0, 50)])
+def test_advance_matches_oracle(prog, nx, ny, npml, ns, tblock, dtype):
+    sim = _sim_for(prog, nx, ny, dtype, npml=npml, radius=0.12, tblock=4)
+    sim.advance(ns, tblock=tblock)
+    g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=0.12, dft=False)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, prog)
+
+
+@pytest.mark.parametrize("force_v", [1, 2, 4])
+@pytest.mark.parametrize("chunk_rows", [0, 5, 16])
+@pytest.mark.parametrize("prog,nx,ny,npml", [("3_3", 150, 284, 9), ("3_2", 131, 260, 8), ("3_4", 97, 300, 8)])
+def test_advance_vector_widths_and_chunking(prog, nx, ny, npml, force_v, chunk_rows):
+    """Wide enough for several strips per vector width, several row chunks, ragged edges."""
+    from simulation_b200 import _lib
+    ns = 45
+    _lib.lib().fdtd2d_tune(force_v, chunk_rows)
+    try:
+        sim = _sim_for(prog, nx, ny, np.float32, npml=npml, radius=0.3)
+        sim.advance(ns, tblock=4)
+        sim.synchronize()
+    finally:
+        _lib.lib().fdtd2d_tune(0, 0)
+    g, src = cases.grid_program(prog, nx, ny, ns, np.float32, npml=npml, radius=0.3, dft=False)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, prog)
+
+
+@pytest.mark.parametrize("ny", [61, 62, 63, 130])
+def test_advance_odd_widths_fall_back_to_narrow_vectors(ny):
+    nx, npml, ns = 50, 6, 40
+    sim = _sim_for("3_3", nx, ny, np.float32, npml=npml)
+    sim.advance(ns)
+    g, src = cases.grid_program("3_3", nx, ny, ns, np.float32, npml=npml)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, "3_3")
+
+
+def test_advance_split_calls_and_mixed_with_step():
+    """advance(a); step(); advance(b) == oracle(a+1+b): the step counter / source table stay aligned."""
+    nx, ny, npml = 70, 90, 8
+    sim = _sim_for("3_3", nx, ny, np.float64, npml=npml)
+    sim.advance(23)
+    sim.step()
+    sim.advance(30, tblock=3)
+    g, src = cases.grid_program("3_3", nx, ny, 54, np.float64, npml=npml)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, "3_3")
+
+
+def test_advance_nonzero_initial_state_and_random_medium():
+    """Uploaded (non-zero, including row 0 / column 0 / last row / last column) state and a seeded random naz."""
+    rng = np.random.default_rng(7)
+    nx, ny, npml, ns = 66, 140, 8, 33
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    sim = _sim_for("3_2", nx, ny, np.float32, npml=npml, naz=naz)
+    g, src = cases.grid_program("3_2", nx, ny, ns, np.float32, npml=npml, naz=naz.copy())
+    for name in ("dz", "hx", "hy", "ihx", "ihy"):
+        a = rng.standard_normal((nx, ny)).astype(np.float32)
+        sim.set(name, a)
+        getattr(g, name)[...] = a
+    sim.advance(ns)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, "3_2")
+
+
+# ------------------------------------------------------------------ committed goldens (made by the reference)
+@pytest.mark.parametrize("tag,dtype", [("f32", np.float32), ("f64", np.float64)])
+@pytest.mark.parametrize("prog", ["3_1", "3_2", "3_3"])
+def test_advance_matches_reference_goldens(prog, tag, dtype):
+    ref = cases.golden(f"drive_{prog}_{tag}")
+    nx, ny, ns = int(ref["nx"]), int(ref["ny"]), int(ref["ns"])
+    npml = int(ref["npml"]) if "npml" in ref else 0
+    sim = _sim_for(prog, nx, ny, dtype, npml=npml)
+    sim.advance(ns)
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy", "ezi", "hxi", "bc"):
+        if name in ref and (name not in ("ihx", "ihy") or prog != "3_1"):
+            got = sim.get(name)
+            if prog == "3_1":
+                assert np.array_equal(got, ref[name]), name       # identity-PML form: +-0 may differ in sign
+            else:
+                assert got.tobytes() == ref[name].tobytes(), name
+
+
+def test_reference_main_3_2_and_3_3_fp64():
+    """BASELINE config 3: the reference program as shipped (60x60, fp64)."""
+    for prog in ("3_2", "3_3"):
+        nx, ny, ns = cases.GRID_MAIN[prog]
+        sim = _sim_for(prog, nx, ny, np.float64, npml=8)
+        sim.advance(ns)
+        assert sim.get("ez").tobytes() == cases.golden(f"main_fd2d_{prog}")["ez"].tobytes()
+
+
+def test_numba_program_3_4_golden_within_tolerance():
+    ref = cases.golden("drive_3_4_f64")
+    nx, ny, ns, npml = (int(ref[k]) for k in ("nx", "ny", "ns", "npml"))
+    sim = _sim_for("3_4", nx, ny, np.float64, npml=npml, radius=0.12)
+    sim.advance(ns)
+    peak = np.abs(ref["ez"]).max()
+    for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy"):
+        scale = max(np.abs(ref[name]).max(), peak)
+        assert np.abs(sim.get(name) - ref[name]).max() <= 1e-12 * scale, name     # numba fastmath is not bit-stable
+
+
+# ------------------------------------------------------------------ medium and large grids
+def test_medium_grid_vs_oracle_fp32():
+    nx, ny, npml, ns = 384, 640, 40, 160
+    sim = _sim_for("3_3", nx, ny, np.float32, npml=npml)
+    sim.advance(ns)
+    g, src = cases.grid_program("3_3", nx, ny, ns, np.float32, npml=npml)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, "3_3")
+    # north-star tolerance against the fp64 oracle: <= 1e-5 of peak |Ez|
+    g64, src64 = cases.grid_program("3_3", nx, ny, ns, np.float64, npml=npml)
+    orc.advance_2d(g64, src64)
+    peak = np.abs(g64.ez).max()
+    assert np.abs(sim.get("ez").astype(np.float64) - g64.ez).max() <= 1e-5 * peak
+
+
+@pytest.mark.parametrize("n", [4096])
+def test_large_grid_fused_equals_unfused_bitwise(n):
+    """Size-independent property at a grid the CPU oracle cannot reach: T-blocked == single-step fused ==
+    one-kernel-per-reference-function, bit for bit, on every array."""
+    ns = 24
+    a = _sim_for("3_3", n, n, np.float32, npml=80)
+    b = _sim_for("3_3", n, n, np.float32, npml=80)
+    a.advance(ns, tblock=4)
+    b.advance(ns, tblock=1)
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+    del b
+    c = _sim_for("3_3", n, n, np.float32, npml=80)
+    for _ in range(ns):
+        c.step()
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(a.tensor(name), c.tensor(name)), name
+    assert float(a.tensor("ez").abs().max()) > 0.5          # the pulse is really there
+
+
+def test_full_size_linearity_32768():
+    """BASELINE config 5 size (32768^2 fp32): scaling the source by 2 scales every field by exactly 2
+    (power-of-two scaling commutes with every rounding) -- a bitwise property that needs no oracle."""
+    from simulation_b200 import fd2d, surface
+    free, _ = torch.cuda.mem_get_info()
+    n = 32768
+    need = 2 * (13 * n * n * 4)
+    if free < need * 1.05:
+        pytest.skip(f"needs {need / 2**30:.0f} GiB of device memory")
+    ns = 8
+    w = surface.Sinusoid(1500e6)
+    tab = w.table(1, ns)
+    a = fd2d.Fdtd2D(n, n, 80, np.float32, source=fd2d.PointSource(n // 2 - 5, n // 2 - 5, surface.Samples(tab)))
+    b = fd2d.Fdtd2D(n, n, 80, np.float32, source=fd2d.PointSource(n // 2 - 5, n // 2 - 5, surface.Samples(2.0 * tab)))
+    a.advance(ns)
+    b.advance(ns)
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(a.tensor(name) * 2.0, b.tensor(name)), name
+    assert float(a.tensor("ez").abs().max()) > 0.0
+
+
+# ------------------------------------------------------------------ error behaviour of the boundary
+def test_errors_are_reported_not_swallowed():
+    from simulation_b200 import _lib, fd2d, surface
+    sim = _sim_for("3_3", 64, 64, np.float32, npml=8)
+    with pytest.raises(_lib.FdtdError):
+        sim.advance(4, tblock=9)                                 # tblock out of range
+    with pytest.raises(_lib.FdtdError):
+        fd2d.inctdz(64, 64, 40, sim.hxi, sim.tensor("dz"))       # 2*npml > nx
+    with pytest.raises(_lib.FdtdError):
+        fd2d.hfield(64, 64, sim.pml, sim.tensor("ez").cpu(), sim.tensor("ihx"), sim.tensor("ihy"),
+                    sim.tensor("hx"), sim.tensor("hy"))           # host tensor: no CPU path
