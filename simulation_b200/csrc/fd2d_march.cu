@@ -18,7 +18,7 @@
 namespace {
 
 constexpr int TMAX = 8;          // deepest pipeline instantiated
-constexpr int WARPS = 4;         // warps per CTA (independent; only for L1 locality of neighbouring strips)
+constexpr int MAX_WARPS = 8;     // warps per CTA are independent; a CTA only groups neighbouring strips for L1 locality
 
 template <typename real>
 struct MarchParams {
@@ -108,7 +108,7 @@ __device__ __forceinline__ void load_row(const MarchParams<real> &p, int g, bool
 }
 
 template <typename real, int V, int T, bool LOSSY>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(MAX_WARPS * 32)
 k_march(const __grid_constant__ MarchParams<real> p) {
     constexpr int W = 32 * V;            // columns per strip
     constexpr int USE = W - 2 * T;       // columns a strip produces
@@ -116,7 +116,7 @@ k_march(const __grid_constant__ MarchParams<real> p) {
     const real half = real(0.5);
 
     const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= p.nstrips * p.nchunks) return;
     const int strip = w % p.nstrips;
     const int chunk = w / p.nstrips;
@@ -320,12 +320,17 @@ __global__ void k_incident_line(int ny, int npml, int T, real *ezi, real *hxi, r
     }
 }
 
+int g_force_v = 0;          // test / tuning hooks (fdtd2d_tune)
+int g_chunk_rows = 0;
+int g_warps = 0;
+
 template <typename real, int V, int T>
 int launch_march(const MarchParams<real> &mp, bool lossy, cudaStream_t st) {
     const int nw = mp.nstrips * mp.nchunks;
-    const int grid = (nw + WARPS - 1) / WARPS;
-    if (lossy) k_march<real, V, T, true><<<grid, WARPS * 32, 0, st>>>(mp);
-    else       k_march<real, V, T, false><<<grid, WARPS * 32, 0, st>>>(mp);
+    const int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : 4;
+    const int grid = (nw + warps - 1) / warps;
+    if (lossy) k_march<real, V, T, true><<<grid, warps * 32, 0, st>>>(mp);
+    else       k_march<real, V, T, false><<<grid, warps * 32, 0, st>>>(mp);
     FDTD_LAUNCH_CHECK("k_march");
     return FDTD_OK;
 }
@@ -350,8 +355,6 @@ template <> int pick_v<float>(int ny, int T) {
 }
 template <> int pick_v<double>(int ny, int T) { return (ny % 2 == 0 && T % 2 == 0) ? 2 : 1; }
 
-int g_force_v = 0;          // test / tuning hooks (fdtd2d_tune)
-int g_chunk_rows = 0;
 
 template <typename real>
 int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int tblock, cudaStream_t st,
@@ -437,9 +440,10 @@ int fdtd2d_max_tblock(int dtype, int ny) {
 }
 
 // tuning / test hook (not part of the reference-facing surface): force the vector width and rows per chunk
-int fdtd2d_tune(int force_v, int chunk_rows) {
+int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta) {
     g_force_v = force_v;
     g_chunk_rows = chunk_rows;
+    g_warps = warps_per_cta;
     return FDTD_OK;
 }
 

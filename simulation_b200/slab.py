@@ -1,0 +1,129 @@
+"""Row-slab decomposition of one 2D TM grid over the GPUs of a node: one process per GPU
+(``torch.distributed``), rank r owns a contiguous band of rows and keeps ``ghost`` extra rows of its
+neighbours on each side.
+
+The reference has no multi-GPU path; this is the slab protocol of the north star built on
+the fused kernel: a time block of ``ghost`` steps needs NO communication (the kernel recomputes the
+shrinking ghost band), then each rank refreshes its ghost rows from its neighbours' freshly computed owned
+rows -- one grouped NCCL send/recv per neighbour per block, ``5 * ghost`` rows each way (dz, hx, hy, ihx,
+ihy; plus iz for a lossy medium; ez is recomputed, naz / nbz are static).  The stencil reaches one row per
+step (hy[i-1] in dfield, ez[i+1] in hfield), so ``ghost`` rows stay valid for ``ghost`` steps.
+
+Result: every rank's owned rows are bit-identical to the same rows of a single-device run.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+EXCHANGED = ("dz", "hx", "hy", "ihx", "ihy", "iz")
+
+
+def partition(nx: int, world: int, rank: int) -> tuple:
+    """Rows [lo, hi) of rank ``rank``: contiguous, sizes differ by at most one row."""
+    base, extra = divmod(nx, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class SlabFdtd2D:
+    """One rank's slab.  Same ``advance`` / ``tensor`` / ``get`` surface as :class:`fd2d.Fdtd2D`.
+
+    ``engine_factory(nx, ny, npml, dtype, rows=(lo, hi), ghost=g, **kw)`` builds the per-rank stepper;
+    the default is the CUDA :class:`fd2d.Fdtd2D` (tests inject a CPU stand-in to exercise the exchange
+    logic under gloo without a GPU)."""
+
+    def __init__(self, nx: int, ny: int, npml: int = 0, dtype=np.float32, *, ghost: Optional[int] = None,
+                 tblock: int = 4, group=None, engine_factory: Optional[Callable] = None, **engine_kw):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nx, self.ny = int(nx), int(ny)
+        self.ghost = int(ghost if ghost is not None else tblock)
+        self.row_lo, self.row_hi = partition(self.nx, self.world, self.rank)
+        if self.world > 1 and (self.row_hi - self.row_lo) < self.ghost:
+            raise ValueError(f"slab of {self.row_hi - self.row_lo} rows is thinner than the ghost band {self.ghost}")
+        if engine_factory is None:
+            from .fd2d import Fdtd2D
+            engine_factory = Fdtd2D
+        self.engine = engine_factory(self.nx, self.ny, npml, dtype, rows=(self.row_lo, self.row_hi),
+                                     ghost=self.ghost if self.world > 1 else 0, tblock=tblock, **engine_kw)
+        self.row_base = self.engine.row_base
+        self.up = self.rank - 1 if self.rank > 0 else None            # neighbour owning the rows above
+        self.down = self.rank + 1 if self.rank < self.world - 1 else None
+        self.exchanges = 0
+        self._ghost_dirty = False
+
+    # ---- delegation ---------------------------------------------------------------------------------
+    @property
+    def t(self):
+        return self.engine.t
+
+    @t.setter
+    def t(self, v):
+        self.engine.t = v
+
+    @property
+    def naz(self):
+        return self.engine.naz
+
+    def tensor(self, name, stored=False):
+        return self.engine.tensor(name, stored=stored)
+
+    def get(self, name):
+        return self.engine.get(name)
+
+    def set(self, name, host):
+        self.engine.set(name, host)
+        self._ghost_dirty = True          # ghost rows are refreshed before the next block
+
+    def synchronize(self):
+        self.engine.synchronize()
+
+    # ---- ghost exchange ------------------------------------------------------------------------------
+    def _names(self):
+        return [n for n in EXCHANGED if n != "iz" or getattr(self.engine, "lossy", False)]
+
+    def exchange_ghosts(self) -> None:
+        """Refresh both ghost bands from the neighbours' owned rows (all fields, one grouped batch)."""
+        if self.world == 1:
+            return
+        g, ops, keep = self.ghost, [], []
+        o = self.row_lo - self.row_base                     # array row of the first owned row
+        n_own = self.row_hi - self.row_lo
+        for name in self._names():
+            t = self.engine.tensor(name, stored=True)
+            if self.up is not None:
+                ops.append(dist.P2POp(dist.isend, t[o:o + g], self.up, self.group))
+                ops.append(dist.P2POp(dist.irecv, t[o - g:o], self.up, self.group))
+            if self.down is not None:
+                ops.append(dist.P2POp(dist.isend, t[o + n_own - g:o + n_own], self.down, self.group))
+                ops.append(dist.P2POp(dist.irecv, t[o + n_own:o + n_own + g], self.down, self.group))
+            keep.append(t)
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        self.exchanges += 1
+
+    def advance(self, nsteps: int, tblock: Optional[int] = None) -> None:
+        """``nsteps`` steps: blocks of at most ``ghost`` steps, a ghost exchange after every block."""
+        left = int(nsteps)
+        if self._ghost_dirty:
+            self.exchange_ghosts()
+            self._ghost_dirty = False
+        while left > 0:
+            n = min(left, self.ghost) if self.world > 1 else left
+            self.engine.advance(n, tblock=tblock)
+            left -= n
+            self.exchange_ghosts()
+
+    def gather(self, name: str) -> Optional[np.ndarray]:
+        """Whole-grid field on rank 0 (tests / small grids only)."""
+        mine = self.engine.tensor(name).contiguous()
+        if self.world == 1:
+            return mine.cpu().numpy()
+        parts = [None] * self.world
+        dist.all_gather_object(parts, mine.cpu().numpy(), group=self.group)
+        return np.concatenate(parts, axis=0) if self.rank == 0 else None

@@ -86,13 +86,13 @@ def test_advance_vector_widths_and_chunking(prog, nx, ny, npml, force_v, chunk_r
     """Wide enough for several strips per vector width, several row chunks, ragged edges."""
     from simulation_b200 import _lib
     ns = 45
-    _lib.lib().fdtd2d_tune(force_v, chunk_rows)
+    _lib.lib().fdtd2d_tune(force_v, chunk_rows, 0)
     try:
         sim = _sim_for(prog, nx, ny, np.float32, npml=npml, radius=0.3)
         sim.advance(ns, tblock=4)
         sim.synchronize()
     finally:
-        _lib.lib().fdtd2d_tune(0, 0)
+        _lib.lib().fdtd2d_tune(0, 0, 0)
     g, src = cases.grid_program(prog, nx, ny, ns, np.float32, npml=npml, radius=0.3, dft=False)
     orc.advance_2d(g, src)
     _assert_same(sim, g, prog)
@@ -193,15 +193,15 @@ def test_medium_grid_vs_oracle_fp32():
 def test_large_grid_fused_equals_unfused_bitwise(n):
     """Size-independent property at a grid the CPU oracle cannot reach: T-blocked == single-step fused ==
     one-kernel-per-reference-function, bit for bit, on every array."""
-    ns = 24
-    a = _sim_for("3_3", n, n, np.float32, npml=80)
-    b = _sim_for("3_3", n, n, np.float32, npml=80)
+    ns, npml = 64, 8                      # pulse peak (t0=20) has crossed the 8-cell PML into the total-field box
+    a = _sim_for("3_3", n, n, np.float32, npml=npml)
+    b = _sim_for("3_3", n, n, np.float32, npml=npml)
     a.advance(ns, tblock=4)
     b.advance(ns, tblock=1)
     for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
         assert torch.equal(a.tensor(name), b.tensor(name)), name
     del b
-    c = _sim_for("3_3", n, n, np.float32, npml=80)
+    c = _sim_for("3_3", n, n, np.float32, npml=npml)
     for _ in range(ns):
         c.step()
     for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
