@@ -182,10 +182,10 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     n, K, W, T = args.size, args.steps, args.warmup, args.tblock
-    if any(k in os.environ for k in ("FDTD_FORCE_V", "FDTD_CHUNK_ROWS", "FDTD_WARPS")):      # tuning sweeps only
+    knobs = ("FDTD_FORCE_V", "FDTD_CHUNK_ROWS", "FDTD_WARPS", "FDTD_RING", "FDTD_CAREFUL")
+    if any(k in os.environ for k in knobs):                                                 # tuning sweeps only
         from simulation_b200 import _lib
-        _lib.lib().fdtd2d_tune(int(os.environ.get("FDTD_FORCE_V", "0")), int(os.environ.get("FDTD_CHUNK_ROWS", "0")),
-                               int(os.environ.get("FDTD_WARPS", "0")))
+        _lib.lib().fdtd2d_tune(*[int(os.environ.get(k, "0")) for k in knobs])
     nx_global = n * world                       # weak scaling: one n x n slab per GPU
     wave = surface.Sinusoid(1500e6)
     src = fd2d.PointSource(nx_global // 2 - 5, n // 2 - 5, wave, hard=True)

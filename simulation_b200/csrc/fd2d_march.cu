@@ -18,6 +18,7 @@
 namespace {
 
 constexpr int TMAX = 8;          // deepest pipeline instantiated
+constexpr int MAX_SPECIAL = 12;  // most edge / TFSF / source strips (or chunks) a split launch can list
 constexpr int MAX_WARPS = 8;     // warps per CTA are independent; a CTA only groups neighbouring strips for L1 locality
 
 template <typename real>
@@ -35,6 +36,8 @@ struct MarchParams {
     int tfsf, npml;
     const real *ezi_hist, *hxi_hist;           // [T][ny], [T][2]
     int src_i, src_j, src_hard;                // point source on dz (src_i < 0: none)
+    int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
+    int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
     double src[TMAX];
 };
 
@@ -73,222 +76,325 @@ template <> struct VecIO<double, 2> {
     }
 };
 
-template <typename real, int V, bool LOSSY>
-struct Row {           // one grid row as it travels between stages (state at one time level)
-    real dz[V], hx[V], hy[V], ihx[V], ihy[V], naz[V], iz[V], nbz[V];
-};
+// ---- cp.async (LDGSTS): global -> shared without a register round trip; src_bytes = 0 zero-fills
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc, int src_bytes) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <typename real, int V, bool LOSSY>
-struct Held {          // the row a stage holds: D/E already advanced, H not yet
+template <typename real, int V>
+__device__ __forceinline__ void lds_vec(const void *smem_src, real (&d)[V]) {
+    if constexpr (sizeof(real) * V == 16) {
+        const float4 t = *reinterpret_cast<const float4 *>(smem_src);
+        const real *q = reinterpret_cast<const real *>(&t);
+#pragma unroll
+        for (int v = 0; v < V; ++v) d[v] = q[v];
+    } else if constexpr (sizeof(real) * V == 8) {
+        const float2 t = *reinterpret_cast<const float2 *>(smem_src);
+        const real *q = reinterpret_cast<const real *>(&t);
+#pragma unroll
+        for (int v = 0; v < V; ++v) d[v] = q[v];
+    } else {
+        d[0] = *reinterpret_cast<const real *>(smem_src);
+    }
+}
+
+// One grid row as it lives in registers.  A set is first the ARRIVING row of a stage (state at the stage's
+// input time level; `ez` not yet meaningful), then the row the stage HOLDS (D/E advanced, H not yet), then --
+// updated in place -- the row handed to the next stage.  Sets are never copied: with the row loop unrolled
+// T+1 times the T+1 sets rotate through the roles under compile-time indices (no register moves).
+template <typename real, int V>
+struct RowSet {
     real dz[V], ez[V], hx[V], hy[V], ihx[V], ihy[V], naz[V], iz[V], nbz[V];
 };
 
-template <typename real, int V, bool LOSSY>
-__device__ __forceinline__ void load_row(const MarchParams<real> &p, int g, bool col_in, int jb,
-                                         Row<real, V, LOSSY> &r) {
-    if (g >= p.in_lo && g < p.in_hi && col_in) {
-        const size_t off = (size_t)(g - p.row_base) * (size_t)p.ny + (size_t)jb;
-        VecIO<real, V>::ld(p.in_dz + off, r.dz);
-        VecIO<real, V>::ld(p.in_hx + off, r.hx);
-        VecIO<real, V>::ld(p.in_hy + off, r.hy);
-        VecIO<real, V>::ld(p.in_ihx + off, r.ihx);
-        VecIO<real, V>::ld(p.in_ihy + off, r.ihy);
-        VecIO<real, V>::ld(p.naz + off, r.naz);
-        if (LOSSY) {
-            VecIO<real, V>::ld(p.in_iz + off, r.iz);
-            VecIO<real, V>::ld(p.nbz + off, r.nbz);
-        }
-    } else {
+template <typename real, int V>
+struct ColCoef {       // per-column PML coefficients and update masks, fixed for the whole march
+    real gy2[V], gy3[V], fy1[V], fy2[V], fy3[V];
+    unsigned dmask, hmask;         // bit v: D / H update applies to column jb+v
+};
+
+// One pipeline stage at sub-step s: finish D,E of the arriving row A (global row rs) and H of the held row Hd
+// (global row rs-1), both in place.  FAST: interior warp -- no edge masks, no TFSF / source cells.
+template <typename real, int V, bool LOSSY, bool FAST>
+__device__ __forceinline__ void march_stage(const MarchParams<real> &p, const ColCoef<real, V> &c, RowSet<real, V> &A,
+                                            RowSet<real, V> &Hd, const int rs, const int s, const int jb,
+                                            const bool tf_cols, const bool src_cols) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const real half = real(0.5);
+    const int hr = rs - 1;
+    const int rd = FAST ? rs : min(max(rs, 0), p.nx - 1);
+    const int rh = FAST ? hr : min(max(hr, 0), p.nx - 1);
+    const real gx2 = __ldg(p.gx2 + rd), gx3 = __ldg(p.gx3 + rd);
+    const real fx1 = __ldg(p.fx1 + rh), fx2 = __ldg(p.fx2 + rh), fx3 = __ldg(p.fx3 + rh);
+    const bool drow = FAST || ((rs >= 1) && (rs < p.nx));
+    const bool hrow = FAST || ((hr >= 0) && (hr <= p.nx - 2));
+
+    // ---- D of row rs:  dz = gx3*gy3*dz + gx2*gy2*0.5*(hy - hy[i-1] - hx + hx[j-1])
+    const real hx_left = __shfl_up_sync(FULL, A.hx[V - 1], 1);
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            r.dz[v] = r.hx[v] = r.hy[v] = r.ihx[v] = r.ihy[v] = r.naz[v] = real(0);
-            r.iz[v] = r.nbz[v] = real(0);
+    for (int v = 0; v < V; ++v) {
+        const real hxl = (v == 0) ? hx_left : A.hx[v == 0 ? 0 : v - 1];
+        const real curl = ((A.hy[v] - Hd.hy[v]) - A.hx[v]) + hxl;
+        const real dn = ((gx3 * c.gy3[v]) * A.dz[v]) + (((gx2 * c.gy2[v]) * half) * curl);
+        if (FAST) A.dz[v] = dn;
+        else A.dz[v] = (drow && ((c.dmask >> v) & 1u)) ? dn : A.dz[v];
+    }
+    if (!FAST) {
+        const int ia = p.npml - 1, iz_ = p.nx - p.npml, ja = p.npml - 1, jz = p.ny - p.npml;
+        if (src_cols && rs == p.src_i) {             // point source (after the stencil, before inctdz)
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (jb + v == p.src_j) A.dz[v] = fdtd::inject<real>(A.dz[v], p.src[s], p.src_hard);
+        }
+        if (tf_cols && rs >= ia && rs <= iz_) {      // inctdz: uses hxi of the previous step
+            const real a = half * __ldg(p.hxi_hist + 2 * s), b = half * __ldg(p.hxi_hist + 2 * s + 1);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                if (jb + v == ja) A.dz[v] = A.dz[v] + a;
+                if (jb + v == jz) A.dz[v] = A.dz[v] - b;
+            }
+        }
+    }
+    // ---- E of row rs
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if (LOSSY) {
+            A.ez[v] = A.naz[v] * (A.dz[v] - A.iz[v]);
+            A.iz[v] = A.iz[v] + A.nbz[v] * A.ez[v];
+        } else {
+            A.ez[v] = A.naz[v] * A.dz[v];
+        }
+    }
+    // ---- H of the held row hr (needs ez[hr][j+1] and ez[rs][j]), in place
+    const real ez_right = __shfl_down_sync(FULL, Hd.ez[0], 1);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const real er = (v == V - 1) ? ez_right : Hd.ez[v == V - 1 ? v : v + 1];
+        const real cm = Hd.ez[v] - er;
+        const real cn = Hd.ez[v] - A.ez[v];
+        const real sx = Hd.ihx[v] + cm;
+        const real sy = Hd.ihy[v] + cn;
+        const real hx2 = (c.fy3[v] * Hd.hx[v]) + (c.fy2[v] * ((half * cm) + (fx1 * sx)));
+        const real hy2 = (fx3 * Hd.hy[v]) - (fx2 * ((half * cn) + (c.fy1[v] * sy)));
+        if (FAST) {
+            Hd.ihx[v] = sx; Hd.ihy[v] = sy; Hd.hx[v] = hx2; Hd.hy[v] = hy2;
+        } else {
+            const bool up = hrow && ((c.hmask >> v) & 1u);
+            Hd.ihx[v] = up ? sx : Hd.ihx[v];
+            Hd.ihy[v] = up ? sy : Hd.ihy[v];
+            Hd.hx[v] = up ? hx2 : Hd.hx[v];
+            Hd.hy[v] = up ? hy2 : Hd.hy[v];
+        }
+    }
+    if (!FAST && p.tfsf) {
+        const int ia = p.npml - 1, iz_ = p.nx - p.npml, ja = p.npml - 1, jz = p.ny - p.npml;
+        if (tf_cols && hr >= ia && hr <= iz_) {      // incthx
+            const real *ez_i = p.ezi_hist + (size_t)s * p.ny;
+            const real a = half * __ldg(ez_i + ja), b = half * __ldg(ez_i + jz);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                if (jb + v == ja - 1) Hd.hx[v] = Hd.hx[v] + a;
+                if (jb + v == jz) Hd.hx[v] = Hd.hx[v] - b;
+            }
+        }
+        if (hr == ia - 1 || hr == iz_) {             // incthy (two rows of the whole grid)
+            const real *ez_i = p.ezi_hist + (size_t)s * p.ny;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int j = jb + v;
+                if (j >= ja && j <= jz) {
+                    const real h = half * __ldg(ez_i + j);
+                    if (hr == ia - 1) Hd.hy[v] = Hd.hy[v] - h;
+                    if (hr == iz_) Hd.hy[v] = Hd.hy[v] + h;
+                }
+            }
         }
     }
 }
 
-template <typename real, int V, int T, bool LOSSY>
-__global__ void __launch_bounds__(MAX_WARPS * 32)
-k_march(const __grid_constant__ MarchParams<real> p) {
+// The march of one warp over its (strip, chunk).  Rows are staged through a per-lane ring of `ring_depth`
+// rows in shared memory filled by cp.async (each lane reads back only the 16 B it copied itself: no barrier,
+// no register cost), keeping ring_depth-1 rows x 6 arrays in flight per warp to cover the HBM latency.
+template <typename real, int V, int T, bool LOSSY, bool FAST>
+__device__ __forceinline__ void march_body(const MarchParams<real> &p, const int strip, const int chunk, const int lane,
+                                           unsigned char *const ring, const int ring_depth) {
     constexpr int W = 32 * V;            // columns per strip
-    constexpr int USE = W - 2 * T;       // columns a strip produces
-    constexpr unsigned FULL = 0xffffffffu;
-    const real half = real(0.5);
+    constexpr int HALO = ((T + V - 1) / V) * V;   // recomputed columns per side: >= T, multiple of V (aligned vectors)
+    constexpr int USE = W - 2 * HALO;    // columns a strip produces
+    constexpr int NS = T + 1;            // register row sets
+    constexpr int NARR = LOSSY ? 8 : 6;  // arrays staged per row
+    constexpr int LB = V * (int)sizeof(real);
+    constexpr int SLOT = NARR * 32 * LB; // ring bytes per row (per warp)
 
-    const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= p.nstrips * p.nchunks) return;
-    const int strip = w % p.nstrips;
-    const int chunk = w / p.nstrips;
-
-    const int c0 = strip * USE - T;                  // first column of the strip (halo included)
+    const int c0 = strip * USE - HALO;               // first column of the strip (halo included)
     const int jb = c0 + lane * V;                    // first column of this lane
-    const bool col_in = (jb >= 0) && (jb + V <= p.ny);
-    const bool col_store = col_in && (lane * V >= T) && (lane * V + V <= W - T);
+    const bool col_in = FAST || ((jb >= 0) && (jb + V <= p.ny));
+    const bool col_store = col_in && (lane * V >= HALO) && (lane * V + V <= W - HALO);
     const int i0 = p.out_lo + chunk * p.chunk_rows;
     const int i1 = min(i0 + p.chunk_rows, p.out_hi);
 
-    // per-column PML coefficients live in registers for the whole march
-    real gy2[V], gy3[V], fy1[V], fy2[V], fy3[V];
-    unsigned dmask = 0, hmask = 0;                   // bit v: D / H update applies to column jb+v
+    ColCoef<real, V> c;
+    c.dmask = c.hmask = 0;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        gy2[v] = gy3[v] = fy2[v] = fy3[v] = real(1);
-        fy1[v] = real(0);
+        c.gy2[v] = c.gy3[v] = c.fy2[v] = c.fy3[v] = real(1);
+        c.fy1[v] = real(0);
     }
     if (col_in) {
-        VecIO<real, V>::ld(p.gy2 + jb, gy2);
-        VecIO<real, V>::ld(p.gy3 + jb, gy3);
-        VecIO<real, V>::ld(p.fy1 + jb, fy1);
-        VecIO<real, V>::ld(p.fy2 + jb, fy2);
-        VecIO<real, V>::ld(p.fy3 + jb, fy3);
+        VecIO<real, V>::ld(p.gy2 + jb, c.gy2);
+        VecIO<real, V>::ld(p.gy3 + jb, c.gy3);
+        VecIO<real, V>::ld(p.fy1 + jb, c.fy1);
+        VecIO<real, V>::ld(p.fy2 + jb, c.fy2);
+        VecIO<real, V>::ld(p.fy3 + jb, c.fy3);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            if (jb + v >= 1) dmask |= 1u << v;
-            if (jb + v <= p.ny - 2) hmask |= 1u << v;
+            if (jb + v >= 1) c.dmask |= 1u << v;
+            if (jb + v <= p.ny - 2) c.hmask |= 1u << v;
         }
     }
+    // warp-uniform "does this strip touch a special column" flags (careful path only)
+    const int ja = p.npml - 1, jz = p.ny - p.npml;
+    const bool tf_cols = !FAST && p.tfsf && ((ja - 1 >= c0 && ja - 1 < c0 + W) || (ja >= c0 && ja < c0 + W) ||
+                                             (jz >= c0 && jz < c0 + W));
+    const bool src_cols = !FAST && (p.src_i >= 0) && (p.src_j >= c0 && p.src_j < c0 + W);
 
-    // warp-uniform "does this strip touch a special column" flags
-    const int ja = p.npml - 1, jz = p.ny - p.npml;   // TFSF box edges along j: [ja, jz]
-    const bool tf_cols = p.tfsf && ((ja - 1 >= c0 && ja - 1 < c0 + W) || (ja >= c0 && ja < c0 + W) ||
-                                    (jz >= c0 && jz < c0 + W));
-    const bool src_cols = (p.src_i >= 0) && (p.src_j >= c0 && p.src_j < c0 + W);
-    const int ia = p.npml - 1, iz_ = p.nx - p.npml;  // TFSF box edges along i: [ia, iz_]
-
-    Held<real, V, LOSSY> P[T];
+    RowSet<real, V> S[NS];
 #pragma unroll
-    for (int s = 0; s < T; ++s)
+    for (int k = 0; k < NS; ++k)
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            P[s].dz[v] = P[s].ez[v] = P[s].hx[v] = P[s].hy[v] = P[s].ihx[v] = P[s].ihy[v] = real(0);
-            P[s].naz[v] = P[s].iz[v] = P[s].nbz[v] = real(0);
+            S[k].dz[v] = S[k].ez[v] = S[k].hx[v] = S[k].hy[v] = S[k].ihx[v] = S[k].ihy[v] = real(0);
+            S[k].naz[v] = S[k].iz[v] = S[k].nbz[v] = real(0);
         }
 
-    Row<real, V, LOSSY> cur, nxt;
-    load_row<real, V, LOSSY>(p, i0 - T, col_in, jb, nxt);
-
-    for (int r = i0 - T; r < i1 + T; ++r) {
-        cur = nxt;
-        load_row<real, V, LOSSY>(p, r + 1 < i1 + T ? r + 1 : -1, col_in, jb, nxt);   // prefetch next row
-
-        real ez_out[V];
-#pragma unroll
-        for (int s = 0; s < T; ++s) {
-            const int rs = r - s;                    // global row carried by `cur` at this stage
-            const int hr = rs - 1;                   // global row held by this stage
-            const int rd = min(max(rs, 0), p.nx - 1);
-            const int rh = min(max(hr, 0), p.nx - 1);
-            const real gx2 = __ldg(p.gx2 + rd), gx3 = __ldg(p.gx3 + rd);
-            const real fx1 = __ldg(p.fx1 + rh), fx2 = __ldg(p.fx2 + rh), fx3 = __ldg(p.fx3 + rh);
-            const bool drow = (rs >= 1) && (rs < p.nx);
-            const bool hrow = (hr >= 0) && (hr <= p.nx - 2);
-            Held<real, V, LOSSY> &H = P[s];
-
-            // ---- D of row rs:  dz = gx3*gy3*dz + gx2*gy2*0.5*(hy - hy[i-1] - hx + hx[j-1])
-            real d[V], e[V], iznew[V];
-            const real hx_left = __shfl_up_sync(FULL, cur.hx[V - 1], 1);
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const real hxl = (v == 0) ? hx_left : cur.hx[v == 0 ? 0 : v - 1];
-                const real curl = ((cur.hy[v] - H.hy[v]) - cur.hx[v]) + hxl;
-                const real dn = ((gx3 * gy3[v]) * cur.dz[v]) + (((gx2 * gy2[v]) * half) * curl);
-                d[v] = (drow && ((dmask >> v) & 1u)) ? dn : cur.dz[v];
-            }
-            if (src_cols && rs == p.src_i) {         // point source (after the stencil, before inctdz)
-#pragma unroll
-                for (int v = 0; v < V; ++v)
-                    if (jb + v == p.src_j) d[v] = fdtd::inject<real>(d[v], p.src[s], p.src_hard);
-            }
-            if (tf_cols && rs >= ia && rs <= iz_) {  // inctdz: uses hxi of the previous step
-                const real a = half * __ldg(p.hxi_hist + 2 * s), b = half * __ldg(p.hxi_hist + 2 * s + 1);
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    if (jb + v == ja) d[v] = d[v] + a;
-                    if (jb + v == jz) d[v] = d[v] - b;
-                }
-            }
-            // ---- E of row rs
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                if (LOSSY) {
-                    e[v] = cur.naz[v] * (d[v] - cur.iz[v]);
-                    iznew[v] = cur.iz[v] + cur.nbz[v] * e[v];
-                } else {
-                    e[v] = cur.naz[v] * d[v];
-                    iznew[v] = real(0);
-                }
-            }
-            // ---- H of the held row hr (needs ez[hr][j+1] and ez[rs][j])
-            real hxn[V], hyn[V], ax[V], ay[V];
-            const real ez_right = __shfl_down_sync(FULL, H.ez[0], 1);
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const real er = (v == V - 1) ? ez_right : H.ez[v == V - 1 ? v : v + 1];
-                const real cm = H.ez[v] - er;
-                const real cn = H.ez[v] - e[v];
-                const real sx = H.ihx[v] + cm;
-                const real sy = H.ihy[v] + cn;
-                const real hx2 = (fy3[v] * H.hx[v]) + (fy2[v] * ((half * cm) + (fx1 * sx)));
-                const real hy2 = (fx3 * H.hy[v]) - (fx2 * ((half * cn) + (fy1[v] * sy)));
-                const bool up = hrow && ((hmask >> v) & 1u);
-                ax[v] = up ? sx : H.ihx[v];
-                ay[v] = up ? sy : H.ihy[v];
-                hxn[v] = up ? hx2 : H.hx[v];
-                hyn[v] = up ? hy2 : H.hy[v];
-            }
-            if (p.tfsf) {
-                if (tf_cols && hr >= ia && hr <= iz_) {      // incthx
-                    const real *ez_i = p.ezi_hist + (size_t)s * p.ny;
-                    const real a = half * __ldg(ez_i + ja), b = half * __ldg(ez_i + jz);
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        if (jb + v == ja - 1) hxn[v] = hxn[v] + a;
-                        if (jb + v == jz) hxn[v] = hxn[v] - b;
-                    }
-                }
-                if (hr == ia - 1 || hr == iz_) {             // incthy (two rows of the whole grid)
-                    const real *ez_i = p.ezi_hist + (size_t)s * p.ny;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const int j = jb + v;
-                        if (j >= ja && j <= jz) {
-                            const real h = half * __ldg(ez_i + j);
-                            if (hr == ia - 1) hyn[v] = hyn[v] - h;
-                            if (hr == iz_) hyn[v] = hyn[v] + h;
-                        }
-                    }
-                }
-            }
-            // ---- hand the finished row to the next stage, keep the arriving one
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const real odz = H.dz[v], onaz = H.naz[v], oiz = H.iz[v], onbz = H.nbz[v];
-                ez_out[v] = H.ez[v];
-                H.dz[v] = d[v];   H.ez[v] = e[v];
-                H.hx[v] = cur.hx[v];  H.hy[v] = cur.hy[v];
-                H.ihx[v] = cur.ihx[v];  H.ihy[v] = cur.ihy[v];
-                H.naz[v] = cur.naz[v];
-                if (LOSSY) { H.iz[v] = iznew[v]; H.nbz[v] = cur.nbz[v]; }
-                cur.dz[v] = odz;  cur.hx[v] = hxn[v];  cur.hy[v] = hyn[v];
-                cur.ihx[v] = ax[v];  cur.ihy[v] = ay[v];  cur.naz[v] = onaz;
-                if (LOSSY) { cur.iz[v] = oiz; cur.nbz[v] = onbz; }
-            }
+    unsigned char *const lane_ring = ring + lane * LB;
+    // asynchronous copies of global row g into ring slot k (zero fill outside the stored rows / the grid)
+    auto fetch = [&](const int g, const int k) {
+        const bool ok = (g >= p.in_lo) && (g < p.in_hi) && col_in;
+        const size_t off = ok ? (size_t)(g - p.row_base) * (size_t)p.ny + (size_t)jb : 0;
+        const int nb = ok ? LB : 0;
+        unsigned char *dst = lane_ring + (size_t)k * SLOT;
+        cp_async<LB>(dst + 0 * 32 * LB, p.in_dz + off, nb);
+        cp_async<LB>(dst + 1 * 32 * LB, p.in_hx + off, nb);
+        cp_async<LB>(dst + 2 * 32 * LB, p.in_hy + off, nb);
+        cp_async<LB>(dst + 3 * 32 * LB, p.in_ihx + off, nb);
+        cp_async<LB>(dst + 4 * 32 * LB, p.in_ihy + off, nb);
+        cp_async<LB>(dst + 5 * 32 * LB, p.naz + off, nb);
+        if (LOSSY) {
+            cp_async<LB>(dst + 6 * 32 * LB, p.in_iz + off, nb);
+            cp_async<LB>(dst + 7 * 32 * LB, p.nbz + off, nb);
         }
+        cp_async_commit();
+    };
+    auto take = [&](const int k, RowSet<real, V> &row) {
+        const unsigned char *src = lane_ring + (size_t)k * SLOT;
+        lds_vec<real, V>(src + 0 * 32 * LB, row.dz);
+        lds_vec<real, V>(src + 1 * 32 * LB, row.hx);
+        lds_vec<real, V>(src + 2 * 32 * LB, row.hy);
+        lds_vec<real, V>(src + 3 * 32 * LB, row.ihx);
+        lds_vec<real, V>(src + 4 * 32 * LB, row.ihy);
+        lds_vec<real, V>(src + 5 * 32 * LB, row.naz);
+        if (LOSSY) {
+            lds_vec<real, V>(src + 6 * 32 * LB, row.iz);
+            lds_vec<real, V>(src + 7 * 32 * LB, row.nbz);
+        }
+    };
 
-        // `cur` is now row r-T at time t+T
-        const int ro = r - T;
-        if (ro >= i0 && ro < i1 && col_store) {
-            const size_t off = (size_t)(ro - p.row_base) * (size_t)p.ny + (size_t)jb;
-            VecIO<real, V>::st(p.out_dz + off, cur.dz);
-            VecIO<real, V>::st(p.out_ez + off, ez_out);
-            VecIO<real, V>::st(p.out_hx + off, cur.hx);
-            VecIO<real, V>::st(p.out_hy + off, cur.hy);
-            VecIO<real, V>::st(p.out_ihx + off, cur.ihx);
-            VecIO<real, V>::st(p.out_ihy + off, cur.ihy);
-            if (LOSSY) VecIO<real, V>::st(p.out_iz + off, cur.iz);
+    const int r_begin = i0 - T, r_end = i1 + T;      // rows fed to stage 0: [r_begin, r_end)
+    for (int k = 0; k < ring_depth - 1; ++k) fetch(r_begin + k < r_end ? r_begin + k : -1, k);
+    int slot = 0;                                     // ring slot of the row consumed next
+
+    for (int r = r_begin; r < r_end; r += NS) {
+#pragma unroll
+        for (int u = 0; u < NS; ++u) {
+            const int rr = r + u;                     // global row arriving at stage 0 (may overrun r_end: zero rows)
+            // the oldest of the ring_depth-1 pending rows has landed
+            switch (ring_depth) {
+                case 2: cp_async_wait<0>(); break;
+                case 3: cp_async_wait<1>(); break;
+                case 4: cp_async_wait<2>(); break;
+                case 6: cp_async_wait<4>(); break;
+                default: cp_async_wait<6>(); break;   // ring_depth == 8
+            }
+            take(slot, S[u]);
+            {   // refill the slot consumed one sub-iteration ago (its values are long in registers)
+                const int g = rr + ring_depth - 1;
+                fetch(g < r_end ? g : -1, slot == 0 ? ring_depth - 1 : slot - 1);
+            }
+            slot = (slot + 1 == ring_depth) ? 0 : slot + 1;
+#pragma unroll
+            for (int s = 0; s < T; ++s)
+                march_stage<real, V, LOSSY, FAST>(p, c, S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], rr - s, s,
+                                                  jb, tf_cols, src_cols);
+            // the set held by the last stage is now row rr-T at time t+T
+            RowSet<real, V> &O = S[(u + 1) % NS];
+            const int ro = rr - T;
+            if (ro >= i0 && ro < i1 && col_store) {
+                const size_t off = (size_t)(ro - p.row_base) * (size_t)p.ny + (size_t)jb;
+                VecIO<real, V>::st(p.out_dz + off, O.dz);
+                VecIO<real, V>::st(p.out_ez + off, O.ez);
+                VecIO<real, V>::st(p.out_hx + off, O.hx);
+                VecIO<real, V>::st(p.out_hy + off, O.hy);
+                VecIO<real, V>::st(p.out_ihx + off, O.ihx);
+                VecIO<real, V>::st(p.out_ihy + off, O.ihy);
+                if (LOSSY) VecIO<real, V>::st(p.out_iz + off, O.iz);
+            }
         }
     }
+    cp_async_wait<0>();
+}
+
+// k-th id (0-based) of the ascending sequence 0,1,2,... with the sorted ids in `skip` removed
+__device__ __forceinline__ int kth_not_in(int k, const int *skip, int n) {
+    for (int q = 0; q < n; ++q)
+        if (skip[q] <= k) ++k;
+    return k;
+}
+
+// Two launches per pass share this kernel template:
+//   FAST    : interior warps -- (ordinary strips) x (ordinary chunks): every column (halo included) is an
+//             ordinary cell and every row touched (warm-up, drain and unroll overrun included) is an ordinary
+//             stored row, so the body carries no masks, clamps or TFSF / source cells;
+//   careful : the listed special strips x all chunks, plus ordinary strips x the listed special chunks
+//             (grid edges, PEC row / column, TFSF box edges, the point source); or everything (all_careful).
+template <typename real, int V, int T, bool LOSSY, bool FAST>
+__global__ void __launch_bounds__(MAX_WARPS * 32)
+k_march(const __grid_constant__ MarchParams<real> p, const int ring_depth, const int all_careful) {
+    extern __shared__ __align__(16) unsigned char ring_smem[];
+    constexpr int SLOT = (LOSSY ? 8 : 6) * 32 * V * (int)sizeof(real);
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    unsigned char *const ring = ring_smem + (size_t)(threadIdx.x >> 5) * ring_depth * SLOT;
+    const int nsf = p.nstrips - p.n_sstrips, ncf = p.nchunks - p.n_schunks;   // ordinary strips / chunks
+    int strip, chunk;
+    if (FAST) {
+        if (w >= nsf * ncf) return;
+        strip = kth_not_in(w % nsf, p.sstrips, p.n_sstrips);
+        chunk = kth_not_in(w / nsf, p.schunks, p.n_schunks);
+    } else if (all_careful) {
+        if (w >= p.nstrips * p.nchunks) return;
+        strip = w % p.nstrips;
+        chunk = w / p.nstrips;
+    } else {
+        const int na = p.n_sstrips * p.nchunks;
+        if (w < na) {
+            strip = p.sstrips[w % p.n_sstrips];
+            chunk = w / p.n_sstrips;
+        } else {
+            const int x = w - na;
+            if (x >= nsf * p.n_schunks) return;
+            strip = kth_not_in(x % nsf, p.sstrips, p.n_sstrips);
+            chunk = p.schunks[x / nsf];
+        }
+    }
+    march_body<real, V, T, LOSSY, FAST>(p, strip, chunk, lane, ring, ring_depth);
 }
 
 // ---- incident line: T steps of the 1D auxiliary FDTD (ezinct ... hxinct), recording what the 2D pass
@@ -323,20 +429,75 @@ __global__ void k_incident_line(int ny, int npml, int T, real *ezi, real *hxi, r
 int g_force_v = 0;          // test / tuning hooks (fdtd2d_tune)
 int g_chunk_rows = 0;
 int g_warps = 0;
+int g_ring = 0;
+int g_careful = 0;
 
-template <typename real, int V, int T>
-int launch_march(const MarchParams<real> &mp, bool lossy, cudaStream_t st) {
-    const int nw = mp.nstrips * mp.nchunks;
-    const int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : 4;
-    const int grid = (nw + warps - 1) / warps;
-    if (lossy) k_march<real, V, T, true><<<grid, warps * 32, 0, st>>>(mp);
-    else       k_march<real, V, T, false><<<grid, warps * 32, 0, st>>>(mp);
+inline int ring_depth_or_default() { return (g_ring == 2 || g_ring == 3 || g_ring == 4 || g_ring == 6 || g_ring == 8) ? g_ring : 4; }
+
+template <typename real, int V, int T, bool LOSSY, bool FAST>
+int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStream_t st) {
+    if (items <= 0) return FDTD_OK;
+    const int ring = ring_depth_or_default();
+    const size_t slot = (size_t)(LOSSY ? 8 : 6) * 32 * V * sizeof(real);
+    int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : 4;
+    while (warps > 1 && (size_t)warps * ring * slot > 200 * 1024) --warps;
+    const size_t smem = (size_t)warps * ring * slot;
+    static size_t configured = 0;                       // per instantiation: largest dynamic smem opted in so far
+    if (smem > 48 * 1024 && smem > configured) {
+        FDTD_CUDA(cudaFuncSetAttribute(k_march<real, V, T, LOSSY, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = (items + warps - 1) / warps;
+    k_march<real, V, T, LOSSY, FAST><<<grid, warps * 32, smem, st>>>(mp, ring, all_careful);
     FDTD_LAUNCH_CHECK("k_march");
     return FDTD_OK;
 }
 
+// classify strips and chunks on the host (same conditions as the kernel relies on) and launch the two kernels
+template <typename real, int V, int T, bool LOSSY>
+int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
+    constexpr int W = 32 * V, HALO = ((T + V - 1) / V) * V, USE = W - 2 * HALO;
+    const int ja = mp.npml - 1, jz = mp.ny - mp.npml, ia = mp.npml - 1, iz_ = mp.nx - mp.npml;
+    int ns = 0, nc = 0;
+    bool overflow = g_careful != 0;
+    for (int k = 0; k < mp.nstrips && !overflow; ++k) {
+        const int c0 = k * USE - HALO, c1 = c0 + W;     // columns [c0, c1)
+        bool special = (c0 < 1) || (c1 > mp.ny - 1);
+        if (mp.tfsf) special = special || (ja - 1 >= c0 && ja - 1 < c1) || (ja >= c0 && ja < c1) || (jz >= c0 && jz < c1);
+        if (mp.src_i >= 0) special = special || (mp.src_j >= c0 && mp.src_j < c1);
+        if (special) {
+            if (ns == MAX_SPECIAL) overflow = true;
+            else mp.sstrips[ns++] = k;
+        }
+    }
+    for (int k = 0; k < mp.nchunks && !overflow; ++k) {
+        const int i0 = mp.out_lo + k * mp.chunk_rows, i1 = min(i0 + mp.chunk_rows, mp.out_hi);
+        const int lo = i0 - T - 1, hi = i1 + 2 * T + 2; // rows touched: [lo, hi)
+        bool special = (lo < max(1, mp.in_lo)) || (hi > min(mp.nx - 1, mp.in_hi));
+        if (mp.tfsf) special = special || (ia - 1 >= lo && ia - 1 < hi) || (iz_ >= lo && iz_ < hi);
+        if (special) {
+            if (nc == MAX_SPECIAL) overflow = true;
+            else mp.schunks[nc++] = k;
+        }
+    }
+    if (overflow) {                                      // tiny grids: everything through the careful kernel
+        mp.n_sstrips = mp.n_schunks = 0;
+        return launch_one<real, V, T, LOSSY, false>(mp, mp.nstrips * mp.nchunks, 1, st);
+    }
+    mp.n_sstrips = ns; mp.n_schunks = nc;
+    const int nsf = mp.nstrips - ns, ncf = mp.nchunks - nc;
+    int rc = launch_one<real, V, T, LOSSY, false>(mp, ns * mp.nchunks + nsf * nc, 0, st);
+    if (rc != FDTD_OK) return rc;
+    return launch_one<real, V, T, LOSSY, true>(mp, nsf * ncf, 0, st);
+}
+
+template <typename real, int V, int T>
+int launch_march(MarchParams<real> &mp, bool lossy, cudaStream_t st) {
+    return lossy ? launch_march_k<real, V, T, true>(mp, st) : launch_march_k<real, V, T, false>(mp, st);
+}
+
 template <typename real, int V>
-int launch_march_T(int T, const MarchParams<real> &mp, bool lossy, cudaStream_t st) {
+int launch_march_T(int T, MarchParams<real> &mp, bool lossy, cudaStream_t st) {
     switch (T) {
         case 1: return launch_march<real, V, 1>(mp, lossy, st);
         case 2: return launch_march<real, V, 2>(mp, lossy, st);
@@ -346,15 +507,10 @@ int launch_march_T(int T, const MarchParams<real> &mp, bool lossy, cudaStream_t 
     }
 }
 
-// vector width: widest V dividing ny and T (strip origin c0 = strip*(32V-2T) - T must be V-aligned)
-template <typename real> int pick_v(int ny, int T);
-template <> int pick_v<float>(int ny, int T) {
-    if (ny % 4 == 0 && T % 4 == 0) return 4;
-    if (ny % 2 == 0 && T % 2 == 0) return 2;
-    return 1;
-}
-template <> int pick_v<double>(int ny, int T) { return (ny % 2 == 0 && T % 2 == 0) ? 2 : 1; }
-
+// vector width: widest V dividing ny (rows start V-aligned; the strip halo is rounded up to a multiple of V)
+template <typename real> int pick_v(int ny);
+template <> int pick_v<float>(int ny) { return ny % 4 == 0 ? 4 : (ny % 2 == 0 ? 2 : 1); }
+template <> int pick_v<double>(int ny) { return ny % 2 == 0 ? 2 : 1; }
 
 template <typename real>
 int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int tblock, cudaStream_t st,
@@ -389,9 +545,10 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.src_i = tfsf ? -1 : q->src_i; mp.src_j = q->src_j; mp.src_hard = q->src_hard;
         for (int s = 0; s < TMAX; ++s) mp.src[s] = (src && s < T) ? src[done + s] : 0.0;
 
-        int V = g_force_v ? g_force_v : pick_v<real>(q->ny, T);
-        if (q->ny % V != 0 || T % V != 0) V = 1;
-        const int use = 32 * V - 2 * T;
+        int V = g_force_v ? g_force_v : pick_v<real>(q->ny);
+        if (q->ny % V != 0 || (sizeof(real) == 8 && V == 4)) V = 1;
+        const int halo = ((T + V - 1) / V) * V;
+        const int use = 32 * V - 2 * halo;
         mp.nstrips = (q->ny + use - 1) / use;
         const int rows = mp.out_hi - mp.out_lo;
         int chunk = g_chunk_rows;
@@ -440,10 +597,12 @@ int fdtd2d_max_tblock(int dtype, int ny) {
 }
 
 // tuning / test hook (not part of the reference-facing surface): force the vector width and rows per chunk
-int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta) {
+int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, int force_careful) {
     g_force_v = force_v;
     g_chunk_rows = chunk_rows;
     g_warps = warps_per_cta;
+    g_ring = ring_depth;
+    g_careful = force_careful;
     return FDTD_OK;
 }
 

@@ -86,13 +86,13 @@ def test_advance_vector_widths_and_chunking(prog, nx, ny, npml, force_v, chunk_r
     """Wide enough for several strips per vector width, several row chunks, ragged edges."""
     from simulation_b200 import _lib
     ns = 45
-    _lib.lib().fdtd2d_tune(force_v, chunk_rows, 0)
+    _lib.lib().fdtd2d_tune(force_v, chunk_rows, 0, 0, 0)
     try:
         sim = _sim_for(prog, nx, ny, np.float32, npml=npml, radius=0.3)
         sim.advance(ns, tblock=4)
         sim.synchronize()
     finally:
-        _lib.lib().fdtd2d_tune(0, 0, 0)
+        _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
     g, src = cases.grid_program(prog, nx, ny, ns, np.float32, npml=npml, radius=0.3, dft=False)
     orc.advance_2d(g, src)
     _assert_same(sim, g, prog)

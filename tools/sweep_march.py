@@ -21,15 +21,15 @@ def main():
     ap.add_argument("--ts", default="4,3,2,1")
     ap.add_argument("--warps", default="4,2,8")
     ap.add_argument("--chunks", default="0,256,1024")
+    ap.add_argument("--rings", default="4")
+    ap.add_argument("--careful", type=int, default=0)
     a = ap.parse_args()
     n = a.size
     sim = fd2d.Fdtd2D(n, n, 80, np.float32, source=fd2d.PointSource(n // 2 - 5, n // 2 - 5, surface.Sinusoid(1500e6)))
     lib = _lib.lib()
     ints = lambda s: [int(x) for x in s.split(",")]
-    for T, V, W, C in itertools.product(ints(a.ts), ints(a.vs), ints(a.warps), ints(a.chunks)):
-        if T % V != 0 and V != 1:
-            continue
-        lib.fdtd2d_tune(V, C, W)
+    for T, V, W, C, R in itertools.product(ints(a.ts), ints(a.vs), ints(a.warps), ints(a.chunks), ints(a.rings)):
+        lib.fdtd2d_tune(V, C, W, R, a.careful)
         steps = (a.steps // T) * T
         sim.advance(2 * T, tblock=T)
         torch.cuda.synchronize()
@@ -39,8 +39,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        print(f"T={T} V={V} warps={W} chunk={C:5d}  {n * n * steps / ms / 1e6:8.1f} Gcell/s  {ms / steps:7.3f} ms/step", flush=True)
-    lib.fdtd2d_tune(0, 0, 0)
+        print(f"T={T} V={V} warps={W} chunk={C:5d} ring={R}  {n * n * steps / ms / 1e6:8.1f} Gcell/s  {ms / steps:7.3f} ms/step", flush=True)
+    lib.fdtd2d_tune(0, 0, 0, 0, 0)
 
 
 if __name__ == "__main__":
