@@ -136,6 +136,12 @@ typedef struct {
     void *ezi_hist, *hxi_hist;  /* scratch: tblock*ny and tblock*2 elements (FDTD_TFSF) */
     int src_i, src_j, src_hard; /* point source on dz at GLOBAL (src_i, src_j); src_i < 0: none.
                                    With FDTD_TFSF the table drives ezi[3] instead (hard). */
+    /* Optional promise that unlocks the interior fast kernel: for GLOBAL rows i in [ident_row_lo, ident_row_hi)
+     * the x-vectors, and for columns j in [ident_col_lo, ident_col_hi) the y-vectors, hold exactly the
+     * identity set (f?1 = 0, f?2 = f?3 = g?2 = g?3 = 1) -- true for [npml, N-1-npml) after pmlparam
+     * (fd2d/program/fd2d_3_3.py:113-122).  Multiplications by 1 are then skipped (exact).  All zero: no promise.
+     * fdtd2d_check_identity() verifies a promise on the device. */
+    int ident_row_lo, ident_row_hi, ident_col_lo, ident_col_hi;
 } fdtd2d_problem;
 
 /* Advance nsteps full time steps (reference order: ezinct, dfield+source, inctdz, efield, hxinct, hfield,
@@ -145,6 +151,8 @@ typedef struct {
  * src: HOST float64 table, one sample per step.  *cur_out = set holding the result. */
 int fdtd2d_advance(const fdtd2d_problem *p, int cur, int nsteps, const double *src, int tblock,
                    void *stream, int *cur_out);
+/* number of coefficient entries that violate the ident_* promise of `p` (0 = promise holds); synchronises */
+int fdtd2d_check_identity(const fdtd2d_problem *p, long long *violations);
 /* largest supported tblock for a dtype / ny (0 if unsupported) */
 int fdtd2d_max_tblock(int dtype, int ny);
 

@@ -51,7 +51,8 @@ class Problem2D(C.Structure):
                 ("state", (C.c_void_p * NFIELDS) * 2),
                 ("ezi", C.c_void_p), ("hxi", C.c_void_p), ("bc", C.c_void_p),
                 ("ezi_hist", C.c_void_p), ("hxi_hist", C.c_void_p),
-                ("src_i", C.c_int), ("src_j", C.c_int), ("src_hard", C.c_int)]
+                ("src_i", C.c_int), ("src_j", C.c_int), ("src_hard", C.c_int),
+                ("ident_row_lo", C.c_int), ("ident_row_hi", C.c_int), ("ident_col_lo", C.c_int), ("ident_col_hi", C.c_int)]
 
 
 # every symbol include/fdtd_b200.h declares: name -> (restype, argtypes)
@@ -80,6 +81,7 @@ SYMBOLS = {
     "fdtd2d_incthx": (_I, [_I, _I, _I, _I, _P, _P, _P]),
     "fdtd2d_incthy": (_I, [_I, _I, _I, _I, _P, _P, _P]),
     "fdtd2d_advance": (_I, [C.POINTER(Problem2D), _I, _I, C.POINTER(_D), _I, _P, C.POINTER(_I)]),
+    "fdtd2d_check_identity": (_I, [C.POINTER(Problem2D), C.POINTER(C.c_longlong)]),
     "fdtd2d_max_tblock": (_I, [_I, _I]),
     "fdtd2d_tune": (_I, [_I, _I, _I, _I, _I]),
 }

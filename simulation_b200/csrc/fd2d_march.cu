@@ -36,6 +36,7 @@ struct MarchParams {
     int tfsf, npml;
     const real *ezi_hist, *hxi_hist;           // [T][ny], [T][2]
     int src_i, src_j, src_hard;                // point source on dz (src_i < 0: none)
+    int ident_row_lo, ident_row_hi, ident_col_lo, ident_col_hi;   // rows / cols [lo,hi) with identity PML coefficients
     int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
     int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
     double src[TMAX];
@@ -129,10 +130,14 @@ __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const Co
     constexpr unsigned FULL = 0xffffffffu;
     const real half = real(0.5);
     const int hr = rs - 1;
+    // FAST warps only touch rows / columns whose ten PML coefficients are the identity set (the host
+    // guarantees it through fdtd2d_problem::ident_*): multiplications by exactly 1 are dropped -- an exact
+    // identity for every input -- while 0*x is kept, because it decides the sign of a zero sum.
     const int rd = FAST ? rs : min(max(rs, 0), p.nx - 1);
     const int rh = FAST ? hr : min(max(hr, 0), p.nx - 1);
-    const real gx2 = __ldg(p.gx2 + rd), gx3 = __ldg(p.gx3 + rd);
-    const real fx1 = __ldg(p.fx1 + rh), fx2 = __ldg(p.fx2 + rh), fx3 = __ldg(p.fx3 + rh);
+    const real gx2 = FAST ? real(1) : __ldg(p.gx2 + rd), gx3 = FAST ? real(1) : __ldg(p.gx3 + rd);
+    const real fx1 = FAST ? real(0) : __ldg(p.fx1 + rh);
+    const real fx2 = FAST ? real(1) : __ldg(p.fx2 + rh), fx3 = FAST ? real(1) : __ldg(p.fx3 + rh);
     const bool drow = FAST || ((rs >= 1) && (rs < p.nx));
     const bool hrow = FAST || ((hr >= 0) && (hr <= p.nx - 2));
 
@@ -142,7 +147,8 @@ __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const Co
     for (int v = 0; v < V; ++v) {
         const real hxl = (v == 0) ? hx_left : A.hx[v == 0 ? 0 : v - 1];
         const real curl = ((A.hy[v] - Hd.hy[v]) - A.hx[v]) + hxl;
-        const real dn = ((gx3 * c.gy3[v]) * A.dz[v]) + (((gx2 * c.gy2[v]) * half) * curl);
+        const real gy2 = FAST ? real(1) : c.gy2[v], gy3 = FAST ? real(1) : c.gy3[v];
+        const real dn = ((gx3 * gy3) * A.dz[v]) + (((gx2 * gy2) * half) * curl);
         if (FAST) A.dz[v] = dn;
         else A.dz[v] = (drow && ((c.dmask >> v) & 1u)) ? dn : A.dz[v];
     }
@@ -181,8 +187,9 @@ __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const Co
         const real cn = Hd.ez[v] - A.ez[v];
         const real sx = Hd.ihx[v] + cm;
         const real sy = Hd.ihy[v] + cn;
-        const real hx2 = (c.fy3[v] * Hd.hx[v]) + (c.fy2[v] * ((half * cm) + (fx1 * sx)));
-        const real hy2 = (fx3 * Hd.hy[v]) - (fx2 * ((half * cn) + (c.fy1[v] * sy)));
+        const real fy1 = FAST ? real(0) : c.fy1[v], fy2 = FAST ? real(1) : c.fy2[v], fy3 = FAST ? real(1) : c.fy3[v];
+        const real hx2 = (fy3 * Hd.hx[v]) + (fy2 * ((half * cm) + (fx1 * sx)));
+        const real hy2 = (fx3 * Hd.hy[v]) - (fx2 * ((half * cn) + (fy1 * sy)));
         if (FAST) {
             Hd.ihx[v] = sx; Hd.ihy[v] = sy; Hd.hx[v] = hx2; Hd.hy[v] = hy2;
         } else {
@@ -219,12 +226,14 @@ __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const Co
     }
 }
 
-// The march of one warp over its (strip, chunk).  Rows are staged through a per-lane ring of `ring_depth`
-// rows in shared memory filled by cp.async (each lane reads back only the 16 B it copied itself: no barrier,
-// no register cost), keeping ring_depth-1 rows x 6 arrays in flight per warp to cover the HBM latency.
+// The march of one warp over its (strip, chunk).  Rows are staged through a per-lane ring of RING rows in
+// shared memory filled by cp.async (each lane reads back only the 16 B it copied itself: no barrier, no
+// register cost), keeping RING-1 rows x 6 arrays in flight per warp to cover the HBM latency.
+constexpr int RING = 4;
+
 template <typename real, int V, int T, bool LOSSY, bool FAST>
 __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int strip, const int chunk, const int lane,
-                                           unsigned char *const ring, const int ring_depth) {
+                                           unsigned char *const ring) {
     constexpr int W = 32 * V;            // columns per strip
     constexpr int HALO = ((T + V - 1) / V) * V;   // recomputed columns per side: >= T, multiple of V (aligned vectors)
     constexpr int USE = W - 2 * HALO;    // columns a strip produces
@@ -247,7 +256,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         c.gy2[v] = c.gy3[v] = c.fy2[v] = c.fy3[v] = real(1);
         c.fy1[v] = real(0);
     }
-    if (col_in) {
+    if (!FAST && col_in) {
         VecIO<real, V>::ld(p.gy2 + jb, c.gy2);
         VecIO<real, V>::ld(p.gy3 + jb, c.gy3);
         VecIO<real, V>::ld(p.fy1 + jb, c.fy1);
@@ -275,12 +284,18 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         }
 
     unsigned char *const lane_ring = ring + lane * LB;
-    // asynchronous copies of global row g into ring slot k (zero fill outside the stored rows / the grid)
-    auto fetch = [&](const int g, const int k) {
-        const bool ok = (g >= p.in_lo) && (g < p.in_hi) && col_in;
-        const size_t off = ok ? (size_t)(g - p.row_base) * (size_t)p.ny + (size_t)jb : 0;
+    const int r_begin = i0 - T, r_end = i1 + T;      // rows fed to stage 0: [r_begin, r_end)
+    // element offsets (row-major, local array rows) of the row fetched next / stored next; advanced by ny per row
+    long long off_f = (long long)(r_begin - p.row_base) * p.ny + jb;
+    long long off_s = (long long)(r_begin - T - p.row_base) * p.ny + jb;
+    int g_f = r_begin;                                // global row fetched next
+    // asynchronous copies of global row g_f into ring slot k (zero fill outside the stored rows / the grid;
+    // FAST warps only ever touch stored interior rows, so their copies are unconditional)
+    auto fetch = [&](const int k) {
+        const bool ok = FAST || ((g_f >= p.in_lo) && (g_f < p.in_hi) && (g_f < r_end) && col_in);
+        const long long off = ok ? off_f : 0;
         const int nb = ok ? LB : 0;
-        unsigned char *dst = lane_ring + (size_t)k * SLOT;
+        unsigned char *dst = lane_ring + k * SLOT;
         cp_async<LB>(dst + 0 * 32 * LB, p.in_dz + off, nb);
         cp_async<LB>(dst + 1 * 32 * LB, p.in_hx + off, nb);
         cp_async<LB>(dst + 2 * 32 * LB, p.in_hy + off, nb);
@@ -292,9 +307,11 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
             cp_async<LB>(dst + 7 * 32 * LB, p.nbz + off, nb);
         }
         cp_async_commit();
+        off_f += p.ny;
+        ++g_f;
     };
     auto take = [&](const int k, RowSet<real, V> &row) {
-        const unsigned char *src = lane_ring + (size_t)k * SLOT;
+        const unsigned char *src = lane_ring + k * SLOT;
         lds_vec<real, V>(src + 0 * 32 * LB, row.dz);
         lds_vec<real, V>(src + 1 * 32 * LB, row.hx);
         lds_vec<real, V>(src + 2 * 32 * LB, row.hy);
@@ -307,28 +324,18 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         }
     };
 
-    const int r_begin = i0 - T, r_end = i1 + T;      // rows fed to stage 0: [r_begin, r_end)
-    for (int k = 0; k < ring_depth - 1; ++k) fetch(r_begin + k < r_end ? r_begin + k : -1, k);
+#pragma unroll
+    for (int k = 0; k < RING - 1; ++k) fetch(k);
     int slot = 0;                                     // ring slot of the row consumed next
 
     for (int r = r_begin; r < r_end; r += NS) {
 #pragma unroll
         for (int u = 0; u < NS; ++u) {
-            const int rr = r + u;                     // global row arriving at stage 0 (may overrun r_end: zero rows)
-            // the oldest of the ring_depth-1 pending rows has landed
-            switch (ring_depth) {
-                case 2: cp_async_wait<0>(); break;
-                case 3: cp_async_wait<1>(); break;
-                case 4: cp_async_wait<2>(); break;
-                case 6: cp_async_wait<4>(); break;
-                default: cp_async_wait<6>(); break;   // ring_depth == 8
-            }
+            const int rr = r + u;                     // global row arriving at stage 0 (may overrun r_end)
+            cp_async_wait<RING - 2>();                // the oldest of the RING-1 pending rows has landed
             take(slot, S[u]);
-            {   // refill the slot consumed one sub-iteration ago (its values are long in registers)
-                const int g = rr + ring_depth - 1;
-                fetch(g < r_end ? g : -1, slot == 0 ? ring_depth - 1 : slot - 1);
-            }
-            slot = (slot + 1 == ring_depth) ? 0 : slot + 1;
+            fetch(slot == 0 ? RING - 1 : slot - 1);   // refill the slot consumed one sub-iteration ago
+            slot = (slot + 1 == RING) ? 0 : slot + 1;
 #pragma unroll
             for (int s = 0; s < T; ++s)
                 march_stage<real, V, LOSSY, FAST>(p, c, S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], rr - s, s,
@@ -337,15 +344,15 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
             RowSet<real, V> &O = S[(u + 1) % NS];
             const int ro = rr - T;
             if (ro >= i0 && ro < i1 && col_store) {
-                const size_t off = (size_t)(ro - p.row_base) * (size_t)p.ny + (size_t)jb;
-                VecIO<real, V>::st(p.out_dz + off, O.dz);
-                VecIO<real, V>::st(p.out_ez + off, O.ez);
-                VecIO<real, V>::st(p.out_hx + off, O.hx);
-                VecIO<real, V>::st(p.out_hy + off, O.hy);
-                VecIO<real, V>::st(p.out_ihx + off, O.ihx);
-                VecIO<real, V>::st(p.out_ihy + off, O.ihy);
-                if (LOSSY) VecIO<real, V>::st(p.out_iz + off, O.iz);
+                VecIO<real, V>::st(p.out_dz + off_s, O.dz);
+                VecIO<real, V>::st(p.out_ez + off_s, O.ez);
+                VecIO<real, V>::st(p.out_hx + off_s, O.hx);
+                VecIO<real, V>::st(p.out_hy + off_s, O.hy);
+                VecIO<real, V>::st(p.out_ihx + off_s, O.ihx);
+                VecIO<real, V>::st(p.out_ihy + off_s, O.ihy);
+                if (LOSSY) VecIO<real, V>::st(p.out_iz + off_s, O.iz);
             }
+            off_s += p.ny;
         }
     }
     cp_async_wait<0>();
@@ -366,12 +373,12 @@ __device__ __forceinline__ int kth_not_in(int k, const int *skip, int n) {
 //             (grid edges, PEC row / column, TFSF box edges, the point source); or everything (all_careful).
 template <typename real, int V, int T, bool LOSSY, bool FAST>
 __global__ void __launch_bounds__(MAX_WARPS * 32)
-k_march(const __grid_constant__ MarchParams<real> p, const int ring_depth, const int all_careful) {
+k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
     extern __shared__ __align__(16) unsigned char ring_smem[];
     constexpr int SLOT = (LOSSY ? 8 : 6) * 32 * V * (int)sizeof(real);
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    unsigned char *const ring = ring_smem + (size_t)(threadIdx.x >> 5) * ring_depth * SLOT;
+    unsigned char *const ring = ring_smem + (size_t)(threadIdx.x >> 5) * RING * SLOT;
     const int nsf = p.nstrips - p.n_sstrips, ncf = p.nchunks - p.n_schunks;   // ordinary strips / chunks
     int strip, chunk;
     if (FAST) {
@@ -394,7 +401,7 @@ k_march(const __grid_constant__ MarchParams<real> p, const int ring_depth, const
             chunk = p.schunks[x / nsf];
         }
     }
-    march_body<real, V, T, LOSSY, FAST>(p, strip, chunk, lane, ring, ring_depth);
+    march_body<real, V, T, LOSSY, FAST>(p, strip, chunk, lane, ring);
 }
 
 // ---- incident line: T steps of the 1D auxiliary FDTD (ezinct ... hxinct), recording what the 2D pass
@@ -426,18 +433,26 @@ __global__ void k_incident_line(int ny, int npml, int T, real *ezi, real *hxi, r
     }
 }
 
+// counts entries of the promised identity ranges that are not exactly the identity coefficient set
+template <typename real>
+__global__ void k_check_identity(const real *f1, const real *f2, const real *f3, const real *g2, const real *g3, int lo,
+                                 int hi, unsigned long long *bad) {
+    const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const bool ok = f1[i] == real(0) && !signbit(f1[i]) && f2[i] == real(1) && f3[i] == real(1) && g2[i] == real(1) &&
+                    g3[i] == real(1);
+    if (!ok) atomicAdd(bad, 1ull);
+}
+
 int g_force_v = 0;          // test / tuning hooks (fdtd2d_tune)
 int g_chunk_rows = 0;
 int g_warps = 0;
-int g_ring = 0;
 int g_careful = 0;
-
-inline int ring_depth_or_default() { return (g_ring == 2 || g_ring == 3 || g_ring == 4 || g_ring == 6 || g_ring == 8) ? g_ring : 4; }
 
 template <typename real, int V, int T, bool LOSSY, bool FAST>
 int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStream_t st) {
     if (items <= 0) return FDTD_OK;
-    const int ring = ring_depth_or_default();
+    const int ring = RING;
     const size_t slot = (size_t)(LOSSY ? 8 : 6) * 32 * V * sizeof(real);
     int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : 4;
     while (warps > 1 && (size_t)warps * ring * slot > 200 * 1024) --warps;
@@ -448,7 +463,7 @@ int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStre
         configured = smem;
     }
     const int grid = (items + warps - 1) / warps;
-    k_march<real, V, T, LOSSY, FAST><<<grid, warps * 32, smem, st>>>(mp, ring, all_careful);
+    k_march<real, V, T, LOSSY, FAST><<<grid, warps * 32, smem, st>>>(mp, all_careful);
     FDTD_LAUNCH_CHECK("k_march");
     return FDTD_OK;
 }
@@ -462,7 +477,7 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     bool overflow = g_careful != 0;
     for (int k = 0; k < mp.nstrips && !overflow; ++k) {
         const int c0 = k * USE - HALO, c1 = c0 + W;     // columns [c0, c1)
-        bool special = (c0 < 1) || (c1 > mp.ny - 1);
+        bool special = (c0 < max(1, mp.ident_col_lo)) || (c1 > min(mp.ny - 1, mp.ident_col_hi));
         if (mp.tfsf) special = special || (ja - 1 >= c0 && ja - 1 < c1) || (ja >= c0 && ja < c1) || (jz >= c0 && jz < c1);
         if (mp.src_i >= 0) special = special || (mp.src_j >= c0 && mp.src_j < c1);
         if (special) {
@@ -472,8 +487,8 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     }
     for (int k = 0; k < mp.nchunks && !overflow; ++k) {
         const int i0 = mp.out_lo + k * mp.chunk_rows, i1 = min(i0 + mp.chunk_rows, mp.out_hi);
-        const int lo = i0 - T - 1, hi = i1 + 2 * T + 2; // rows touched: [lo, hi)
-        bool special = (lo < max(1, mp.in_lo)) || (hi > min(mp.nx - 1, mp.in_hi));
+        const int lo = i0 - T - 1, hi = i1 + 2 * T + RING + 2; // rows touched (fetch run-ahead included): [lo, hi)
+        bool special = (lo < max(max(1, mp.in_lo), mp.ident_row_lo)) || (hi > min(min(mp.nx - 1, mp.in_hi), mp.ident_row_hi));
         if (mp.tfsf) special = special || (ia - 1 >= lo && ia - 1 < hi) || (iz_ >= lo && iz_ < hi);
         if (special) {
             if (nc == MAX_SPECIAL) overflow = true;
@@ -541,6 +556,8 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.out_lo = max(q->row_lo - rem, mp.in_lo);
         mp.out_hi = min(q->row_hi + rem, mp.in_hi);
         mp.tfsf = tfsf; mp.npml = q->npml;
+        mp.ident_row_lo = q->ident_row_lo; mp.ident_row_hi = q->ident_row_hi;
+        mp.ident_col_lo = q->ident_col_lo; mp.ident_col_hi = q->ident_col_hi;
         mp.ezi_hist = (const real *)q->ezi_hist; mp.hxi_hist = (const real *)q->hxi_hist;
         mp.src_i = tfsf ? -1 : q->src_i; mp.src_j = q->src_j; mp.src_hard = q->src_hard;
         for (int s = 0; s < TMAX; ++s) mp.src[s] = (src && s < T) ? src[done + s] : 0.0;
@@ -553,11 +570,11 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         const int rows = mp.out_hi - mp.out_lo;
         int chunk = g_chunk_rows;
         if (chunk <= 0) {
-            // enough warps for ~3 waves at 16 warps/SM, but keep the 2T-row recompute overhead <= ~6%
-            const long want = 3L * fdtd::sm_count() * 16;
-            long nchunks = (want + mp.nstrips - 1) / mp.nstrips;
-            chunk = (int)((rows + nchunks - 1) / max(nchunks, 1L));
-            chunk = max(chunk, 32 * T);
+            // many short chunks keep the last wave full (8 resident warps per SM): aim at >= 4 waves of warps,
+            // with the 2T-row warm-up/drain recompute between ~3 % (64T rows) and ~12 % (16T rows)
+            const long want = 4L * fdtd::sm_count() * 8;
+            chunk = (int)((long)rows * mp.nstrips / want);
+            chunk = min(max(chunk, 16 * T), 64 * T);
         }
         chunk = max(1, min(chunk, rows));
         mp.chunk_rows = chunk;
@@ -591,6 +608,31 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
 
 extern "C" {
 
+int fdtd2d_check_identity(const fdtd2d_problem *q, long long *violations) {
+    FDTD_REQUIRE(q && violations, "fdtd2d_check_identity: null argument");
+    FDTD_REQUIRE(q->dtype == FDTD_F32 || q->dtype == FDTD_F64, "fdtd2d_check_identity: unknown dtype %d", q->dtype);
+    FDTD_REQUIRE(q->ident_row_lo >= 0 && q->ident_row_hi <= q->nx && q->ident_col_lo >= 0 && q->ident_col_hi <= q->ny,
+                 "fdtd2d_check_identity: identity ranges outside the grid");
+    unsigned long long *bad = nullptr, host = 0;
+    FDTD_CUDA(cudaMalloc(&bad, sizeof(*bad)));
+    FDTD_CUDA(cudaMemset(bad, 0, sizeof(*bad)));
+    const int nr = q->ident_row_hi - q->ident_row_lo, nc = q->ident_col_hi - q->ident_col_lo;
+    if (q->dtype == FDTD_F32) {
+        using R = float;
+        if (nr > 0) k_check_identity<R><<<(nr + 255) / 256, 256>>>((const R *)q->pml.fx1, (const R *)q->pml.fx2, (const R *)q->pml.fx3, (const R *)q->pml.gx2, (const R *)q->pml.gx3, q->ident_row_lo, q->ident_row_hi, bad);
+        if (nc > 0) k_check_identity<R><<<(nc + 255) / 256, 256>>>((const R *)q->pml.fy1, (const R *)q->pml.fy2, (const R *)q->pml.fy3, (const R *)q->pml.gy2, (const R *)q->pml.gy3, q->ident_col_lo, q->ident_col_hi, bad);
+    } else {
+        using R = double;
+        if (nr > 0) k_check_identity<R><<<(nr + 255) / 256, 256>>>((const R *)q->pml.fx1, (const R *)q->pml.fx2, (const R *)q->pml.fx3, (const R *)q->pml.gx2, (const R *)q->pml.gx3, q->ident_row_lo, q->ident_row_hi, bad);
+        if (nc > 0) k_check_identity<R><<<(nc + 255) / 256, 256>>>((const R *)q->pml.fy1, (const R *)q->pml.fy2, (const R *)q->pml.fy3, (const R *)q->pml.gy2, (const R *)q->pml.gy3, q->ident_col_lo, q->ident_col_hi, bad);
+    }
+    FDTD_LAUNCH_CHECK("k_check_identity");
+    FDTD_CUDA(cudaMemcpy(&host, bad, sizeof(host), cudaMemcpyDeviceToHost));
+    FDTD_CUDA(cudaFree(bad));
+    *violations = (long long)host;
+    return FDTD_OK;
+}
+
 int fdtd2d_max_tblock(int dtype, int ny) {
     (void)ny;
     return (dtype == FDTD_F32 || dtype == FDTD_F64) ? 4 : 0;
@@ -601,7 +643,7 @@ int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, 
     g_force_v = force_v;
     g_chunk_rows = chunk_rows;
     g_warps = warps_per_cta;
-    g_ring = ring_depth;
+    (void)ring_depth;
     g_careful = force_careful;
     return FDTD_OK;
 }
@@ -622,6 +664,8 @@ int fdtd2d_advance(const fdtd2d_problem *q, int cur, int nsteps, const double *s
                      "fdtd2d_advance: %d steps need ghost rows [%d,%d) but only [%d,%d) are stored", nsteps, need_lo,
                      need_hi, q->row_base, q->row_base + q->rows_alloc);
     }
+    FDTD_REQUIRE(q->ident_row_lo >= 0 && q->ident_row_hi <= q->nx && q->ident_col_lo >= 0 && q->ident_col_hi <= q->ny,
+                 "fdtd2d_advance: identity ranges outside the grid");
     const bool lossy = (q->flags & FDTD_LOSSY) != 0, tfsf = (q->flags & FDTD_TFSF) != 0;
     for (int s = 0; s < 2; ++s)
         for (int f = 0; f < FDTD2D_NFIELDS; ++f) {

@@ -199,6 +199,8 @@ class Fdtd2D:
                 self._hxi_hist = z1(max(self.tblock, 1) * 2)
             else:
                 self.ezi = self.hxi = self.bc = self._ezi_hist = self._hxi_hist = None
+            if self.check_identity() != 0:
+                raise _lib.FdtdError("PML vectors violate the identity-coefficient promise outside the layer")
 
     # ---- array access -----------------------------------------------------------------------------
     def _to_dev_rows(self, host, fill):
@@ -261,7 +263,22 @@ class Fdtd2D:
             p.src_i, p.src_j, p.src_hard = self.source.i, self.source.j, int(self.source.hard)
         else:
             p.src_i, p.src_j, p.src_hard = -1, -1, 1
+        # pmlparam leaves every coefficient at its identity value on [npml, N-1-npml): promise it to the kernel
+        p.ident_row_lo, p.ident_row_hi = self._ident(self.nx)
+        p.ident_col_lo, p.ident_col_hi = self._ident(self.ny)
         return p
+
+    def _ident(self, n):
+        lo, hi = self.npml, n - 1 - self.npml
+        return (lo, hi) if hi > lo else (0, 0)
+
+    def check_identity(self) -> int:
+        """Device-side verification of the identity-coefficient promise (0 = holds)."""
+        bad = C.c_longlong(-1)
+        p = self._problem()
+        with torch.cuda.device(self.device):
+            check(lib().fdtd2d_check_identity(C.byref(p), C.byref(bad)), "fdtd2d_check_identity")
+        return int(bad.value)
 
     def advance(self, nsteps: int, tblock: Optional[int] = None) -> None:
         """``nsteps`` full time steps through the fused, temporally blocked kernel (asynchronous)."""
