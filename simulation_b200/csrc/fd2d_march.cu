@@ -518,6 +518,8 @@ int launch_march_T(int T, MarchParams<real> &mp, bool lossy, cudaStream_t st) {
         case 2: return launch_march<real, V, 2>(mp, lossy, st);
         case 3: return launch_march<real, V, 3>(mp, lossy, st);
         case 4: return launch_march<real, V, 4>(mp, lossy, st);
+        case 6: return launch_march<real, V, 6>(mp, lossy, st);
+        case 8: if constexpr (V <= 2) return launch_march<real, V, 8>(mp, lossy, st);
         default: fdtd::set_error("unsupported time-block depth %d for vector width %d", T, V); return FDTD_EUNSUPPORTED;
     }
 }
@@ -533,7 +535,8 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
     const bool lossy = (q->flags & FDTD_LOSSY) != 0, tfsf = (q->flags & FDTD_TFSF) != 0;
     int done = 0;
     while (done < nsteps) {
-        const int T = min(tblock, nsteps - done);
+        int T = min(tblock, nsteps - done);
+        if (T == 5 || T == 7) --T;                      // instantiated depths: 1, 2, 3, 4, 6, 8
         const int rem = nsteps - done - T;              // steps still to come after this pass
         MarchParams<real> mp;
         void *const *in = q->state[cur];
@@ -564,6 +567,8 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
 
         int V = g_force_v ? g_force_v : pick_v<real>(q->ny);
         if (q->ny % V != 0 || (sizeof(real) == 8 && V == 4)) V = 1;
+        if (T == 8 && V == 4) V = 2;                    // 9 register row sets of 4 columns do not fit
+        if (T == 8 && sizeof(real) == 8) V = 1;         // ... nor do 9 sets of 2 doubles
         const int halo = ((T + V - 1) / V) * V;
         const int use = 32 * V - 2 * halo;
         mp.nstrips = (q->ny + use - 1) / use;
@@ -635,7 +640,7 @@ int fdtd2d_check_identity(const fdtd2d_problem *q, long long *violations) {
 
 int fdtd2d_max_tblock(int dtype, int ny) {
     (void)ny;
-    return (dtype == FDTD_F32 || dtype == FDTD_F64) ? 4 : 0;
+    return (dtype == FDTD_F32 || dtype == FDTD_F64) ? 8 : 0;
 }
 
 // tuning / test hook (not part of the reference-facing surface): force the vector width and rows per chunk
@@ -653,7 +658,7 @@ int fdtd2d_advance(const fdtd2d_problem *q, int cur, int nsteps, const double *s
     FDTD_REQUIRE(q && cur_out, "fdtd2d_advance: null problem / cur_out");
     FDTD_REQUIRE(cur == 0 || cur == 1, "fdtd2d_advance: cur must be 0 or 1");
     FDTD_REQUIRE(q->nx >= 2 && q->ny >= 2, "fdtd2d_advance: grid %dx%d too small", q->nx, q->ny);
-    FDTD_REQUIRE(tblock >= 1 && tblock <= 4, "fdtd2d_advance: tblock %d outside [1, 4]", tblock);
+    FDTD_REQUIRE(tblock >= 1 && tblock <= 8, "fdtd2d_advance: tblock %d outside [1, 8]", tblock);
     FDTD_REQUIRE(nsteps >= 0, "fdtd2d_advance: nsteps < 0");
     FDTD_REQUIRE(q->row_lo >= 0 && q->row_hi <= q->nx && q->row_lo < q->row_hi, "fdtd2d_advance: bad owned rows [%d,%d)", q->row_lo, q->row_hi);
     FDTD_REQUIRE(q->row_base <= q->row_lo && q->row_base + q->rows_alloc >= q->row_hi, "fdtd2d_advance: owned rows outside the stored rows");
