@@ -43,6 +43,8 @@ extern "C" {
 #define FDTD_ABC    4          /* 1D two-step-delay absorbing boundaries (programs 1_2 ..) */
 #define FDTD_FLUX   8          /* 1D flux form Dx/Ex/Ix (programs 2_1, 2_2) */
 #define FDTD_DEBYE 16          /* 1D Debye medium Sx (program 2_3) */
+#define FDTD_LAZY_EZ 32        /* 2D advance: do not store ez at all (caller finishes with a non-lazy advance
+                                  or fdtd2d_efield); ignored with FDTD_LOSSY.  Default: the last pass stores ez. */
 
 /* structs of device pointers, in the reference's declaration order
  * (fd2d/cuda/test_3_4.cu:20-36, fd1d/cuda/test_2_3.cu:17-27) */

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libfdtd_b200.so")
 
 F32, F64 = 0, 1
-TFSF, LOSSY, ABC, FLUX, DEBYE = 1, 2, 4, 8, 16
+TFSF, LOSSY, ABC, FLUX, DEBYE, LAZY_EZ = 1, 2, 4, 8, 16, 32
 DZ, EZ, HX, HY, IHX, IHY, IZ, NFIELDS = range(8)
 
 

@@ -37,6 +37,7 @@ struct MarchParams {
     const real *ezi_hist, *hxi_hist;           // [T][ny], [T][2]
     int src_i, src_j, src_hard;                // point source on dz (src_i < 0: none)
     int ident_row_lo, ident_row_hi, ident_col_lo, ident_col_hi;   // rows / cols [lo,hi) with identity PML coefficients
+    int write_ez;                              // 0: this pass leaves ez untouched (it is never read by a pass)
     int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
     int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
     double src[TMAX];
@@ -345,7 +346,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
             const int ro = rr - T;
             if (ro >= i0 && ro < i1 && col_store) {
                 VecIO<real, V>::st(p.out_dz + off_s, O.dz);
-                VecIO<real, V>::st(p.out_ez + off_s, O.ez);
+                if (p.write_ez) VecIO<real, V>::st(p.out_ez + off_s, O.ez);
                 VecIO<real, V>::st(p.out_hx + off_s, O.hx);
                 VecIO<real, V>::st(p.out_hy + off_s, O.hy);
                 VecIO<real, V>::st(p.out_ihx + off_s, O.ihx);
@@ -449,6 +450,27 @@ int g_chunk_rows = 0;
 int g_warps = 0;
 int g_careful = 0;
 
+int g_serial = 0;            // tuning hook: 1 = no side stream (careful then interior, in order)
+
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+
+// one high-priority side stream + fork/join events per device, created on first use
+SideStream *side_stream() {
+    static SideStream table[64];
+    static bool ready[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!ready[dev]) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&table[dev].stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&table[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&table[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ready[dev] = true;
+    }
+    return &table[dev];
+}
+
 template <typename real, int V, int T, bool LOSSY, bool FAST>
 int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStream_t st) {
     if (items <= 0) return FDTD_OK;
@@ -501,9 +523,24 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     }
     mp.n_sstrips = ns; mp.n_schunks = nc;
     const int nsf = mp.nstrips - ns, ncf = mp.nchunks - nc;
-    int rc = launch_one<real, V, T, LOSSY, false>(mp, ns * mp.nchunks + nsf * nc, 0, st);
+    const int n_careful = ns * mp.nchunks + nsf * nc, n_fast = nsf * ncf;
+    // The careful kernel is small (edges only) and would run alone at a fraction of a wave: fork it onto a side
+    // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
+    SideStream *side = (n_careful > 0 && n_fast > 0 && !g_serial) ? side_stream() : nullptr;
+    if (side == nullptr) {
+        int rc = launch_one<real, V, T, LOSSY, false>(mp, n_careful, 0, st);
+        if (rc != FDTD_OK) return rc;
+        return launch_one<real, V, T, LOSSY, true>(mp, n_fast, 0, st);
+    }
+    FDTD_CUDA(cudaEventRecord(side->fork, st));
+    FDTD_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    int rc = launch_one<real, V, T, LOSSY, false>(mp, n_careful, 0, side->stream);
     if (rc != FDTD_OK) return rc;
-    return launch_one<real, V, T, LOSSY, true>(mp, nsf * ncf, 0, st);
+    FDTD_CUDA(cudaEventRecord(side->join, side->stream));
+    rc = launch_one<real, V, T, LOSSY, true>(mp, n_fast, 0, st);
+    if (rc != FDTD_OK) return rc;
+    FDTD_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    return FDTD_OK;
 }
 
 template <typename real, int V, int T>
@@ -559,6 +596,9 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.out_lo = max(q->row_lo - rem, mp.in_lo);
         mp.out_hi = min(q->row_hi + rem, mp.in_hi);
         mp.tfsf = tfsf; mp.npml = q->npml;
+        // ez is an output only (every pass recomputes it from dz): intermediate passes need not store it.
+        // With a lossy medium it cannot be rebuilt afterwards (iz has moved on), so it is always stored.
+        mp.write_ez = lossy || (rem == 0 && !(q->flags & FDTD_LAZY_EZ));
         mp.ident_row_lo = q->ident_row_lo; mp.ident_row_hi = q->ident_row_hi;
         mp.ident_col_lo = q->ident_col_lo; mp.ident_col_hi = q->ident_col_hi;
         mp.ezi_hist = (const real *)q->ezi_hist; mp.hxi_hist = (const real *)q->hxi_hist;
@@ -648,7 +688,7 @@ int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, 
     g_force_v = force_v;
     g_chunk_rows = chunk_rows;
     g_warps = warps_per_cta;
-    (void)ring_depth;
+    g_serial = ring_depth;      // (slot reused) 1 = serialise the careful and interior kernels
     g_careful = force_careful;
     return FDTD_OK;
 }

@@ -280,8 +280,11 @@ class Fdtd2D:
             check(lib().fdtd2d_check_identity(C.byref(p), C.byref(bad)), "fdtd2d_check_identity")
         return int(bad.value)
 
-    def advance(self, nsteps: int, tblock: Optional[int] = None) -> None:
-        """``nsteps`` full time steps through the fused, temporally blocked kernel (asynchronous)."""
+    def advance(self, nsteps: int, tblock: Optional[int] = None, lazy_ez: bool = False) -> None:
+        """``nsteps`` full time steps through the fused, temporally blocked kernel (asynchronous).
+
+        ``ez`` is an output only, so just the last pass stores it; ``lazy_ez=True`` skips even that (used by
+        the slab driver between ghost exchanges) and leaves ``ez`` stale until a later non-lazy ``advance``."""
         if nsteps <= 0:
             return
         tb = int(tblock or self.tblock)
@@ -291,6 +294,8 @@ class Fdtd2D:
         if self.source is not None:
             src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)
         p = self._problem()
+        if lazy_ez:
+            p.flags |= _lib.LAZY_EZ
         out = C.c_int(-1)
         with torch.cuda.device(self.device):
             check(lib().fdtd2d_advance(C.byref(p), self._cur, int(nsteps),

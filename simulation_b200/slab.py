@@ -115,8 +115,8 @@ class SlabFdtd2D:
             self._ghost_dirty = False
         while left > 0:
             n = min(left, self.ghost) if self.world > 1 else left
-            self.engine.advance(n, tblock=tblock)
             left -= n
+            self.engine.advance(n, tblock=tblock, lazy_ez=left > 0)    # ez is stored by the last block only
             self.exchange_ghosts()
 
     def gather(self, name: str) -> Optional[np.ndarray]:

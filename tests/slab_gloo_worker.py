@@ -45,7 +45,7 @@ class NumpyStandIn:
         o = self.row_lo - self.row_base
         return t[o:o + self.row_hi - self.row_lo]
 
-    def advance(self, n, tblock=None):
+    def advance(self, n, tblock=None, lazy_ez=False):
         for k in range(n):
             t = self.t + 1
             orc.step_2d(self.g, np.int32(t), self.table[t - 1] if self.table is not None else 0.0)
