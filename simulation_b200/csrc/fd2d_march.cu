@@ -450,7 +450,8 @@ int g_chunk_rows = 0;
 int g_warps = 0;
 int g_careful = 0;
 
-int g_serial = 0;            // tuning hook: 1 = no side stream (careful then interior, in order)
+int g_serial = 1;            // 1 = careful then interior kernel in stream order (measured best: co-resident
+                             // careful CTAs evict the interior kernel's instruction stream); 2 = fork onto a side stream
 
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
 
@@ -476,7 +477,8 @@ int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStre
     if (items <= 0) return FDTD_OK;
     const int ring = RING;
     const size_t slot = (size_t)(LOSSY ? 8 : 6) * 32 * V * sizeof(real);
-    int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : 4;
+    // 8 independent warps per CTA on big grids; fewer when there are not enough warps to fill every SM
+    int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : (items >= 32 * fdtd::sm_count() ? 8 : (items >= 8 * fdtd::sm_count() ? 4 : 2));
     while (warps > 1 && (size_t)warps * ring * slot > 200 * 1024) --warps;
     const size_t smem = (size_t)warps * ring * slot;
     static size_t configured = 0;                       // per instantiation: largest dynamic smem opted in so far
@@ -526,7 +528,7 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     const int n_careful = ns * mp.nchunks + nsf * nc, n_fast = nsf * ncf;
     // The careful kernel is small (edges only) and would run alone at a fraction of a wave: fork it onto a side
     // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
-    SideStream *side = (n_careful > 0 && n_fast > 0 && !g_serial) ? side_stream() : nullptr;
+    SideStream *side = (n_careful > 0 && n_fast > 0 && g_serial == 2) ? side_stream() : nullptr;
     if (side == nullptr) {
         int rc = launch_one<real, V, T, LOSSY, false>(mp, n_careful, 0, st);
         if (rc != FDTD_OK) return rc;
@@ -616,10 +618,10 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         int chunk = g_chunk_rows;
         if (chunk <= 0) {
             // many short chunks keep the last wave full (8 resident warps per SM): aim at >= 4 waves of warps,
-            // with the 2T-row warm-up/drain recompute between ~3 % (64T rows) and ~12 % (16T rows)
+            // with the 2T-row warm-up/drain recompute between ~6 % (32T rows, measured optimum) and ~12 % (16T rows)
             const long want = 4L * fdtd::sm_count() * 8;
             chunk = (int)((long)rows * mp.nstrips / want);
-            chunk = min(max(chunk, 16 * T), 64 * T);
+            chunk = min(max(chunk, 16 * T), 32 * T);
         }
         chunk = max(1, min(chunk, rows));
         mp.chunk_rows = chunk;
@@ -688,7 +690,7 @@ int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, 
     g_force_v = force_v;
     g_chunk_rows = chunk_rows;
     g_warps = warps_per_cta;
-    g_serial = ring_depth;      // (slot reused) 1 = serialise the careful and interior kernels
+    g_serial = (ring_depth == 2) ? 2 : 1;     // (slot reused) 2 = fork the careful kernel onto a side stream
     g_careful = force_careful;
     return FDTD_OK;
 }

@@ -181,7 +181,9 @@ class Fdtd2D:
         self.rows_alloc = min(self.row_hi + self.ghost, self.nx) - self.row_base
         self.t = 0                                        # steps taken so far (next step is t+1)
         code = _lib.dtype_code(self.np_dtype)
-        self.tblock = int(tblock) if tblock else lib().fdtd2d_max_tblock(code, self.ny)
+        self.max_tblock = lib().fdtd2d_max_tblock(code, self.ny)
+        # measured optimum on B200: 6 steps per pass in fp32 (register row sets still fit with 4-wide vectors)
+        self.tblock = int(tblock) if tblock else min(self.max_tblock, 6 if self.np_dtype == np.float32 else 4)
 
         with torch.cuda.device(self.device):
             shape = (self.rows_alloc, self.ny)
@@ -195,8 +197,8 @@ class Fdtd2D:
             if self.tfsf:
                 z1 = lambda n: torch.zeros(n, dtype=self.dtype, device=self.device)
                 self.ezi, self.hxi, self.bc = z1(self.ny), z1(self.ny), z1(4)
-                self._ezi_hist = z1(max(self.tblock, 1) * self.ny)
-                self._hxi_hist = z1(max(self.tblock, 1) * 2)
+                self._ezi_hist = z1(self.max_tblock * self.ny)
+                self._hxi_hist = z1(self.max_tblock * 2)
             else:
                 self.ezi = self.hxi = self.bc = self._ezi_hist = self._hxi_hist = None
             if self.check_identity() != 0:
@@ -288,8 +290,8 @@ class Fdtd2D:
         if nsteps <= 0:
             return
         tb = int(tblock or self.tblock)
-        if self.tfsf and tb > self.tblock:
-            raise _lib.FdtdError(f"tblock {tb} exceeds the incident-line scratch sized for {self.tblock}")
+        if tb > self.max_tblock:
+            raise _lib.FdtdError(f"tblock {tb} exceeds the deepest supported time block {self.max_tblock}")
         src = None
         if self.source is not None:
             src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)

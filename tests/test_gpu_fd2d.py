@@ -68,11 +68,11 @@ def test_step_functions_match_oracle(prog, nx, ny, npml, ns, dtype):
 
 # ------------------------------------------------------------------ fused, temporally blocked advance
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("tblock", [1, 2, 3, 4])
+@pytest.mark.parametrize("tblock", [1, 2, 3, 4, 5, 6, 8])
 @pytest.mark.parametrize("prog,nx,ny,npml,ns", [("3_2", 56, 72, 8, 61), ("3_3", 64, 48, 7, 75),
                                                 ("3_4", 60, 72, 8, 66), ("3_1", 40, 56, 0, 50)])
 def test_advance_matches_oracle(prog, nx, ny, npml, ns, tblock, dtype):
-    sim = _sim_for(prog, nx, ny, dtype, npml=npml, radius=0.12, tblock=4)
+    sim = _sim_for(prog, nx, ny, dtype, npml=npml, radius=0.12)
     sim.advance(ns, tblock=tblock)
     g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=0.12, dft=False)
     orc.advance_2d(g, src)
@@ -80,16 +80,19 @@ def test_advance_matches_oracle(prog, nx, ny, npml, ns, tblock, dtype):
 
 
 @pytest.mark.parametrize("force_v", [1, 2, 4])
-@pytest.mark.parametrize("chunk_rows", [0, 5, 16])
-@pytest.mark.parametrize("prog,nx,ny,npml", [("3_3", 150, 284, 9), ("3_2", 131, 260, 8), ("3_4", 97, 300, 8)])
-def test_advance_vector_widths_and_chunking(prog, nx, ny, npml, force_v, chunk_rows):
-    """Wide enough for several strips per vector width, several row chunks, ragged edges."""
+@pytest.mark.parametrize("chunk_rows,tblock,side", [(0, 6, 0), (5, 4, 0), (16, 6, 2), (40, 8, 0)])
+@pytest.mark.parametrize("prog,nx,ny,npml", [("3_3", 150, 284, 9), ("3_2", 131, 260, 8), ("3_4", 97, 300, 8),
+                                             ("3_2", 420, 1100, 8), ("3_3", 400, 1000, 12)])
+def test_advance_vector_widths_and_chunking(prog, nx, ny, npml, force_v, chunk_rows, tblock, side):
+    """Wide enough for several strips per vector width, several row chunks, ragged edges; the two big
+    grids have a true interior, so the interior (identity-coefficient) kernel and the edge kernel both run,
+    in stream order and forked onto the side stream."""
     from simulation_b200 import _lib
     ns = 45
-    _lib.lib().fdtd2d_tune(force_v, chunk_rows, 0, 0, 0)
+    _lib.lib().fdtd2d_tune(force_v, chunk_rows, 0, side, 0)
     try:
         sim = _sim_for(prog, nx, ny, np.float32, npml=npml, radius=0.3)
-        sim.advance(ns, tblock=4)
+        sim.advance(ns, tblock=tblock)
         sim.synchronize()
     finally:
         _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
@@ -175,6 +178,32 @@ def test_numba_program_3_4_golden_within_tolerance():
 
 
 # ------------------------------------------------------------------ medium and large grids
+def test_interior_kernel_equals_edge_kernel_everywhere():
+    """Force every warp through the careful (edge) kernel and compare with the default split: bitwise equal."""
+    from simulation_b200 import _lib
+    nx, ny, npml, ns = 1200, 1600, 20, 60
+    a = _sim_for("3_3", nx, ny, np.float32, npml=npml)
+    a.advance(ns)
+    _lib.lib().fdtd2d_tune(0, 0, 0, 0, 1)
+    try:
+        b = _sim_for("3_3", nx, ny, np.float32, npml=npml)
+        b.advance(ns)
+        b.synchronize()
+    finally:
+        _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+    assert float(a.tensor("ez").abs().max()) > 0.5
+
+
+def test_identity_promise_is_checked():
+    from simulation_b200 import _lib
+    sim = _sim_for("3_2", 128, 160, np.float32, npml=8)
+    assert sim.check_identity() == 0
+    sim.pml.gy2[40] = 0.5                       # inside the promised identity range
+    assert sim.check_identity() == 1
+
+
 def test_medium_grid_vs_oracle_fp32():
     nx, ny, npml, ns = 384, 640, 40, 160
     sim = _sim_for("3_3", nx, ny, np.float32, npml=npml)
