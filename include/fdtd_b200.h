@@ -155,6 +155,9 @@ int fdtd2d_advance(const fdtd2d_problem *p, int cur, int nsteps, const double *s
                    void *stream, int *cur_out);
 /* number of coefficient entries that violate the ident_* promise of `p` (0 = promise holds); synchronises */
 int fdtd2d_check_identity(const fdtd2d_problem *p, long long *violations);
+/* resolve (module-load) every kernel instantiation a problem of this dtype / width can launch, so that no
+ * time step pays CUDA's lazy loading */
+int fdtd2d_preload(int dtype, int ny, int lossy);
 /* largest supported tblock for a dtype / ny (0 if unsupported) */
 int fdtd2d_max_tblock(int dtype, int ny);
 

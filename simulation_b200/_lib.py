@@ -82,6 +82,7 @@ SYMBOLS = {
     "fdtd2d_incthy": (_I, [_I, _I, _I, _I, _P, _P, _P]),
     "fdtd2d_advance": (_I, [C.POINTER(Problem2D), _I, _I, C.POINTER(_D), _I, _P, C.POINTER(_I)]),
     "fdtd2d_check_identity": (_I, [C.POINTER(Problem2D), C.POINTER(C.c_longlong)]),
+    "fdtd2d_preload": (_I, [_I, _I, _I]),
     "fdtd2d_max_tblock": (_I, [_I, _I]),
     "fdtd2d_tune": (_I, [_I, _I, _I, _I, _I]),
 }

@@ -563,6 +563,26 @@ int launch_march_T(int T, MarchParams<real> &mp, bool lossy, cudaStream_t st) {
     }
 }
 
+// CUDA loads kernels lazily: the first launch of every instantiation pays a module load of several ms.
+// preload() resolves all instantiations one problem can reach (every depth, both kernels) ahead of time.
+template <typename real, int V, int T>
+void touch_T(bool lossy) {
+    cudaFuncAttributes a;
+    if (lossy) {
+        cudaFuncGetAttributes(&a, k_march<real, V, T, true, true>);
+        cudaFuncGetAttributes(&a, k_march<real, V, T, true, false>);
+    } else {
+        cudaFuncGetAttributes(&a, k_march<real, V, T, false, true>);
+        cudaFuncGetAttributes(&a, k_march<real, V, T, false, false>);
+    }
+}
+template <typename real, int V>
+void touch_V(bool lossy) {
+    touch_T<real, V, 1>(lossy); touch_T<real, V, 2>(lossy); touch_T<real, V, 3>(lossy);
+    touch_T<real, V, 4>(lossy); touch_T<real, V, 6>(lossy);
+    if constexpr (V <= 2) touch_T<real, V, 8>(lossy);
+}
+
 // vector width: widest V dividing ny (rows start V-aligned; the strip halo is rounded up to a multiple of V)
 template <typename real> int pick_v(int ny);
 template <> int pick_v<float>(int ny) { return ny % 4 == 0 ? 4 : (ny % 2 == 0 ? 2 : 1); }
@@ -677,6 +697,24 @@ int fdtd2d_check_identity(const fdtd2d_problem *q, long long *violations) {
     FDTD_CUDA(cudaMemcpy(&host, bad, sizeof(host), cudaMemcpyDeviceToHost));
     FDTD_CUDA(cudaFree(bad));
     *violations = (long long)host;
+    return FDTD_OK;
+}
+
+int fdtd2d_preload(int dtype, int ny, int lossy) {
+    if (dtype == FDTD_F32) {
+        const int V = g_force_v ? g_force_v : pick_v<float>(ny);
+        if (V == 4) touch_V<float, 4>(lossy != 0);
+        if (V >= 2) touch_V<float, 2>(lossy != 0);       // depth 8 falls back to 2-wide vectors
+        if (V == 1) touch_V<float, 1>(lossy != 0);
+    } else if (dtype == FDTD_F64) {
+        const int V = g_force_v ? g_force_v : pick_v<double>(ny);
+        if (V == 2) touch_V<double, 2>(lossy != 0);
+        touch_V<double, 1>(lossy != 0);
+    } else {
+        fdtd::set_error("fdtd2d_preload: unknown dtype %d", dtype);
+        return FDTD_EINVAL;
+    }
+    FDTD_LAUNCH_CHECK("fdtd2d_preload");
     return FDTD_OK;
 }
 

@@ -201,6 +201,7 @@ class Fdtd2D:
                 self._hxi_hist = z1(self.max_tblock * 2)
             else:
                 self.ezi = self.hxi = self.bc = self._ezi_hist = self._hxi_hist = None
+            check(lib().fdtd2d_preload(code, self.ny, int(self.lossy)), "fdtd2d_preload")
             if self.check_identity() != 0:
                 raise _lib.FdtdError("PML vectors violate the identity-coefficient promise outside the layer")
 
