@@ -329,31 +329,52 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
     for (int k = 0; k < RING - 1; ++k) fetch(k);
     int slot = 0;                                     // ring slot of the row consumed next
 
-    for (int r = r_begin; r < r_end; r += NS) {
+    auto store_row = [&](const RowSet<real, V> &O, const int ro) {
+        if (ro >= i0 && ro < i1 && col_store) {
+            VecIO<real, V>::st(p.out_dz + off_s, O.dz);
+            if (p.write_ez) VecIO<real, V>::st(p.out_ez + off_s, O.ez);
+            VecIO<real, V>::st(p.out_hx + off_s, O.hx);
+            VecIO<real, V>::st(p.out_hy + off_s, O.hy);
+            VecIO<real, V>::st(p.out_ihx + off_s, O.ihx);
+            VecIO<real, V>::st(p.out_ihy + off_s, O.ihy);
+            if (LOSSY) VecIO<real, V>::st(p.out_iz + off_s, O.iz);
+        }
+        off_s += p.ny;
+    };
+
+    if constexpr (FAST) {
+        // interior: row loop unrolled NS times, the register sets rotate through the roles (no moves)
+        for (int r = r_begin; r < r_end; r += NS) {
 #pragma unroll
-        for (int u = 0; u < NS; ++u) {
-            const int rr = r + u;                     // global row arriving at stage 0 (may overrun r_end)
-            cp_async_wait<RING - 2>();                // the oldest of the RING-1 pending rows has landed
-            take(slot, S[u]);
-            fetch(slot == 0 ? RING - 1 : slot - 1);   // refill the slot consumed one sub-iteration ago
+            for (int u = 0; u < NS; ++u) {
+                const int rr = r + u;                 // global row arriving at stage 0 (may overrun r_end)
+                cp_async_wait<RING - 2>();            // the oldest of the RING-1 pending rows has landed
+                take(slot, S[u]);
+                fetch(slot == 0 ? RING - 1 : slot - 1);   // refill the slot consumed one sub-iteration ago
+                slot = (slot + 1 == RING) ? 0 : slot + 1;
+#pragma unroll
+                for (int s = 0; s < T; ++s)
+                    march_stage<real, V, LOSSY, FAST>(p, c, S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], rr - s,
+                                                      s, jb, tf_cols, src_cols);
+                store_row(S[(u + 1) % NS], rr - T);   // the set held by the last stage: row rr-T at time t+T
+            }
+        }
+    } else {
+        // edges: compact code matters more than instruction count (this kernel is a fraction of a wave and
+        // shares the instruction cache with the interior kernel): one rolled row loop, the sets are shifted
+        // by register copies -- S[s] arrives at stage s, S[s+1] is held by it, S[T] leaves.
+#pragma unroll 1
+        for (int rr = r_begin; rr < r_end; ++rr) {
+            cp_async_wait<RING - 2>();
+            take(slot, S[0]);
+            fetch(slot == 0 ? RING - 1 : slot - 1);
             slot = (slot + 1 == RING) ? 0 : slot + 1;
 #pragma unroll
             for (int s = 0; s < T; ++s)
-                march_stage<real, V, LOSSY, FAST>(p, c, S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], rr - s, s,
-                                                  jb, tf_cols, src_cols);
-            // the set held by the last stage is now row rr-T at time t+T
-            RowSet<real, V> &O = S[(u + 1) % NS];
-            const int ro = rr - T;
-            if (ro >= i0 && ro < i1 && col_store) {
-                VecIO<real, V>::st(p.out_dz + off_s, O.dz);
-                if (p.write_ez) VecIO<real, V>::st(p.out_ez + off_s, O.ez);
-                VecIO<real, V>::st(p.out_hx + off_s, O.hx);
-                VecIO<real, V>::st(p.out_hy + off_s, O.hy);
-                VecIO<real, V>::st(p.out_ihx + off_s, O.ihx);
-                VecIO<real, V>::st(p.out_ihy + off_s, O.ihy);
-                if (LOSSY) VecIO<real, V>::st(p.out_iz + off_s, O.iz);
-            }
-            off_s += p.ny;
+                march_stage<real, V, LOSSY, FAST>(p, c, S[s], S[s + 1], rr - s, s, jb, tf_cols, src_cols);
+            store_row(S[T], rr - T);
+#pragma unroll
+            for (int k = T; k >= 1; --k) S[k] = S[k - 1];
         }
     }
     cp_async_wait<0>();
