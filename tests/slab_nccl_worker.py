@@ -1,0 +1,55 @@
+"""Worker for tests/test_gpu_slab.py: run under torch.distributed.run, one rank per GPU (NCCL).
+N-rank slab run of the fused CUDA path vs the single-device run of the same problem: bitwise equal."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from simulation_b200 import fd2d, slab, surface   # noqa: E402
+
+
+def make_source(prog, nx, ny):
+    if prog == "3_3":
+        return fd2d.IncidentWave(surface.Gaussian(20, 8.0))
+    return fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6), hard=True)
+
+
+def main():
+    prog, nx, ny, npml, ns, tblock = sys.argv[1], *[int(x) for x in sys.argv[2:7]]
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    rank = dist.get_rank()
+    rng = np.random.default_rng(11)
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    s = slab.SlabFdtd2D(nx, ny, npml, np.float32, tblock=tblock, source=make_source(prog, nx, ny), naz=naz)
+    s.advance(7)                       # ragged split of the step count across advance() calls
+    s.advance(ns - 7)
+    s.synchronize()
+    ok = True
+    fields = {name: s.gather(name) for name in ("dz", "ez", "hx", "hy", "ihx", "ihy")}
+    if rank == 0:
+        one = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=make_source(prog, nx, ny), naz=naz)
+        one.advance(ns)
+        for name, whole in fields.items():
+            ref = one.get(name)
+            if whole.tobytes() != ref.tobytes():
+                bad = np.argwhere(whole != ref)
+                print(f"MISMATCH {name}: {len(bad)} cells, first {bad[:4].tolist()}", flush=True)
+                ok = False
+        assert np.abs(fields["ez"]).max() > 1e-3
+        print(f"slab x{dist.get_world_size()} {prog} {nx}x{ny} ns={ns} T={tblock}: {'OK' if ok else 'FAIL'}, "
+              f"{s.exchanges} exchanges", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,35 @@
+"""Multi-GPU parity of the slab decomposition (needs >= 2 GPUs; skipped on a single-GPU box):
+N ranks over NCCL == one device, bit for bit, on every array."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("prog,nx,ny,npml,ns,tblock", [
+    ("3_2", 1024, 1536, 40, 61, 6),
+    ("3_3", 900, 1200, 24, 80, 4),       # TFSF: every rank replicates the incident line
+    ("3_2", 517, 640, 16, 33, 1),        # uneven split, exchange every step
+])
+def test_slab_equals_single_device(prog, nx, ny, npml, ns, tblock):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = min(n, 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "slab_nccl_worker.py"), prog, str(nx), str(ny), str(npml), str(ns), str(tblock)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
