@@ -23,14 +23,22 @@ def main():
     ap.add_argument("--chunks", default="0,256,1024")
     ap.add_argument("--rings", default="4")
     ap.add_argument("--careful", type=int, default=0)
+    ap.add_argument("--prog", default="3_2")
+    ap.add_argument("--npml", type=int, default=80)
     a = ap.parse_args()
     n = a.size
-    sim = fd2d.Fdtd2D(n, n, 80, np.float32, source=fd2d.PointSource(n // 2 - 5, n // 2 - 5, surface.Sinusoid(1500e6)))
+    if a.prog == "3_2":
+        sim = fd2d.Fdtd2D(n, n, a.npml, np.float32, source=fd2d.PointSource(n // 2 - 5, n // 2 - 5, surface.Sinusoid(1500e6)))
+    elif a.prog == "3_3":
+        sim = fd2d.Fdtd2D(n, n, a.npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)))
+    else:
+        naz, nbz = surface.dielectric_cylinder(n, n, a.npml, int(n * 0.15), surface.DT, 30.0, 0.30, np.float32)
+        sim = fd2d.Fdtd2D(n, n, a.npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=naz, nbz=nbz)
     lib = _lib.lib()
     ints = lambda s: [int(x) for x in s.split(",")]
     for T, V, W, C, R in itertools.product(ints(a.ts), ints(a.vs), ints(a.warps), ints(a.chunks), ints(a.rings)):
         lib.fdtd2d_tune(V, C, W, R, a.careful)
-        steps = (a.steps // T) * T
+        steps = max(1, a.steps // T) * T
         sim.advance(2 * T, tblock=T)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
