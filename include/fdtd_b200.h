@@ -147,7 +147,8 @@ typedef struct {
 } fdtd2d_problem;
 
 /* Advance nsteps full time steps (reference order: ezinct, dfield+source, inctdz, efield, hxinct, hfield,
- * incthx, incthy -- fd2d/python/fd2d_3_4.py:268-277) from state set `cur`, tblock steps per kernel pass.
+ * incthx, incthy -- fd2d/python/fd2d_3_4.py:268-277) from state set `cur`, at most tblock (1..8) steps per kernel
+ * pass; tblock = 0 lets the library choose depth, vector width and chunking by grid size.
  * Rows [row_lo-g, row_hi+g) with g = nsteps must be present and current in set `cur` (clipped to the
  * grid); single device: row_lo=row_base=0, row_hi=rows_alloc=nx and any nsteps is allowed.
  * src: HOST float64 table, one sample per step.  *cur_out = set holding the result. */

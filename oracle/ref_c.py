@@ -64,3 +64,23 @@ def step_3_3(lib, t, g, src_value):
     lib.hfield(nx, ny, C.byref(ps), _p(g.ez), _p(g.ihx), _p(g.ihy), _p(g.hx), _p(g.hy))
     lib.incthx(nx, ny, n, _p(g.ezi), _p(g.hx))
     lib.incthy(nx, ny, n, _p(g.ezi), _p(g.hy))
+
+
+class CMedium(C.Structure):        # fd2d/clang/test_3_4.c: typedef struct { float *naz, *nbz; } medium;
+    _fields_ = [("naz", FP), ("nbz", FP)]
+
+
+def step_3_4(lib, t, g, src_value):
+    """One step of the reference C program 3_4 (TFSF + lossy medium, DFT skipped) on an oracle Grid2D (fp32)."""
+    nx, ny, n = g.nx, g.ny, g.npml
+    ps = pml_struct(g.pml)
+    md = CMedium(_p(g.naz), _p(g.nbz))
+    lib.ezinct(ny, _p(g.ezi), _p(g.hxi), _p(g.bc))
+    lib.dfield(C.c_int(int(t)), nx, ny, C.byref(ps), _p(g.ezi), _p(g.dz), _p(g.hx), _p(g.hy))
+    g.ezi[3] = src_value
+    lib.inctdz(nx, ny, n, _p(g.hxi), _p(g.dz))
+    lib.efield(nx, ny, C.byref(md), _p(g.dz), _p(g.iz), _p(g.ez))
+    lib.hxinct(ny, _p(g.ezi), _p(g.hxi))
+    lib.hfield(nx, ny, C.byref(ps), _p(g.ez), _p(g.ihx), _p(g.ihy), _p(g.hx), _p(g.hy))
+    lib.incthx(nx, ny, n, _p(g.ezi), _p(g.hx))
+    lib.incthy(nx, ny, n, _p(g.ezi), _p(g.hy))

@@ -608,9 +608,34 @@ template <typename real> int pick_v(int ny);
 template <> int pick_v<float>(int ny) { return ny % 4 == 0 ? 4 : (ny % 2 == 0 ? 2 : 1); }
 template <> int pick_v<double>(int ny) { return ny % 2 == 0 ? 2 : 1; }
 
+// Launch shape by grid size (cells stored on this device), from the sweeps in profiles/r1_sweep_grid_sizes_3_2.txt:
+// small grids live in L2 and need many short warps (narrow vectors, shallow blocking, 16-row chunks); big grids
+// are HBM-bound and want 4-wide vectors, 6 steps per pass and 128-row chunks.
+struct Plan { int V, T, chunk; };
+
+template <typename real>
+Plan choose_plan(long cells, int ny, bool lossy) {
+    Plan p;
+    if (sizeof(real) == 4) {
+        if (cells < 1500000L)        p = {1, 4, 16};
+        else if (cells < 6000000L)   p = {2, 4, 16};
+        else if (cells < 24000000L)  p = {2, 6, 64};
+        else if (cells < 100000000L) p = {2, 6, 128};
+        else                         p = {lossy ? 2 : 4, 6, 128};   // 7 row sets x 4 columns x 9 lossy fields spill
+    } else {
+        if (cells < 3000000L)        p = {1, 4, 16};
+        else if (cells < 24000000L)  p = {1, 4, 64};
+        else                         p = {2, 4, 128};
+    }
+    while (p.V > 1 && ny % p.V != 0) p.V >>= 1;
+    return p;
+}
+
 template <typename real>
 int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int tblock, cudaStream_t st,
             int *cur_out) {
+    const Plan plan = choose_plan<real>((long)q->rows_alloc * q->ny, q->ny, (q->flags & FDTD_LOSSY) != 0);
+    if (tblock <= 0) tblock = plan.T;
     const bool lossy = (q->flags & FDTD_LOSSY) != 0, tfsf = (q->flags & FDTD_TFSF) != 0;
     int done = 0;
     while (done < nsteps) {
@@ -647,7 +672,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.src_i = tfsf ? -1 : q->src_i; mp.src_j = q->src_j; mp.src_hard = q->src_hard;
         for (int s = 0; s < TMAX; ++s) mp.src[s] = (src && s < T) ? src[done + s] : 0.0;
 
-        int V = g_force_v ? g_force_v : pick_v<real>(q->ny);
+        int V = g_force_v ? g_force_v : plan.V;
         if (q->ny % V != 0 || (sizeof(real) == 8 && V == 4)) V = 1;
         if (T == 8 && V == 4) V = 2;                    // 9 register row sets of 4 columns do not fit
         if (T == 8 && sizeof(real) == 8) V = 1;         // ... nor do 9 sets of 2 doubles
@@ -656,13 +681,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.nstrips = (q->ny + use - 1) / use;
         const int rows = mp.out_hi - mp.out_lo;
         int chunk = g_chunk_rows;
-        if (chunk <= 0) {
-            // many short chunks keep the last wave full (8 resident warps per SM): aim at >= 4 waves of warps,
-            // with the 2T-row warm-up/drain recompute between ~6 % (32T rows, measured optimum) and ~12 % (16T rows)
-            const long want = 4L * fdtd::sm_count() * 8;
-            chunk = (int)((long)rows * mp.nstrips / want);
-            chunk = min(max(chunk, 16 * T), 32 * T);
-        }
+        if (chunk <= 0) chunk = max(plan.chunk, 4 * T);   // at most ~50 % warm-up/drain recompute on shallow grids
         chunk = max(1, min(chunk, rows));
         mp.chunk_rows = chunk;
         mp.nchunks = (rows + chunk - 1) / chunk;
@@ -721,14 +740,13 @@ int fdtd2d_check_identity(const fdtd2d_problem *q, long long *violations) {
 }
 
 int fdtd2d_preload(int dtype, int ny, int lossy) {
+    (void)ny;
     if (dtype == FDTD_F32) {
-        const int V = g_force_v ? g_force_v : pick_v<float>(ny);
-        if (V == 4) touch_V<float, 4>(lossy != 0);
-        if (V >= 2) touch_V<float, 2>(lossy != 0);       // depth 8 falls back to 2-wide vectors
-        if (V == 1) touch_V<float, 1>(lossy != 0);
+        touch_V<float, 4>(lossy != 0);
+        touch_V<float, 2>(lossy != 0);
+        touch_V<float, 1>(lossy != 0);
     } else if (dtype == FDTD_F64) {
-        const int V = g_force_v ? g_force_v : pick_v<double>(ny);
-        if (V == 2) touch_V<double, 2>(lossy != 0);
+        touch_V<double, 2>(lossy != 0);
         touch_V<double, 1>(lossy != 0);
     } else {
         fdtd::set_error("fdtd2d_preload: unknown dtype %d", dtype);
@@ -758,7 +776,7 @@ int fdtd2d_advance(const fdtd2d_problem *q, int cur, int nsteps, const double *s
     FDTD_REQUIRE(q && cur_out, "fdtd2d_advance: null problem / cur_out");
     FDTD_REQUIRE(cur == 0 || cur == 1, "fdtd2d_advance: cur must be 0 or 1");
     FDTD_REQUIRE(q->nx >= 2 && q->ny >= 2, "fdtd2d_advance: grid %dx%d too small", q->nx, q->ny);
-    FDTD_REQUIRE(tblock >= 1 && tblock <= 8, "fdtd2d_advance: tblock %d outside [1, 8]", tblock);
+    FDTD_REQUIRE(tblock >= 0 && tblock <= 8, "fdtd2d_advance: tblock %d outside [0, 8] (0 = choose by grid size)", tblock);
     FDTD_REQUIRE(nsteps >= 0, "fdtd2d_advance: nsteps < 0");
     FDTD_REQUIRE(q->row_lo >= 0 && q->row_hi <= q->nx && q->row_lo < q->row_hi, "fdtd2d_advance: bad owned rows [%d,%d)", q->row_lo, q->row_hi);
     FDTD_REQUIRE(q->row_base <= q->row_lo && q->row_base + q->rows_alloc >= q->row_hi, "fdtd2d_advance: owned rows outside the stored rows");

@@ -182,8 +182,7 @@ class Fdtd2D:
         self.t = 0                                        # steps taken so far (next step is t+1)
         code = _lib.dtype_code(self.np_dtype)
         self.max_tblock = lib().fdtd2d_max_tblock(code, self.ny)
-        # measured optimum on B200: 6 steps per pass in fp32 (register row sets still fit with 4-wide vectors)
-        self.tblock = int(tblock) if tblock else min(self.max_tblock, 6 if self.np_dtype == np.float32 else 4)
+        self.tblock = int(tblock) if tblock else 0       # 0: the library picks depth / vector width / chunking by grid size
 
         with torch.cuda.device(self.device):
             shape = (self.rows_alloc, self.ny)
@@ -290,7 +289,7 @@ class Fdtd2D:
         the slab driver between ghost exchanges) and leaves ``ez`` stale until a later non-lazy ``advance``."""
         if nsteps <= 0:
             return
-        tb = int(tblock or self.tblock)
+        tb = int(tblock if tblock is not None else self.tblock)
         if tb > self.max_tblock:
             raise _lib.FdtdError(f"tblock {tb} exceeds the deepest supported time block {self.max_tblock}")
         src = None

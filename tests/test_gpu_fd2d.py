@@ -259,6 +259,36 @@ def test_full_size_linearity_32768():
     assert float(a.tensor("ez").abs().max()) > 0.0
 
 
+def test_baseline_config_4_vs_reference_c_openmp():
+    """BASELINE config 4 at full size: 4096x4096 fp32, npml=80, TFSF Gaussian, lossy dielectric cylinder
+    (eps_r=30, sigma=0.3, radius 6 m -> 599 cells), 300 steps -- the fused GPU path against the REFERENCE's own
+    C/OpenMP step functions (oracle/_ref, fd2d/clang/test_3_4.c) on identical coefficient arrays.  The two differ
+    only by subnormal-born rounding (see tests/test_oracle_vs_ref_c.py), far inside the 1e-5-of-peak tolerance."""
+    import os
+    from oracle import ref_c
+    from simulation_b200 import fd2d, surface
+    if not ref_c.available("3_4"):
+        pytest.skip("oracle/_ref not built")
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    n, npml, ns = 4096, 80, 300
+    rgrid = int(6.0 / 0.01 - 1)
+    naz, nbz = surface.dielectric_cylinder(n, n, npml, rgrid, surface.DT, 30.0, 0.30, np.float32)
+    sim = fd2d.Fdtd2D(n, n, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=naz, nbz=nbz)
+    sim.advance(ns)
+    g = orc.Grid2D(n, n, npml, np.float32, tfsf=True, lossy=True, naz=naz.copy(), nbz=nbz.copy())
+    src = orc.source_table("gaussian", ns, t0=20, spread=8.0)
+    lib = ref_c.load("3_4")
+    for k, t in enumerate(orc.step_indices(ns)):
+        ref_c.step_3_4(lib, t, g, src[k])
+    peak = float(np.abs(g.ez).max())
+    assert peak > 0.5
+    for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy"):
+        got, want = sim.get(name), getattr(g, name)
+        err = float(np.abs(got.astype(np.float64) - want).max())
+        assert err <= 1e-5 * peak, (name, err)
+        assert err <= 1e-12, (name, err)          # in fact: subnormal-level differences only
+
+
 # ------------------------------------------------------------------ error behaviour of the boundary
 def test_errors_are_reported_not_swallowed():
     from simulation_b200 import _lib, fd2d, surface
