@@ -82,7 +82,7 @@ def test_advance_matches_oracle(prog, nx, ny, npml, ns, tblock, dtype):
 @pytest.mark.parametrize("force_v", [1, 2, 4])
 @pytest.mark.parametrize("chunk_rows,tblock,side", [(0, 6, 0), (5, 4, 0), (16, 6, 2), (40, 8, 0)])
 @pytest.mark.parametrize("prog,nx,ny,npml", [("3_3", 150, 284, 9), ("3_2", 131, 260, 8), ("3_4", 97, 300, 8),
-                                             ("3_2", 420, 1100, 8), ("3_3", 400, 1000, 12)])
+                                             ("3_2", 420, 1100, 8), ("3_3", 400, 1000, 12), ("3_4", 380, 1040, 10)])
 def test_advance_vector_widths_and_chunking(prog, nx, ny, npml, force_v, chunk_rows, tblock, side):
     """Wide enough for several strips per vector width, several row chunks, ragged edges; the two big
     grids have a true interior, so the interior (identity-coefficient) kernel and the edge kernel both run,
