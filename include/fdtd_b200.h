@@ -32,6 +32,8 @@ extern "C" {
 #define FDTD_F32 0
 #define FDTD_F64 1
 
+#define FDTD_MAX_FREQS 8       /* frequencies per running-DFT call */
+
 #define FDTD_OK            0
 #define FDTD_EINVAL       -1   /* bad argument (size, alignment, dtype, null pointer) */
 #define FDTD_ECUDA        -2   /* a CUDA runtime call or kernel launch failed */
@@ -86,6 +88,13 @@ int fdtd1d_dxfield(int dtype, int nx, void *dx, const void *hy, const fdtd_sourc
 int fdtd1d_exfield_flux(int dtype, int nx, const fdtd_medium1d *md, const void *dx, void *ix, void *sx,
                         void *ex, void *stream);
 
+/* running DFT: r_pt[n,:] += cos_n*ex[:], i_pt[n,:] -= sin_n*ex[:], and r_in/i_in from ex[sample_index] (10 in the
+ * reference).  cosv/sinv: HOST float64 arrays of nf phase factors cos/sin(2*pi*f_n*dt*t), evaluated by the caller
+ * with the reference's expression; products and sums are formed in float64 and rounded into the array type (the
+ * numpy semantics for float32 arrays).  replaces fourier of fd1d/cuda/test_2_3.cu:35-48 (numpy fd1d_2_2.py:65-71) */
+int fdtd1d_fourier(int dtype, int nf, int nx, const double *cosv, const double *sinv, const void *ex,
+                   int sample_index, const fdtd_ftrans *ft, void *stream);
+
 /* --------------------------------------------------------------------- 1D: fused time-blocked path */
 typedef struct {
     int dtype, nx, flags;              /* FDTD_ABC | FDTD_FLUX | FDTD_DEBYE */
@@ -113,6 +122,11 @@ int fdtd2d_inctdz(int dtype, int nx, int ny, int npml, const void *hxi, void *dz
 /* replaces efield of fd2d/cuda/test_3_4.cu:99-109 / test_3_3.cu:69-78; iz == NULL: ez = naz*dz */
 int fdtd2d_efield(int dtype, int nx, int ny, const fdtd_medium2d *md, const void *dz, void *iz, void *ez,
                   void *stream);
+/* running DFT of Ez (r_pt/i_pt: nf x nx x ny) and of the source sample ezi[sample_index] (6 in the reference);
+ * phase factors as for fdtd1d_fourier.  replaces fourier of fd2d/cuda/test_3_4.cu:45-60
+ * (numba fd2d/python/fd2d_3_4.py:89-99).  ezi == NULL: skip r_in / i_in. */
+int fdtd2d_fourier(int dtype, int nf, int nx, int ny, const double *cosv, const double *sinv, const void *ezi,
+                   int sample_index, const void *ez, const fdtd_ftrans *ft, void *stream);
 /* replaces hxinct of fd2d/cuda/test_3_4.cu:112-118 */
 int fdtd2d_hxinct(int dtype, int ny, const void *ezi, void *hxi, void *stream);
 /* replaces hfield of fd2d/cuda/test_3_4.cu:121-133 (numpy fd2d_3_3.py:91-98) */

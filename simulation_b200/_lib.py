@@ -36,6 +36,10 @@ class Source(C.Structure):
     _fields_ = [("target", C.c_void_p), ("index", C.c_longlong), ("hard", C.c_int), ("value", C.c_double)]
 
 
+class FTrans(C.Structure):
+    _fields_ = [("r_pt", C.c_void_p), ("i_pt", C.c_void_p), ("r_in", C.c_void_p), ("i_in", C.c_void_p)]
+
+
 class Problem1D(C.Structure):
     _fields_ = [("dtype", C.c_int), ("nx", C.c_int), ("flags", C.c_int),
                 ("ca", C.c_void_p), ("cb", C.c_void_p), ("md", Medium1D),
@@ -71,6 +75,8 @@ SYMBOLS = {
     "fdtd1d_hyfield": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "fdtd1d_dxfield": (_I, [_I, _I, _P, _P, C.POINTER(Source), _P]),
     "fdtd1d_exfield_flux": (_I, [_I, _I, C.POINTER(Medium1D), _P, _P, _P, _P, _P]),
+    "fdtd1d_fourier": (_I, [_I, _I, _I, C.POINTER(_D), C.POINTER(_D), _P, _I, C.POINTER(FTrans), _P]),
+    "fdtd2d_fourier": (_I, [_I, _I, _I, _I, C.POINTER(_D), C.POINTER(_D), _P, _I, _P, C.POINTER(FTrans), _P]),
     "fdtd1d_advance": (_I, [C.POINTER(Problem1D), _I, _I, C.POINTER(_D), _I, _P, C.POINTER(_I)]),
     "fdtd2d_ezinct": (_I, [_I, _I, _P, _P, _P, _P]),
     "fdtd2d_dfield": (_I, [_I, _I, _I, C.POINTER(PmlLayer), _P, _P, _P, C.POINTER(Source), _P]),

@@ -34,6 +34,8 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();   // cached SM count of the current device
+int launch_fourier(int dtype, int nf, size_t ncells, const double *cosv, const double *sinv, const void *field,
+                   const void *sample, const fdtd_ftrans *ft, cudaStream_t st);
 
 // Source injection with the numpy semantics: hard = rounded store, soft = float64 add then one rounding.
 template <typename real>

@@ -299,6 +299,14 @@ int fdtd1d_hyfield(int dtype, int nx, void *ex, void *hy, void *bc, int abc, voi
     return FDTD_OK;
 }
 
+int fdtd1d_fourier(int dtype, int nf, int nx, const double *cosv, const double *sinv, const void *ex, int sample_index,
+                   const fdtd_ftrans *ft, void *stream) {
+    FDTD_REQUIRE(nx >= 1 && sample_index >= 0 && sample_index < nx, "fdtd1d_fourier: bad nx=%d / sample index %d", nx, sample_index);
+    const size_t esz = dtype == FDTD_F64 ? 8 : 4;
+    const void *sample = ex ? (const char *)ex + esz * (size_t)sample_index : nullptr;
+    return fdtd::launch_fourier(dtype, nf, (size_t)nx, cosv, sinv, ex, sample, ft, fdtd::as_stream(stream));
+}
+
 int fdtd1d_advance(const fdtd1d_problem *q, int cur, int nsteps, const double *src, int tblock, void *stream,
                    int *cur_out) {
     FDTD_REQUIRE(q && cur_out, "fdtd1d_advance: null problem / cur_out");

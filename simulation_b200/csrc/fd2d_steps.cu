@@ -119,6 +119,31 @@ __global__ void k_incthy(int nx, int ny, int npml, const real *ezi, real *hy) {
     }
 }
 
+// running DFT of Ez at every cell: r_pt[n] += cos_n * ez, i_pt[n] -= sin_n * ez, evaluated in float64 and rounded
+// into the array type (what numpy / numba do for float32 arrays: the phase factors are float64).
+struct Phases { double c[FDTD_MAX_FREQS], s[FDTD_MAX_FREQS]; };
+
+template <typename real>
+__global__ void k_fourier(int nf, size_t ncells, Phases ph, const real *ez, real *r_pt, real *i_pt) {
+    const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ncells) return;
+    const double e = static_cast<double>(ez[n]);
+    for (int f = 0; f < nf; ++f) {
+        const size_t m = (size_t)f * ncells + n;
+        r_pt[m] = static_cast<real>(static_cast<double>(r_pt[m]) + ph.c[f] * e);
+        i_pt[m] = static_cast<real>(static_cast<double>(i_pt[m]) - ph.s[f] * e);
+    }
+}
+
+template <typename real>
+__global__ void k_fourier_source(int nf, Phases ph, const real *sample, real *r_in, real *i_in) {
+    const int f = threadIdx.x;
+    if (f >= nf) return;
+    const double e = static_cast<double>(*sample);
+    r_in[f] = static_cast<real>(static_cast<double>(r_in[f]) + ph.c[f] * e);
+    i_in[f] = static_cast<real>(static_cast<double>(i_in[f]) - ph.s[f] * e);
+}
+
 inline dim3 grid2d(int nx, int ny) { return dim3((ny + BX - 1) / BX, (nx + BY - 1) / BY); }
 
 template <typename real>
@@ -135,6 +160,28 @@ bool tfsf_geometry_ok(int nx, int ny, int npml) { return npml >= 2 && 2 * npml <
 }  // namespace
 
 namespace fdtd {
+// shared by the 1D and 2D entry points: `ncells` field samples, source sample at sample[0]
+int launch_fourier(int dtype, int nf, size_t ncells, const double *cosv, const double *sinv, const void *field,
+                   const void *sample, const fdtd_ftrans *ft, cudaStream_t st) {
+    FDTD_REQUIRE(nf >= 1 && nf <= FDTD_MAX_FREQS, "fourier: nf=%d outside [1, %d]", nf, FDTD_MAX_FREQS);
+    FDTD_REQUIRE(cosv && sinv && field && ft && ft->r_pt && ft->i_pt, "fourier: null argument");
+    Phases ph;
+    for (int f = 0; f < FDTD_MAX_FREQS; ++f) { ph.c[f] = f < nf ? cosv[f] : 0.0; ph.s[f] = f < nf ? sinv[f] : 0.0; }
+    const unsigned blocks = (unsigned)((ncells + 255) / 256);
+    if (dtype == FDTD_F32) {
+        k_fourier<float><<<blocks, 256, 0, st>>>(nf, ncells, ph, (const float *)field, (float *)ft->r_pt, (float *)ft->i_pt);
+        if (sample && ft->r_in && ft->i_in) k_fourier_source<float><<<1, 32, 0, st>>>(nf, ph, (const float *)sample, (float *)ft->r_in, (float *)ft->i_in);
+    } else if (dtype == FDTD_F64) {
+        k_fourier<double><<<blocks, 256, 0, st>>>(nf, ncells, ph, (const double *)field, (double *)ft->r_pt, (double *)ft->i_pt);
+        if (sample && ft->r_in && ft->i_in) k_fourier_source<double><<<1, 32, 0, st>>>(nf, ph, (const double *)sample, (double *)ft->r_in, (double *)ft->i_in);
+    } else {
+        set_error("fourier: unknown dtype %d", dtype);
+        return FDTD_EINVAL;
+    }
+    FDTD_LAUNCH_CHECK("k_fourier");
+    return FDTD_OK;
+}
+
 int launch_source(int dtype, const fdtd_source *src, cudaStream_t st) {
     return dtype == FDTD_F32 ? apply_source<float>(src, st) : apply_source<double>(src, st);
 }
@@ -189,6 +236,15 @@ int fdtd2d_efield(int dtype, int nx, int ny, const fdtd_medium2d *md, const void
     }
     FDTD_LAUNCH_CHECK("k_efield");
     return FDTD_OK;
+}
+
+int fdtd2d_fourier(int dtype, int nf, int nx, int ny, const double *cosv, const double *sinv, const void *ezi,
+                   int sample_index, const void *ez, const fdtd_ftrans *ft, void *stream) {
+    FDTD_REQUIRE(nx >= 1 && ny >= 1, "fdtd2d_fourier: bad grid %dx%d", nx, ny);
+    FDTD_REQUIRE(!ezi || (sample_index >= 0 && sample_index < ny), "fdtd2d_fourier: sample index %d outside the incident line", sample_index);
+    const size_t esz = dtype == FDTD_F64 ? 8 : 4;
+    const void *sample = ezi ? (const char *)ezi + esz * (size_t)sample_index : nullptr;
+    return fdtd::launch_fourier(dtype, nf, (size_t)nx * ny, cosv, sinv, ez, sample, ft, fdtd::as_stream(stream));
 }
 
 int fdtd2d_hfield(int dtype, int nx, int ny, const fdtd_pmlayer *pml, const void *ez, void *ihx, void *ihy, void *hx,

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib
-from .fd2d import _TORCH_DT, _code, _ptr, _require_cuda, _stream
+from .fd2d import _NP_DT, _TORCH_DT, _code, _phases, _ptr, _require_cuda, _stream, ftrans
 
 
 class medium(NamedTuple):
@@ -64,6 +64,16 @@ def exfield_flux(nx: int, md: medium, dx, ix, ex, sx=None) -> None:
           "exfield_flux")
 
 
+def fourier(t: int, nf: int, nx: int, dt: float, freq, ex, ft: ftrans) -> None:
+    """Running DFT of Ex and of the source sample ``ex[10]`` (fd1d/program/fd1d_2_2.py:65-71, same argument order)."""
+    _require_cuda(ex, *ft)
+    c, s = _phases(freq, dt, t, True, _NP_DT[ex.dtype])
+    fs = ft.as_struct()
+    D = C.POINTER(C.c_double)
+    check(lib().fdtd1d_fourier(_code(ex), nf, nx, c.ctypes.data_as(D), s.ctypes.data_as(D), _ptr(ex), 10, C.byref(fs),
+                               _stream()), "fourier")
+
+
 def hyfield(nx: int, ex, hy, bc=None) -> None:
     """ABC (when ``bc`` is given) then the H update."""
     _require_cuda(ex, hy, bc)
@@ -76,7 +86,8 @@ class Fdtd1D:
     FIELDS = ("ex", "hy", "dx", "ix", "sx")
 
     def __init__(self, nx: int, dtype=np.float32, *, form: str = "fdtd", abc: bool = True, source: Optional[LineSource] = None,
-                 ca=None, cb=None, nax=None, nbx=None, ncx=None, ndx=None, device=None, tblock: int = 32):
+                 ca=None, cb=None, nax=None, nbx=None, ncx=None, ndx=None, device=None, tblock: int = 32, freqs=None,
+                 dt: float = 0.01 / 6e8):
         if not torch.cuda.is_available():
             raise _lib.FdtdError("Fdtd1D needs a CUDA device: the product has no CPU path")
         lib()
@@ -103,6 +114,13 @@ class Fdtd1D:
         self._sets = [{n: z(self.nx) for n in names} for _ in range(2)]
         self._bc = [z(4), z(4)]
         self._cur = 0
+        self.freqs, self.dt = (None if freqs is None else np.asarray(freqs, dtype=self.np_dtype)), float(dt)
+        if self.freqs is not None:
+            nf = len(self.freqs)
+            zz = lambda *shape: torch.zeros(shape, dtype=self.dtype, device=self.device)
+            self.ft = ftrans(zz(nf, self.nx), zz(nf, self.nx), zz(nf, 1), zz(nf, 1))
+        else:
+            self.ft = None
         if source is not None and source.field == "dx" and form != "flux":
             raise _lib.FdtdError("a dx source needs the flux form")
 
@@ -110,6 +128,8 @@ class Fdtd1D:
         return self._bc[self._cur] if name == "bc" else self._sets[self._cur][name]
 
     def get(self, name: str) -> np.ndarray:
+        if name in ("r_pt", "i_pt", "r_in", "i_in"):
+            return getattr(self.ft, name).cpu().numpy()
         return self.tensor(name).cpu().numpy()
 
     def set(self, name: str, host) -> None:
@@ -140,6 +160,11 @@ class Fdtd1D:
     def advance(self, nsteps: int, tblock: Optional[int] = None) -> None:
         if nsteps <= 0:
             return
+        if self.ft is not None:
+            # the DFT samples Ex between the E update and the ABC of every step (fd1d_2_2.py:138-142): unfused steps
+            for _ in range(int(nsteps)):
+                self.step()
+            return
         src = None
         if self.source is not None:
             src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)
@@ -163,6 +188,8 @@ class Fdtd1D:
             else:
                 dxfield(t, self.nx, s["dx"], s["hy"], source=self.source)
                 exfield_flux(self.nx, self.md, s["dx"], s["ix"], s["ex"], s.get("sx"))
+            if self.ft is not None:
+                fourier(t, len(self.freqs), self.nx, self.dt, self.freqs, s["ex"], self.ft)
             hyfield(self.nx, s["ex"], s["hy"], bc)
         self.t = t
 

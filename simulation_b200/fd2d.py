@@ -23,6 +23,7 @@ from . import _lib, surface
 from ._lib import check, lib
 
 _TORCH_DT = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+_NP_DT = {torch.float32: np.float32, torch.float64: np.float64}
 FIELD_NAMES = ("dz", "ez", "hx", "hy", "ihx", "ihy", "iz")
 
 
@@ -70,6 +71,42 @@ class pmlayer(NamedTuple):
 class medium(NamedTuple):
     naz: torch.Tensor
     nbz: Optional[torch.Tensor] = None
+
+
+class ftrans(NamedTuple):
+    """Running-DFT accumulators, reference field order (fd2d/python/fd2d_3_4.py:72-75)."""
+    r_pt: torch.Tensor
+    i_pt: torch.Tensor
+    r_in: torch.Tensor
+    i_in: torch.Tensor
+
+    def as_struct(self) -> _lib.FTrans:
+        return _lib.FTrans(*[t.data_ptr() for t in self])
+
+
+def _phases(freq, dt, t, numpy_style, np_dtype):
+    """float64 phase factors cos/sin(2*pi*f*dt*t) evaluated the way the reference evaluates them: the numpy
+    programs (fd1d_2_2.py:68) multiply in the array dtype until the np.int32 step counter promotes to float64;
+    the numba program (fd2d_3_4.py:94) widens freq[n] to float64 first."""
+    t = np.int32(t)
+    if numpy_style:
+        f = np.asarray(freq, dtype=np_dtype).reshape(-1, 1)
+        arg = 2 * np.pi * f * dt * t
+        return (np.ascontiguousarray(np.cos(arg).astype(np.float64).ravel()),
+                np.ascontiguousarray(np.sin(arg).astype(np.float64).ravel()))
+    f = np.asarray(freq, dtype=np_dtype)
+    arg = np.array([2 * np.pi * np.float64(x) * dt * t for x in f], dtype=np.float64)
+    return np.cos(arg), np.sin(arg)
+
+
+def fourier(t: int, nf: int, nx: int, ny: int, dt: float, freq, ezi, ez, ft: ftrans) -> None:
+    """Running DFT of Ez and of the source sample ``ezi[6]`` (reference argument order)."""
+    _require_cuda(ez, ezi, *ft)
+    c, s = _phases(freq, dt, t, False, _NP_DT[ez.dtype])
+    fs = ft.as_struct()
+    D = C.POINTER(C.c_double)
+    check(lib().fdtd2d_fourier(_code(ez), nf, nx, ny, c.ctypes.data_as(D), s.ctypes.data_as(D), _ptr(ezi), 6, _ptr(ez),
+                               C.byref(fs), _stream()), "fourier")
 
 
 def pmlparam(nx: int, ny: int, npml: int, dtype=np.float32, device=None) -> pmlayer:
@@ -164,7 +201,7 @@ class Fdtd2D:
     """
 
     def __init__(self, nx: int, ny: int, npml: int = 0, dtype=np.float32, *, source=None, naz=None, nbz=None,
-                 device=None, tblock: Optional[int] = None, rows=None, ghost: int = 0):
+                 device=None, tblock: Optional[int] = None, rows=None, ghost: int = 0, freqs=None, dt: float = surface.DT):
         if not torch.cuda.is_available():
             raise _lib.FdtdError("Fdtd2D needs a CUDA device: the product has no CPU path")
         lib()
@@ -203,6 +240,14 @@ class Fdtd2D:
             check(lib().fdtd2d_preload(code, self.ny, int(self.lossy)), "fdtd2d_preload")
             if self.check_identity() != 0:
                 raise _lib.FdtdError("PML vectors violate the identity-coefficient promise outside the layer")
+            # running DFT (program 3_4): accumulators over the stored rows, updated after every step
+            self.freqs, self.dt = (None if freqs is None else np.asarray(freqs, dtype=self.np_dtype)), float(dt)
+            if self.freqs is not None:
+                nf = len(self.freqs)
+                z = lambda *shape: torch.zeros(shape, dtype=self.dtype, device=self.device)
+                self.ft = ftrans(z(nf, self.rows_alloc, self.ny), z(nf, self.rows_alloc, self.ny), z(nf), z(nf))
+            else:
+                self.ft = None
 
     # ---- array access -----------------------------------------------------------------------------
     def _to_dev_rows(self, host, fill):
@@ -230,6 +275,11 @@ class Fdtd2D:
     def get(self, name: str) -> np.ndarray:
         if name in ("ezi", "hxi", "bc"):
             return getattr(self, name).cpu().numpy()
+        if name in ("r_pt", "i_pt"):
+            o = self.row_lo - self.row_base
+            return getattr(self.ft, name)[:, o:o + (self.row_hi - self.row_lo)].cpu().numpy()
+        if name in ("r_in", "i_in"):
+            return getattr(self.ft, name).cpu().numpy()
         return self.tensor(name).cpu().numpy()
 
     def set(self, name: str, host) -> None:
@@ -289,6 +339,20 @@ class Fdtd2D:
         the slab driver between ghost exchanges) and leaves ``ez`` stale until a later non-lazy ``advance``."""
         if nsteps <= 0:
             return
+        if self.ft is not None:
+            # the DFT samples Ez after EVERY step: one fused single-step pass + the fourier kernel per step
+            for _ in range(int(nsteps)):
+                self._advance_fused(1, 1, False)
+                self._fourier(self.t)
+            return
+        self._advance_fused(int(nsteps), tblock, lazy_ez)
+
+    def _fourier(self, t: int) -> None:
+        with torch.cuda.device(self.device):
+            fourier(t, len(self.freqs), self.rows_alloc, self.ny, self.dt, self.freqs, self.ezi,
+                    self.tensor("ez", stored=True), self.ft)
+
+    def _advance_fused(self, nsteps: int, tblock, lazy_ez: bool) -> None:
         tb = int(tblock if tblock is not None else self.tblock)
         if tb > self.max_tblock:
             raise _lib.FdtdError(f"tblock {tb} exceeds the deepest supported time block {self.max_tblock}")
@@ -321,6 +385,8 @@ class Fdtd2D:
             if self.tfsf:
                 inctdz(nx, ny, n, self.hxi, s["dz"])
             efield(nx, ny, medium(self.naz, self.nbz), s["dz"], s["ez"], s.get("iz"))
+            if self.ft is not None:
+                fourier(t, len(self.freqs), nx, ny, self.dt, self.freqs, self.ezi, s["ez"], self.ft)
             if self.tfsf:
                 hxinct(ny, self.ezi, self.hxi)
             hfield(nx, ny, self.pml, s["ez"], s["ihx"], s["ihy"], s["hx"], s["hy"])

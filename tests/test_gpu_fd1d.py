@@ -33,6 +33,10 @@ def _sim_for(prog, nx, dtype, **kw):
     raise KeyError(prog)
 
 
+def _sim_kw_ok():
+    return True
+
+
 def _oracle(prog, nx, ns, dtype):
     p, src = cases.line_program(prog, nx, ns, dtype)
     p.freqs = None                       # running DFT is a next-tier row; fields do not depend on it
@@ -123,3 +127,30 @@ def test_tiny_lines():
         sim = _sim_for("1_2", nx, np.float64)
         sim.advance(40, tblock=5)
         _assert_same(sim, _oracle("1_2", nx, 40, np.float64))
+
+
+# ------------------------------------------------------------------ running DFT (fourier), programs 2_2 / 2_3
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("prog", ["2_2", "2_3"])
+def test_running_dft_matches_oracle(prog, dtype):
+    from simulation_b200 import fd1d
+    nx, ns = 400, 500
+    p, src = cases.line_program(prog, nx, ns, dtype)
+    sim = _sim_for(prog, nx, dtype, freqs=p.freqs)
+    sim.advance(ns)
+    orc.advance_1d(p, src)
+    for n in ("ex", "hy", "r_pt", "i_pt", "r_in", "i_in"):
+        assert sim.get(n).tobytes() == getattr(p, n).tobytes(), n
+
+
+@pytest.mark.parametrize("prog", ["2_2", "2_3"])
+def test_dft_amplitude_goldens(prog):
+    """amplt[2] as the reference programs plot it: fp64 main() golden and fp32 benchmark-twin golden."""
+    for tag, dtype in (("main", np.float64), ("twin", np.float32)):
+        g = cases.golden(f"{tag}_fd1d_{prog}")
+        nx, ns = (cases.LINE_MAIN[prog] if tag == "main" else (int(g["nx"]), int(g["ns"])))
+        p, _ = cases.line_program(prog, nx, ns, dtype)
+        sim = _sim_for(prog, nx, dtype, freqs=p.freqs)
+        sim.advance(ns)
+        amp, _ = orc.dft_amplitude_phase(sim.get("r_pt"), sim.get("i_pt"), sim.get("r_in"), sim.get("i_in"))
+        assert amp[2].tobytes() == g["amplt2"].tobytes(), tag

@@ -177,6 +177,37 @@ def test_numba_program_3_4_golden_within_tolerance():
         assert np.abs(sim.get(name) - ref[name]).max() <= 1e-12 * scale, name     # numba fastmath is not bit-stable
 
 
+# ------------------------------------------------------------------ running DFT (fourier), program 3_4
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_running_dft_matches_oracle(dtype):
+    from simulation_b200 import fd2d, surface
+    nx, ny, npml, ns = 60, 72, 8, 90
+    g, src = cases.grid_program("3_4", nx, ny, ns, dtype, npml=npml, radius=0.12, dft=True)
+    mk = lambda: fd2d.Fdtd2D(nx, ny, npml, dtype, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)),
+                             naz=g.naz.copy(), nbz=g.nbz.copy(), freqs=g.freqs)
+    a, b = mk(), mk()
+    a.advance(ns)                      # fused single-step passes + fourier
+    for _ in range(ns):
+        b.step()                       # reference-named functions, fourier between efield and hxinct
+    orc.advance_2d(g, src)
+    for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy", "r_pt", "i_pt", "r_in", "i_in"):
+        assert a.get(name).tobytes() == getattr(g, name).tobytes(), name
+        assert b.get(name).tobytes() == getattr(g, name).tobytes(), name
+
+
+def test_running_dft_numba_golden():
+    """Program 3_4 as driven through the reference's numba functions (fastmath: tolerance, not bits)."""
+    from simulation_b200 import fd2d, surface
+    ref = cases.golden("drive_3_4_f64")
+    nx, ny, ns, npml = (int(ref[k]) for k in ("nx", "ny", "ns", "npml"))
+    naz, nbz = surface.dielectric_cylinder(nx, ny, npml, int(ref["rgrid"]), surface.DT, 30.0, 0.30, np.float64)
+    sim = fd2d.Fdtd2D(nx, ny, npml, np.float64, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=naz, nbz=nbz,
+                      freqs=np.array((50e6, 300e6, 700e6)))
+    sim.advance(ns)
+    for name in ("r_pt", "i_pt", "r_in", "i_in"):
+        assert np.abs(sim.get(name) - ref[name]).max() <= 1e-11 * np.abs(ref[name]).max(), name
+
+
 # ------------------------------------------------------------------ medium and large grids
 def test_interior_kernel_equals_edge_kernel_everywhere():
     """Force every warp through the careful (edge) kernel and compare with the default split: bitwise equal."""
