@@ -33,13 +33,9 @@ def _sim_for(prog, nx, dtype, **kw):
     raise KeyError(prog)
 
 
-def _sim_kw_ok():
-    return True
-
-
 def _oracle(prog, nx, ns, dtype):
     p, src = cases.line_program(prog, nx, ns, dtype)
-    p.freqs = None                       # running DFT is a next-tier row; fields do not depend on it
+    p.freqs = None                       # fields do not depend on the running DFT (tested separately below)
     orc.advance_1d(p, src)
     return p
 
