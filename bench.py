@@ -140,7 +140,7 @@ def cpu_reference_c(nx, ny, steps, warm=1):
     return nx * ny * steps / dt / 1e6, dt
 
 
-def run_reference(args):
+def run_reference(args, emit=print):
     """--impl reference: rank 0 only; a bounded sample (8192 x 8192 of the 32768 x 32768 workload) per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -167,11 +167,11 @@ def run_reference(args):
                        "sample": sample},
             "cpu_baseline": {"value": v, "unit": "Mcell-updates/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+def run_ours(args, emit=print):
     import torch
     import torch.distributed as dist
     from simulation_b200 import fd2d, surface
@@ -264,7 +264,7 @@ def run_ours(args):
                              "note": "achieved = 48 B x cells x steps / time; a T-step pass moves ~48 B per cell once, "
                                      "so frac may exceed 1 (traffic = real DRAM bytes per launch from ncu)"},
                 "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -301,6 +301,23 @@ def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync):
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner on communicator
+    # creation): park fd 1 on stderr for the whole run and emit the line on the saved descriptor at the end.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    try:
+        _main(lines.append)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    for line in lines:
+        print(line, flush=True)
+
+
+def _main(emit):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=96)
@@ -313,9 +330,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
     else:
-        run_ours(args)
+        run_ours(args, emit)
 
 
 if __name__ == "__main__":
