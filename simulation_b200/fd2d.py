@@ -370,6 +370,85 @@ class Fdtd2D:
         self._cur = out.value
         self.t += int(nsteps)
 
+    # ---- streamed run: host medium in, host Ez out, PCIe overlapped with the time stepping ----------------
+    def _depths(self, nsteps: int, tblock=None):
+        """Pass depths the library will use for ``nsteps`` (instantiated depths: 1, 2, 3, 4, 6, 8)."""
+        tb = int(tblock if tblock else (self.tblock or (6 if self.np_dtype == np.float32 else 4)))
+        out, left = [], int(nsteps)
+        while left > 0:
+            d = min(tb, left)
+            if d in (5, 7):
+                d -= 1
+            out.append(d)
+            left -= d
+        return out
+
+    def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, blocks: int = 8,
+                     tblock=None) -> None:
+        """The whole job a reference ``main()`` does -- medium from the host, ``nsteps`` steps from zero fields,
+        Ez back on the host -- with the PCIe transfers hidden behind the kernels.
+
+        The grid is cut into ``blocks`` row blocks and the passes are issued as a wavefront: while block b of the
+        medium is still uploading, pass 1 runs on block b-1, pass 2 on block b-2, ... (pass p on a block needs pass
+        p-1 on that block and its two neighbours, which the single compute stream guarantees in wave order); the
+        last pass of each block is followed by the download of that block's Ez.  Same kernels, same arithmetic,
+        same result as ``set naz; advance(nsteps); get ez``.  ``naz_host`` / ``ez_host``: pinned CPU tensors of
+        shape (nx, ny).  Point source or no source only (the TFSF incident line is advanced once per whole-grid
+        pass); single device."""
+        if self.tfsf or self.ft is not None or self.rows_alloc != self.nx:
+            raise _lib.FdtdError("run_streamed: single-device grids with a point source (or none) and no running DFT")
+        if tuple(naz_host.shape) != (self.nx, self.ny) or tuple(ez_host.shape) != (self.nx, self.ny):
+            raise _lib.FdtdError("run_streamed: host tensors must have shape (nx, ny)")
+        depths = self._depths(nsteps, tblock)
+        P, B = len(depths), max(1, min(int(blocks), self.nx // max(4 * max(depths), 1)))
+        edges = [self.nx * k // B for k in range(B + 1)]
+        src = None
+        if self.source is not None:
+            src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)
+        first_step = np.concatenate(([0], np.cumsum(depths)))          # step offset of every pass
+        D = C.POINTER(C.c_double)
+        with torch.cuda.device(self.device):
+            compute = torch.cuda.current_stream()
+            up, down = torch.cuda.Stream(), torch.cuda.Stream()
+            up.wait_stream(compute)
+            down.wait_stream(compute)
+            uploaded = []
+            with torch.cuda.stream(up):
+                for b in range(B):
+                    self.naz[edges[b]:edges[b + 1]].copy_(naz_host[edges[b]:edges[b + 1]], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(up)
+                    uploaded.append(ev)
+            cur0 = self._cur
+            for w in range(B + P - 1):
+                for p_idx in range(P):                                     # increasing p inside a wave (see docstring)
+                    b = w - p_idx
+                    if not (0 <= b < B):
+                        continue
+                    if p_idx == 0:
+                        compute.wait_event(uploaded[min(b + 1, B - 1)])    # the pass reads naz up to depth rows below
+                    prob = self._problem()
+                    prob.row_lo, prob.row_hi = edges[b], edges[b + 1]
+                    if p_idx < P - 1:
+                        prob.flags |= _lib.LAZY_EZ
+                    out = C.c_int(-1)
+                    k0 = int(first_step[p_idx])
+                    check(lib().fdtd2d_advance(C.byref(prob), (cur0 + p_idx) % 2, depths[p_idx],
+                                               None if src is None else src[k0:].ctypes.data_as(D),
+                                               depths[p_idx], C.c_void_p(compute.cuda_stream), C.byref(out)),
+                          "fdtd2d_advance (streamed)")
+                    if p_idx == P - 1:
+                        done = torch.cuda.Event()
+                        done.record(compute)
+                        down.wait_event(done)
+                        with torch.cuda.stream(down):
+                            ez_dev = self._sets[(cur0 + P) % 2]["ez"]
+                            ez_host[edges[b]:edges[b + 1]].copy_(ez_dev[edges[b]:edges[b + 1]], non_blocking=True)
+            compute.wait_stream(down)
+            compute.wait_stream(up)
+        self._cur = (cur0 + P) % 2
+        self.t += int(nsteps)
+
     # ---- the unfused path: the reference loop body, one kernel per reference function ----------------
     def step(self) -> None:
         """One time step via the reference-named functions in the reference order (single device only)."""

@@ -322,6 +322,27 @@ def test_baseline_config_4_vs_reference_c_openmp():
         assert err <= 5e-7 * max(float(np.abs(want).max()), peak), (name, err)   # in fact: a few ulp (measured 4e-9)
 
 
+def test_streamed_run_equals_plain_run():
+    """run_streamed (block wavefront, transfers overlapped) == set naz; advance; get ez -- bit for bit, and the
+    whole state with it."""
+    from simulation_b200 import fd2d, surface
+    rng = np.random.default_rng(5)
+    nx, ny, npml, ns = 1500, 1152, 16, 52
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    src = fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6))
+    a = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, naz=naz)
+    a.advance(ns)
+    b = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src)
+    host_naz = torch.from_numpy(naz).pin_memory()
+    host_ez = torch.empty((nx, ny), dtype=torch.float32).pin_memory()
+    b.run_streamed(ns, host_naz, host_ez, blocks=5)
+    b.synchronize()
+    assert torch.equal(host_ez, a.tensor("ez").cpu())
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+    assert b.t == ns and float(host_ez.abs().max()) > 1e-3
+
+
 # ------------------------------------------------------------------ error behaviour of the boundary
 def test_errors_are_reported_not_swallowed():
     from simulation_b200 import _lib, fd2d, surface
