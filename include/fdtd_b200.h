@@ -136,6 +136,12 @@ int fdtd2d_hfield(int dtype, int nx, int ny, const fdtd_pmlayer *pml, const void
 int fdtd2d_incthx(int dtype, int nx, int ny, int npml, const void *ezi, void *hx, void *stream);
 int fdtd2d_incthy(int dtype, int nx, int ny, int npml, const void *ezi, void *hy, void *stream);
 
+/* setup on the device: naz / nbz of the lossy dielectric cylinder of program 3_4 for GLOBAL rows [row_lo, row_hi)
+ * (arrays of (row_hi-row_lo) x ny), float64 evaluation of the reference's Python statements
+ * (fd2d/python/fd2d_3_4.py:173-194), bit-identical to them */
+int fdtd2d_dielectric_cylinder(int dtype, int nx, int ny, int npml, int rgrid, double dt, double epsr, double sigma,
+                               int row_lo, int row_hi, void *naz, void *nbz, void *stream);
+
 /* --------------------------------------------------------------------- 2D: fused time-blocked path */
 enum { FDTD2D_DZ = 0, FDTD2D_EZ, FDTD2D_HX, FDTD2D_HY, FDTD2D_IHX, FDTD2D_IHY, FDTD2D_IZ, FDTD2D_NFIELDS };
 

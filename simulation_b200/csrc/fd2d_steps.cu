@@ -144,6 +144,33 @@ __global__ void k_fourier_source(int nf, Phases ph, const real *sample, real *r_
     i_in[f] = static_cast<real>(static_cast<double>(i_in[f]) - ph.s[f] * e);
 }
 
+// Lossy dielectric cylinder, 3x3 sub-cell average, evaluated in float64 exactly as the reference's Python
+// statements (fd2d/python/fd2d_3_4.py:173-194; the C/CUDA variants' integer m/3 is a known divergence):
+// x = nx/2-1-i+m/3, y = ny/2-1-j+n/3, inside if sqrt(x*x+y*y) <= rgrid.  Rows [row_lo, row_hi) of the global grid.
+template <typename real>
+__global__ void k_cylinder(int nx, int ny, int npml, int rgrid, double dt, double epsr, double sigma, int row_lo,
+                           int row_hi, real *naz, real *nbz) {
+    const int j = blockIdx.x * BX + threadIdx.x;
+    const int i = row_lo + blockIdx.y * BY + threadIdx.y;
+    if (i >= row_hi || j >= ny) return;
+    const size_t n = (size_t)(i - row_lo) * ny + j;
+    double vn = 1.0, vb = 0.0;
+    if (i >= npml && i < nx - npml && j >= npml && j < ny - npml) {
+        const double eps0 = 8.854e-12, de = (epsr - 1) / 9, dc = sigma / 9;
+        double epsn = 1.0, cond = 0.0;
+        for (int m = -1; m < 2; ++m)
+            for (int q = -1; q < 2; ++q) {
+                const double x = (((double)nx / 2 - 1) - (double)i) + (double)m / 3;
+                const double y = (((double)ny / 2 - 1) - (double)j) + (double)q / 3;
+                if (sqrt(x * x + y * y) <= (double)rgrid) { epsn += de; cond += dc; }
+            }
+        vn = 1 / (epsn + cond * dt / eps0);
+        vb = cond * dt / eps0;
+    }
+    naz[n] = static_cast<real>(vn);
+    nbz[n] = static_cast<real>(vb);
+}
+
 inline dim3 grid2d(int nx, int ny) { return dim3((ny + BX - 1) / BX, (nx + BY - 1) / BY); }
 
 template <typename real>
@@ -245,6 +272,16 @@ int fdtd2d_fourier(int dtype, int nf, int nx, int ny, const double *cosv, const 
     const size_t esz = dtype == FDTD_F64 ? 8 : 4;
     const void *sample = ezi ? (const char *)ezi + esz * (size_t)sample_index : nullptr;
     return fdtd::launch_fourier(dtype, nf, (size_t)nx * ny, cosv, sinv, ez, sample, ft, fdtd::as_stream(stream));
+}
+
+int fdtd2d_dielectric_cylinder(int dtype, int nx, int ny, int npml, int rgrid, double dt, double epsr, double sigma,
+                               int row_lo, int row_hi, void *naz, void *nbz, void *stream) {
+    FDTD_REQUIRE(nx >= 1 && ny >= 1 && npml >= 0 && row_lo >= 0 && row_hi <= nx && row_lo < row_hi && naz && nbz,
+                 "fdtd2d_dielectric_cylinder: bad arguments");
+    const dim3 grid((ny + BX - 1) / BX, (row_hi - row_lo + BY - 1) / BY);
+    DISPATCH(dtype, (k_cylinder<real><<<grid, dim3(BX, BY), 0, fdtd::as_stream(stream)>>>(nx, ny, npml, rgrid, dt, epsr, sigma, row_lo, row_hi, (real *)naz, (real *)nbz)));
+    FDTD_LAUNCH_CHECK("k_cylinder");
+    return FDTD_OK;
 }
 
 int fdtd2d_hfield(int dtype, int nx, int ny, const fdtd_pmlayer *pml, const void *ez, void *ihx, void *ihy, void *hx,

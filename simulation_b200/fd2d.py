@@ -115,6 +115,22 @@ def pmlparam(nx: int, ny: int, npml: int, dtype=np.float32, device=None) -> pmla
     return pmlayer(*[torch.from_numpy(a).to(device or "cuda") for a in host])
 
 
+def dielectric(nx: int, ny: int, npml: int, rgrid: int, dt: float, epsr: float, sigma: float, dtype=np.float32,
+               device=None, rows=None) -> medium:
+    """``naz, nbz`` of the lossy dielectric cylinder (reference ``dielectric``, fd2d/python/fd2d_3_4.py:173-194),
+    rasterised ON THE DEVICE -- the host version needs minutes at 32768^2.  ``rows=(lo, hi)``: a slab."""
+    lo, hi = (0, nx) if rows is None else rows
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    tdt = _TORCH_DT[np.dtype(dtype)]
+    naz = torch.empty((hi - lo, ny), dtype=tdt, device=dev)
+    nbz = torch.empty((hi - lo, ny), dtype=tdt, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().fdtd2d_dielectric_cylinder(_lib.dtype_code(dtype), nx, ny, npml, int(rgrid), float(dt), float(epsr),
+                                               float(sigma), int(lo), int(hi), _ptr(naz), _ptr(nbz), _stream()),
+              "dielectric")
+    return medium(naz, nbz)
+
+
 @dataclass(frozen=True)
 class PointSource:
     """``dz[i, j] = waveform(t)`` (hard) or ``+=`` (soft) after the D update (fd2d_3_1.py:48, fd2d_3_2.py:66)."""
@@ -254,6 +270,12 @@ class Fdtd2D:
         """Upload a coefficient array given for the whole grid, the owned rows, or the stored rows."""
         if host is None:
             return torch.full((self.rows_alloc, self.ny), fill, dtype=self.dtype, device=self.device)
+        if isinstance(host, torch.Tensor) and host.is_cuda:           # already on the device (fd2d.dielectric)
+            if tuple(host.shape) == (self.nx, self.ny):
+                host = host[self.row_base:self.row_base + self.rows_alloc]
+            if tuple(host.shape) != (self.rows_alloc, self.ny) or host.dtype != self.dtype:
+                raise _lib.FdtdError(f"device coefficient array has shape {tuple(host.shape)} / {host.dtype}")
+            return host.to(self.device).contiguous()
         if isinstance(host, torch.Tensor):
             host = host.detach().cpu().numpy()
         a = np.asarray(host, dtype=self.np_dtype)

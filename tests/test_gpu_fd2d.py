@@ -322,6 +322,20 @@ def test_baseline_config_4_vs_reference_c_openmp():
         assert err <= 5e-7 * max(float(np.abs(want).max()), peak), (name, err)   # in fact: a few ulp (measured 4e-9)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_device_dielectric_equals_host_setup(dtype):
+    """fd2d.dielectric (device rasteriser) == surface.dielectric_cylinder (host, == the reference's Python)."""
+    from simulation_b200 import fd2d, surface
+    for nx, ny, npml, rgrid in ((100, 100, 8, 14), (257, 190, 12, 61), (512, 768, 80, 120)):
+        h_naz, h_nbz = surface.dielectric_cylinder(nx, ny, npml, rgrid, surface.DT, 30.0, 0.30, dtype)
+        md = fd2d.dielectric(nx, ny, npml, rgrid, surface.DT, 30.0, 0.30, dtype)
+        assert md.naz.cpu().numpy().tobytes() == h_naz.tobytes() and md.nbz.cpu().numpy().tobytes() == h_nbz.tobytes()
+        slab_md = fd2d.dielectric(nx, ny, npml, rgrid, surface.DT, 30.0, 0.30, dtype, rows=(33, 77))
+        assert slab_md.naz.cpu().numpy().tobytes() == h_naz[33:77].tobytes()
+    sim = fd2d.Fdtd2D(100, 100, 8, dtype, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=md.naz[:0].new_ones(100, 100), nbz=None)
+    assert sim.naz.shape == (100, 100)
+
+
 def test_streamed_run_equals_plain_run():
     """run_streamed (block wavefront, transfers overlapped) == set naz; advance; get ez -- bit for bit, and the
     whole state with it."""
