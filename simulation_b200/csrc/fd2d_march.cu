@@ -634,7 +634,8 @@ Plan choose_plan(long cells, int ny, bool lossy) {
 template <typename real>
 int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int tblock, cudaStream_t st,
             int *cur_out) {
-    const Plan plan = choose_plan<real>((long)q->rows_alloc * q->ny, q->ny, (q->flags & FDTD_LOSSY) != 0);
+    // sized by the rows THIS call produces (a slab, or one row block of a streamed run), not by the allocation
+    const Plan plan = choose_plan<real>((long)(q->row_hi - q->row_lo) * q->ny, q->ny, (q->flags & FDTD_LOSSY) != 0);
     if (tblock <= 0) tblock = plan.T;
     const bool lossy = (q->flags & FDTD_LOSSY) != 0, tfsf = (q->flags & FDTD_TFSF) != 0;
     int done = 0;

@@ -21,11 +21,11 @@ def timed(fn, reps=2):
 sim.advance(12)
 print("plain advance(96):            %.1f ms" % timed(lambda: sim.advance(K)))
 dn = torch.ones((n, n), dtype=torch.float32, device="cuda"); de = torch.empty_like(dn)
-for B in (1, 4, 8, 16):
+for B in (8, 16):
     print("wavefront, device tensors B=%2d: %.1f ms" % (B, timed(lambda: sim.run_streamed(K, dn, de, blocks=B))))
 del dn, de
 hn = torch.ones((n, n), dtype=torch.float32).pin_memory(); he = torch.empty((n, n), dtype=torch.float32).pin_memory()
 print("H2D 4 GiB alone:              %.1f ms" % timed(lambda: sim.naz.copy_(hn, non_blocking=True)))
 print("D2H 4 GiB alone:              %.1f ms" % timed(lambda: he.copy_(sim.tensor("ez"), non_blocking=True)))
-for B in (4, 8, 16, 32):
+for B in (8, 12, 16, 20, 24):
     print("streamed, pinned host B=%2d:    %.1f ms" % (B, timed(lambda: sim.run_streamed(K, hn, he, blocks=B))))
