@@ -284,7 +284,7 @@ def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync):
     sync()
     e0.record()
     if world == 1:
-        sim.run_streamed(K, host_naz, host_ez, blocks=8)          # transfers overlapped with the passes
+        sim.run_streamed(K, host_naz, host_ez, blocks=24)          # transfers overlapped with the passes
     else:
         o = sim.row_lo - sim.row_base
         sim.naz[o:o + rows].copy_(host_naz, non_blocking=True)
@@ -301,7 +301,7 @@ def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync):
     return {"value": float(nx_global) * n * K / dt / 1e6, "unit": "Mcell-updates/s",
             "h2d_bytes_per_step": nbytes / K, "d2h_bytes_per_step": nbytes / K,
             "what": f"pinned naz H2D ({nbytes / 2**30:.1f} GiB/GPU) + {K} steps + pinned Ez D2H, CUDA events on the launch "
-                    f"stream, max over ranks; " + ("Fdtd2D.run_streamed: 8 row blocks, transfers overlapped with the passes"
+                    f"stream, max over ranks; " + ("Fdtd2D.run_streamed: 24 row blocks, transfers overlapped with the passes"
                                                    if world == 1 else "slab.advance between the two copies")}
 
 
