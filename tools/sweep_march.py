@@ -25,15 +25,17 @@ def main():
     ap.add_argument("--careful", type=int, default=0)
     ap.add_argument("--prog", default="3_2")
     ap.add_argument("--npml", type=int, default=80)
+    ap.add_argument("--dtype", default="float32")
     a = ap.parse_args()
     n = a.size
+    DT = np.float32 if a.dtype == "float32" else np.float64
     if a.prog == "3_2":
-        sim = fd2d.Fdtd2D(n, n, a.npml, np.float32, source=fd2d.PointSource(n // 2 - 5, n // 2 - 5, surface.Sinusoid(1500e6)))
+        sim = fd2d.Fdtd2D(n, n, a.npml, DT, source=fd2d.PointSource(n // 2 - 5, n // 2 - 5, surface.Sinusoid(1500e6)))
     elif a.prog == "3_3":
-        sim = fd2d.Fdtd2D(n, n, a.npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)))
+        sim = fd2d.Fdtd2D(n, n, a.npml, DT, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)))
     else:
-        naz, nbz = surface.dielectric_cylinder(n, n, a.npml, int(n * 0.15), surface.DT, 30.0, 0.30, np.float32)
-        sim = fd2d.Fdtd2D(n, n, a.npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=naz, nbz=nbz)
+        naz, nbz = surface.dielectric_cylinder(n, n, a.npml, int(n * 0.15), surface.DT, 30.0, 0.30, DT)
+        sim = fd2d.Fdtd2D(n, n, a.npml, DT, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=naz, nbz=nbz)
     lib = _lib.lib()
     ints = lambda s: [int(x) for x in s.split(",")]
     for T, V, W, C, R in itertools.product(ints(a.ts), ints(a.vs), ints(a.warps), ints(a.chunks), ints(a.rings)):
