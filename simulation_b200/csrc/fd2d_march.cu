@@ -623,9 +623,10 @@ Plan choose_plan(long cells, int ny, bool lossy) {
         else if (cells < 100000000L) p = {2, 6, 128};
         else                         p = {lossy ? 2 : 4, 6, 128};   // 7 row sets x 4 columns x 9 lossy fields spill
     } else {
-        if (cells < 3000000L)        p = {1, 4, 16};
-        else if (cells < 24000000L)  p = {1, 4, 64};
-        else                         p = {2, 4, 128};
+        if (cells < 1500000L)        p = {1, 4, 16};           // profiles/r1_sweep_fp64.txt
+        else if (cells < 12000000L)  p = {2, 4, 16};
+        else if (cells < 150000000L) p = {2, 6, 64};
+        else                         p = {2, 6, 128};
     }
     while (p.V > 1 && ny % p.V != 0) p.V >>= 1;
     return p;
