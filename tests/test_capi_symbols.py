@@ -92,3 +92,24 @@ def test_host_classes_refuse_to_run_without_cuda():
         fd2d.Fdtd2D(32, 32, 4)
     with pytest.raises(_lib.FdtdError):
         fd1d.Fdtd1D(32)
+
+
+def _build_c_example(tmp_path):
+    exe = tmp_path / "c_host_3_3"
+    subprocess.run(["gcc", "-Wall", "-O1", os.path.join(ROOT, "examples", "c_host_3_3.c"), "-I", os.path.join(ROOT, "include"),
+                    "-L", os.path.join(ROOT, "simulation_b200", "csrc"), "-lfdtd_b200", "-lm", "-o", str(exe)], check=True)
+    return exe
+
+
+def test_c_host_example_compiles_and_links(tmp_path):
+    """A plain C program shaped like the reference's fd2d/cuda/test_3_3.cu main() links against the C ABI."""
+    assert _build_c_example(tmp_path).exists()
+
+
+@pytest.mark.gpu
+def test_c_host_example_runs(tmp_path):
+    exe = _build_c_example(tmp_path)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "simulation_b200", "csrc") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([str(exe), "600", "760", "150", "24"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "identical bytes" in r.stdout
