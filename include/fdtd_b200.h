@@ -164,6 +164,14 @@ typedef struct {
      * (fd2d/program/fd2d_3_3.py:113-122).  Multiplications by 1 are then skipped (exact).  All zero: no promise.
      * fdtd2d_check_identity() verifies a promise on the device. */
     int ident_row_lo, ident_row_hi, ident_col_lo, ident_col_hi;
+    /* Running DFT fused into the passes (program 3_4's `fourier`, fd2d/python/fd2d_3_4.py:89-99): nf <= 3
+     * frequencies (0 = off); ft.r_pt / ft.i_pt are nf x rows_alloc x ny accumulators, ft.r_in / ft.i_in (nf each,
+     * FDTD_TFSF only, may be NULL) accumulate the source sample ezi[6]; dft_cos / dft_sin are HOST float64 tables
+     * [step][nf] of cos/sin(2*pi*f*dt*t) for the steps of this call.  Same float64-then-round arithmetic and the same
+     * per-step order as fdtd2d_fourier after every step; passes are limited to 4 steps and 2-wide vectors. */
+    int nf;
+    fdtd_ftrans ft;
+    const double *dft_cos, *dft_sin;
 } fdtd2d_problem;
 
 /* Advance nsteps full time steps (reference order: ezinct, dfield+source, inctdz, efield, hxinct, hfield,
@@ -177,7 +185,7 @@ int fdtd2d_advance(const fdtd2d_problem *p, int cur, int nsteps, const double *s
 /* number of coefficient entries that violate the ident_* promise of `p` (0 = promise holds); synchronises */
 int fdtd2d_check_identity(const fdtd2d_problem *p, long long *violations);
 /* resolve (module-load) every kernel instantiation a problem of this dtype / width can launch, so that no
- * time step pays CUDA's lazy loading */
+ * time step pays CUDA's lazy loading.  lossy: bit 0 = FDTD_LOSSY kernels, bit 1 = also the fused-DFT kernels */
 int fdtd2d_preload(int dtype, int ny, int lossy);
 /* largest supported tblock for a dtype / ny (0 if unsupported) */
 int fdtd2d_max_tblock(int dtype, int ny);

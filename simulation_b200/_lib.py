@@ -56,7 +56,8 @@ class Problem2D(C.Structure):
                 ("ezi", C.c_void_p), ("hxi", C.c_void_p), ("bc", C.c_void_p),
                 ("ezi_hist", C.c_void_p), ("hxi_hist", C.c_void_p),
                 ("src_i", C.c_int), ("src_j", C.c_int), ("src_hard", C.c_int),
-                ("ident_row_lo", C.c_int), ("ident_row_hi", C.c_int), ("ident_col_lo", C.c_int), ("ident_col_hi", C.c_int)]
+                ("ident_row_lo", C.c_int), ("ident_row_hi", C.c_int), ("ident_col_lo", C.c_int), ("ident_col_hi", C.c_int),
+                ("nf", C.c_int), ("ft", FTrans), ("dft_cos", C.POINTER(C.c_double)), ("dft_sin", C.POINTER(C.c_double))]
 
 
 # every symbol include/fdtd_b200.h declares: name -> (restype, argtypes)

@@ -18,6 +18,7 @@
 namespace {
 
 constexpr int TMAX = 8;          // deepest pipeline instantiated
+constexpr int NFMAX = 3;         // frequencies of the fused running DFT (the reference uses 3 everywhere)
 constexpr int MAX_SPECIAL = 12;  // most edge / TFSF / source strips (or chunks) a split launch can list
 constexpr int MAX_WARPS = 8;     // warps per CTA are independent; a CTA only groups neighbouring strips for L1 locality
 
@@ -37,6 +38,10 @@ struct MarchParams {
     const real *ezi_hist, *hxi_hist;           // [T][ny], [T][2]
     int src_i, src_j, src_hard;                // point source on dz (src_i < 0: none)
     int ident_row_lo, ident_row_hi, ident_col_lo, ident_col_hi;   // rows / cols [lo,hi) with identity PML coefficients
+    int nf;                                    // fused running DFT: frequencies (0 = off, <= NFMAX)
+    real *r_pt, *i_pt;                         // [nf][rows_alloc][ny] accumulators, updated in place by the owner warp
+    long long dft_plane;                       // elements per frequency plane
+    double dft_c[TMAX][NFMAX], dft_s[TMAX][NFMAX];   // phase factors of every sub-step
     int write_ez;                              // 0: this pass leaves ez untouched (it is never read by a pass)
     int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
     int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
@@ -114,6 +119,7 @@ __device__ __forceinline__ void lds_vec(const void *smem_src, real (&d)[V]) {
 template <typename real, int V>
 struct RowSet {
     real dz[V], ez[V], hx[V], hy[V], ihx[V], ihy[V], naz[V], iz[V], nbz[V];
+    real racc[NFMAX][V], iacc[NFMAX][V];       // running-DFT accumulators travelling with the row (DFT kernels only)
 };
 
 template <typename real, int V>
@@ -124,10 +130,11 @@ struct ColCoef {       // per-column PML coefficients and update masks, fixed fo
 
 // One pipeline stage at sub-step s: finish D,E of the arriving row A (global row rs) and H of the held row Hd
 // (global row rs-1), both in place.  FAST: interior warp -- no edge masks, no TFSF / source cells.
-template <typename real, int V, bool LOSSY, bool FAST>
+template <typename real, int V, int MODE, bool FAST>
 __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const ColCoef<real, V> &c, RowSet<real, V> &A,
                                             RowSet<real, V> &Hd, const int rs, const int s, const int jb,
                                             const bool tf_cols, const bool src_cols) {
+    constexpr bool LOSSY = (MODE & 1) != 0, DFT = (MODE & 2) != 0;
     constexpr unsigned FULL = 0xffffffffu;
     const real half = real(0.5);
     const int hr = rs - 1;
@@ -178,6 +185,18 @@ __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const Co
         } else {
             A.ez[v] = A.naz[v] * A.dz[v];
         }
+    }
+    if (DFT) {       // fourier of sub-step s on the fresh Ez: float64 product and sum, rounded into the array type
+#pragma unroll
+        for (int f = 0; f < NFMAX; ++f)
+            if (f < p.nf) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const double e = static_cast<double>(A.ez[v]);
+                    A.racc[f][v] = static_cast<real>(static_cast<double>(A.racc[f][v]) + p.dft_c[s][f] * e);
+                    A.iacc[f][v] = static_cast<real>(static_cast<double>(A.iacc[f][v]) - p.dft_s[s][f] * e);
+                }
+            }
     }
     // ---- H of the held row hr (needs ez[hr][j+1] and ez[rs][j]), in place
     const real ez_right = __shfl_down_sync(FULL, Hd.ez[0], 1);
@@ -232,14 +251,15 @@ __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const Co
 // register cost), keeping RING-1 rows x 6 arrays in flight per warp to cover the HBM latency.
 constexpr int RING = 4;
 
-template <typename real, int V, int T, bool LOSSY, bool FAST>
+template <typename real, int V, int T, int MODE, bool FAST>
 __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int strip, const int chunk, const int lane,
                                            unsigned char *const ring) {
+    constexpr bool LOSSY = (MODE & 1) != 0, DFT = (MODE & 2) != 0;
     constexpr int W = 32 * V;            // columns per strip
     constexpr int HALO = ((T + V - 1) / V) * V;   // recomputed columns per side: >= T, multiple of V (aligned vectors)
     constexpr int USE = W - 2 * HALO;    // columns a strip produces
     constexpr int NS = T + 1;            // register row sets
-    constexpr int NARR = LOSSY ? 8 : 6;  // arrays staged per row
+    constexpr int NARR = (LOSSY ? 8 : 6) + (DFT ? 2 * NFMAX : 0);  // arrays staged per row
     constexpr int LB = V * (int)sizeof(real);
     constexpr int SLOT = NARR * 32 * LB; // ring bytes per row (per warp)
 
@@ -282,6 +302,8 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         for (int v = 0; v < V; ++v) {
             S[k].dz[v] = S[k].ez[v] = S[k].hx[v] = S[k].hy[v] = S[k].ihx[v] = S[k].ihy[v] = real(0);
             S[k].naz[v] = S[k].iz[v] = S[k].nbz[v] = real(0);
+#pragma unroll
+            for (int f = 0; f < NFMAX; ++f) S[k].racc[f][v] = S[k].iacc[f][v] = real(0);
         }
 
     unsigned char *const lane_ring = ring + lane * LB;
@@ -307,6 +329,18 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
             cp_async<LB>(dst + 6 * 32 * LB, p.in_iz + off, nb);
             cp_async<LB>(dst + 7 * 32 * LB, p.nbz + off, nb);
         }
+        if (DFT) {   // accumulators are read (and later written) by the OWNER of a cell only: no halo reads, no race
+            const bool own = (g_f >= i0) && (g_f < i1) && col_store;
+            const long long offa = own ? off_f : 0;
+            const int na = own ? LB : 0;
+            constexpr int A0 = LOSSY ? 8 : 6;
+#pragma unroll
+            for (int f = 0; f < NFMAX; ++f) {
+                const bool on = f < p.nf;
+                cp_async<LB>(dst + (A0 + 2 * f) * 32 * LB, p.r_pt + (on ? f * p.dft_plane + offa : 0), on ? na : 0);
+                cp_async<LB>(dst + (A0 + 2 * f + 1) * 32 * LB, p.i_pt + (on ? f * p.dft_plane + offa : 0), on ? na : 0);
+            }
+        }
         cp_async_commit();
         off_f += p.ny;
         ++g_f;
@@ -323,6 +357,14 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
             lds_vec<real, V>(src + 6 * 32 * LB, row.iz);
             lds_vec<real, V>(src + 7 * 32 * LB, row.nbz);
         }
+        if (DFT) {
+            constexpr int A0 = LOSSY ? 8 : 6;
+#pragma unroll
+            for (int f = 0; f < NFMAX; ++f) {
+                lds_vec<real, V>(src + (A0 + 2 * f) * 32 * LB, row.racc[f]);
+                lds_vec<real, V>(src + (A0 + 2 * f + 1) * 32 * LB, row.iacc[f]);
+            }
+        }
     };
 
 #pragma unroll
@@ -338,6 +380,14 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
             VecIO<real, V>::st(p.out_ihx + off_s, O.ihx);
             VecIO<real, V>::st(p.out_ihy + off_s, O.ihy);
             if (LOSSY) VecIO<real, V>::st(p.out_iz + off_s, O.iz);
+            if (DFT) {
+#pragma unroll
+                for (int f = 0; f < NFMAX; ++f)
+                    if (f < p.nf) {
+                        VecIO<real, V>::st(p.r_pt + f * p.dft_plane + off_s, O.racc[f]);
+                        VecIO<real, V>::st(p.i_pt + f * p.dft_plane + off_s, O.iacc[f]);
+                    }
+            }
         }
         off_s += p.ny;
     };
@@ -354,7 +404,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
                 slot = (slot + 1 == RING) ? 0 : slot + 1;
 #pragma unroll
                 for (int s = 0; s < T; ++s)
-                    march_stage<real, V, LOSSY, FAST>(p, c, S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], rr - s,
+                    march_stage<real, V, MODE, FAST>(p, c, S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], rr - s,
                                                       s, jb, tf_cols, src_cols);
                 store_row(S[(u + 1) % NS], rr - T);   // the set held by the last stage: row rr-T at time t+T
             }
@@ -371,7 +421,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
             slot = (slot + 1 == RING) ? 0 : slot + 1;
 #pragma unroll
             for (int s = 0; s < T; ++s)
-                march_stage<real, V, LOSSY, FAST>(p, c, S[s], S[s + 1], rr - s, s, jb, tf_cols, src_cols);
+                march_stage<real, V, MODE, FAST>(p, c, S[s], S[s + 1], rr - s, s, jb, tf_cols, src_cols);
             store_row(S[T], rr - T);
 #pragma unroll
             for (int k = T; k >= 1; --k) S[k] = S[k - 1];
@@ -393,11 +443,11 @@ __device__ __forceinline__ int kth_not_in(int k, const int *skip, int n) {
 //             stored row, so the body carries no masks, clamps or TFSF / source cells;
 //   careful : the listed special strips x all chunks, plus ordinary strips x the listed special chunks
 //             (grid edges, PEC row / column, TFSF box edges, the point source); or everything (all_careful).
-template <typename real, int V, int T, bool LOSSY, bool FAST>
+template <typename real, int V, int T, int MODE, bool FAST>
 __global__ void __launch_bounds__(MAX_WARPS * 32)
 k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
     extern __shared__ __align__(16) unsigned char ring_smem[];
-    constexpr int SLOT = (LOSSY ? 8 : 6) * 32 * V * (int)sizeof(real);
+    constexpr int SLOT = (((MODE & 1) ? 8 : 6) + ((MODE & 2) ? 2 * NFMAX : 0)) * 32 * V * (int)sizeof(real);
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned char *const ring = ring_smem + (size_t)(threadIdx.x >> 5) * RING * SLOT;
@@ -423,16 +473,20 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
             chunk = p.schunks[x / nsf];
         }
     }
-    march_body<real, V, T, LOSSY, FAST>(p, strip, chunk, lane, ring);
+    march_body<real, V, T, MODE, FAST>(p, strip, chunk, lane, ring);
 }
 
 // ---- incident line: T steps of the 1D auxiliary FDTD (ezinct ... hxinct), recording what the 2D pass
 // needs: ezi after ezinct+source of every sub-step, and hxi[npml-2], hxi[ny-npml] BEFORE hxinct.
-struct SrcTable { double v[TMAX]; };
+struct SrcTable {
+    double v[TMAX];
+    int nf;                                   // running DFT of the source sample ezi[6] (0 = off)
+    double c[TMAX][NFMAX], s[TMAX][NFMAX];
+};
 
 template <typename real>
 __global__ void k_incident_line(int ny, int npml, int T, real *ezi, real *hxi, real *bc, real *ezi_hist,
-                                real *hxi_hist, const SrcTable src) {
+                                real *hxi_hist, real *r_in, real *i_in, const SrcTable src) {
     for (int s = 0; s < T; ++s) {
         for (int j = 1 + threadIdx.x; j < ny; j += blockDim.x) ezi[j] = ezi[j] + real(0.5) * (hxi[j - 1] - hxi[j]);
         __syncthreads();
@@ -444,6 +498,11 @@ __global__ void k_incident_line(int ny, int npml, int T, real *ezi, real *hxi, r
             ezi[3] = static_cast<real>(src.v[s]);
             hxi_hist[2 * s] = hxi[npml - 2];
             hxi_hist[2 * s + 1] = hxi[ny - npml];
+            for (int f = 0; f < src.nf; ++f) {        // fourier: the source sample, after ezinct + source
+                const double e = static_cast<double>(ezi[6]);
+                r_in[f] = static_cast<real>(static_cast<double>(r_in[f]) + src.c[s][f] * e);
+                i_in[f] = static_cast<real>(static_cast<double>(i_in[f]) - src.s[s][f] * e);
+            }
         }
         __syncthreads();
         for (int j = threadIdx.x; j < ny; j += blockDim.x) {
@@ -492,28 +551,28 @@ SideStream *side_stream() {
     return &table[dev];
 }
 
-template <typename real, int V, int T, bool LOSSY, bool FAST>
+template <typename real, int V, int T, int MODE, bool FAST>
 int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStream_t st) {
     if (items <= 0) return FDTD_OK;
     const int ring = RING;
-    const size_t slot = (size_t)(LOSSY ? 8 : 6) * 32 * V * sizeof(real);
+    const size_t slot = (size_t)(((MODE & 1) ? 8 : 6) + ((MODE & 2) ? 2 * NFMAX : 0)) * 32 * V * sizeof(real);
     // 8 independent warps per CTA on big grids; fewer when there are not enough warps to fill every SM
     int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : (items >= 32 * fdtd::sm_count() ? 8 : (items >= 8 * fdtd::sm_count() ? 4 : 2));
     while (warps > 1 && (size_t)warps * ring * slot > 200 * 1024) --warps;
     const size_t smem = (size_t)warps * ring * slot;
     static size_t configured = 0;                       // per instantiation: largest dynamic smem opted in so far
     if (smem > 48 * 1024 && smem > configured) {
-        FDTD_CUDA(cudaFuncSetAttribute(k_march<real, V, T, LOSSY, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FDTD_CUDA(cudaFuncSetAttribute(k_march<real, V, T, MODE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int grid = (items + warps - 1) / warps;
-    k_march<real, V, T, LOSSY, FAST><<<grid, warps * 32, smem, st>>>(mp, all_careful);
+    k_march<real, V, T, MODE, FAST><<<grid, warps * 32, smem, st>>>(mp, all_careful);
     FDTD_LAUNCH_CHECK("k_march");
     return FDTD_OK;
 }
 
 // classify strips and chunks on the host (same conditions as the kernel relies on) and launch the two kernels
-template <typename real, int V, int T, bool LOSSY>
+template <typename real, int V, int T, int MODE>
 int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     constexpr int W = 32 * V, HALO = ((T + V - 1) / V) * V, USE = W - 2 * HALO;
     const int ja = mp.npml - 1, jz = mp.ny - mp.npml, ia = mp.npml - 1, iz_ = mp.nx - mp.npml;
@@ -541,7 +600,7 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     }
     if (overflow) {                                      // tiny grids: everything through the careful kernel
         mp.n_sstrips = mp.n_schunks = 0;
-        return launch_one<real, V, T, LOSSY, false>(mp, mp.nstrips * mp.nchunks, 1, st);
+        return launch_one<real, V, T, MODE, false>(mp, mp.nstrips * mp.nchunks, 1, st);
     }
     mp.n_sstrips = ns; mp.n_schunks = nc;
     const int nsf = mp.nstrips - ns, ncf = mp.nchunks - nc;
@@ -550,16 +609,16 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
     SideStream *side = (n_careful > 0 && n_fast > 0 && g_serial == 2) ? side_stream() : nullptr;
     if (side == nullptr) {
-        int rc = launch_one<real, V, T, LOSSY, false>(mp, n_careful, 0, st);
+        int rc = launch_one<real, V, T, MODE, false>(mp, n_careful, 0, st);
         if (rc != FDTD_OK) return rc;
-        return launch_one<real, V, T, LOSSY, true>(mp, n_fast, 0, st);
+        return launch_one<real, V, T, MODE, true>(mp, n_fast, 0, st);
     }
     FDTD_CUDA(cudaEventRecord(side->fork, st));
     FDTD_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    int rc = launch_one<real, V, T, LOSSY, false>(mp, n_careful, 0, side->stream);
+    int rc = launch_one<real, V, T, MODE, false>(mp, n_careful, 0, side->stream);
     if (rc != FDTD_OK) return rc;
     FDTD_CUDA(cudaEventRecord(side->join, side->stream));
-    rc = launch_one<real, V, T, LOSSY, true>(mp, n_fast, 0, st);
+    rc = launch_one<real, V, T, MODE, true>(mp, n_fast, 0, st);
     if (rc != FDTD_OK) return rc;
     FDTD_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     return FDTD_OK;
@@ -567,7 +626,15 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
 
 template <typename real, int V, int T>
 int launch_march(MarchParams<real> &mp, bool lossy, cudaStream_t st) {
-    return lossy ? launch_march_k<real, V, T, true>(mp, st) : launch_march_k<real, V, T, false>(mp, st);
+    if (mp.nf > 0) {           // running DFT fused into the pass: narrow vectors, shallow blocking (6 more registers per cell)
+        if constexpr (V <= 2 && T <= 4) {
+            return lossy ? launch_march_k<real, V, T, 3>(mp, st) : launch_march_k<real, V, T, 2>(mp, st);
+        } else {
+            fdtd::set_error("no fused-DFT kernel for vector width %d / depth %d", V, T);
+            return FDTD_EUNSUPPORTED;
+        }
+    }
+    return lossy ? launch_march_k<real, V, T, 1>(mp, st) : launch_march_k<real, V, T, 0>(mp, st);
 }
 
 template <typename real, int V>
@@ -589,13 +656,25 @@ template <typename real, int V, int T>
 void touch_T(bool lossy) {
     cudaFuncAttributes a;
     if (lossy) {
-        cudaFuncGetAttributes(&a, k_march<real, V, T, true, true>);
-        cudaFuncGetAttributes(&a, k_march<real, V, T, true, false>);
+        cudaFuncGetAttributes(&a, k_march<real, V, T, 1, true>);
+        cudaFuncGetAttributes(&a, k_march<real, V, T, 1, false>);
     } else {
-        cudaFuncGetAttributes(&a, k_march<real, V, T, false, true>);
-        cudaFuncGetAttributes(&a, k_march<real, V, T, false, false>);
+        cudaFuncGetAttributes(&a, k_march<real, V, T, 0, true>);
+        cudaFuncGetAttributes(&a, k_march<real, V, T, 0, false>);
     }
 }
+template <typename real, int V, int T>
+void touch_dft(bool lossy) {
+    cudaFuncAttributes a;
+    if (lossy) {
+        cudaFuncGetAttributes(&a, k_march<real, V, T, 3, true>);
+        cudaFuncGetAttributes(&a, k_march<real, V, T, 3, false>);
+    } else {
+        cudaFuncGetAttributes(&a, k_march<real, V, T, 2, true>);
+        cudaFuncGetAttributes(&a, k_march<real, V, T, 2, false>);
+    }
+}
+
 template <typename real, int V>
 void touch_V(bool lossy) {
     touch_T<real, V, 1>(lossy); touch_T<real, V, 2>(lossy); touch_T<real, V, 3>(lossy);
@@ -642,6 +721,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
     int done = 0;
     while (done < nsteps) {
         int T = min(tblock, nsteps - done);
+        if (q->nf > 0) T = min(T, 4);                   // fused-DFT kernels: depth <= 4
         if (T == 5 || T == 7) --T;                      // instantiated depths: 1, 2, 3, 4, 6, 8
         const int rem = nsteps - done - T;              // steps still to come after this pass
         MarchParams<real> mp;
@@ -673,8 +753,19 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.ezi_hist = (const real *)q->ezi_hist; mp.hxi_hist = (const real *)q->hxi_hist;
         mp.src_i = tfsf ? -1 : q->src_i; mp.src_j = q->src_j; mp.src_hard = q->src_hard;
         for (int s = 0; s < TMAX; ++s) mp.src[s] = (src && s < T) ? src[done + s] : 0.0;
+        mp.nf = q->nf;
+        mp.r_pt = (real *)q->ft.r_pt; mp.i_pt = (real *)q->ft.i_pt;
+        mp.dft_plane = (long long)q->rows_alloc * q->ny;
+        for (int s = 0; s < TMAX; ++s)
+            for (int f = 0; f < NFMAX; ++f) {
+                const bool on = q->nf > 0 && s < T && f < q->nf;
+                mp.dft_c[s][f] = on ? q->dft_cos[(size_t)(done + s) * q->nf + f] : 0.0;
+                mp.dft_s[s][f] = on ? q->dft_sin[(size_t)(done + s) * q->nf + f] : 0.0;
+            }
 
         int V = g_force_v ? g_force_v : plan.V;
+        if (q->nf > 0 && V == 4) V = 2;                 // fused-DFT kernels: vector width <= 2
+        if (q->nf > 0 && sizeof(real) == 8) V = 1;      // ... and 1 in float64 (register row sets)
         if (q->ny % V != 0 || (sizeof(real) == 8 && V == 4)) V = 1;
         if (T == 8 && V == 4) V = 2;                    // 9 register row sets of 4 columns do not fit
         if (T == 8 && sizeof(real) == 8) V = 1;         // ... nor do 9 sets of 2 doubles
@@ -691,8 +782,12 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         if (tfsf) {
             SrcTable tab;
             for (int s = 0; s < TMAX; ++s) tab.v[s] = mp.src[s];
+            tab.nf = (mp.nf > 0 && q->ft.r_in && q->ft.i_in) ? mp.nf : 0;
+            for (int s = 0; s < TMAX; ++s)
+                for (int f = 0; f < NFMAX; ++f) { tab.c[s][f] = mp.dft_c[s][f]; tab.s[s][f] = mp.dft_s[s][f]; }
             k_incident_line<real><<<1, 1024, 0, st>>>(q->ny, q->npml, T, (real *)q->ezi, (real *)q->hxi, (real *)q->bc,
-                                                      (real *)q->ezi_hist, (real *)q->hxi_hist, tab);
+                                                      (real *)q->ezi_hist, (real *)q->hxi_hist, (real *)q->ft.r_in,
+                                                      (real *)q->ft.i_in, tab);
             FDTD_LAUNCH_CHECK("k_incident_line");
         }
         int rc;
@@ -719,6 +814,8 @@ extern "C" {
 int fdtd2d_check_identity(const fdtd2d_problem *q, long long *violations) {
     FDTD_REQUIRE(q && violations, "fdtd2d_check_identity: null argument");
     FDTD_REQUIRE(q->dtype == FDTD_F32 || q->dtype == FDTD_F64, "fdtd2d_check_identity: unknown dtype %d", q->dtype);
+    FDTD_REQUIRE(q->nf >= 0 && q->nf <= NFMAX, "fdtd2d_advance: nf=%d outside [0, %d] (use fdtd2d_fourier per step beyond)", q->nf, NFMAX);
+    FDTD_REQUIRE(q->nf == 0 || (q->ft.r_pt && q->ft.i_pt && q->dft_cos && q->dft_sin), "fdtd2d_advance: running DFT needs r_pt, i_pt and the phase tables");
     FDTD_REQUIRE(q->ident_row_lo >= 0 && q->ident_row_hi <= q->nx && q->ident_col_lo >= 0 && q->ident_col_hi <= q->ny,
                  "fdtd2d_check_identity: identity ranges outside the grid");
     unsigned long long *bad = nullptr, host = 0;
@@ -743,6 +840,17 @@ int fdtd2d_check_identity(const fdtd2d_problem *q, long long *violations) {
 
 int fdtd2d_preload(int dtype, int ny, int lossy) {
     (void)ny;
+    if (lossy & 2) {           // bit 1: the fused-DFT kernels as well
+        const bool l = (lossy & 1) != 0;
+        if (dtype == FDTD_F32) {
+            touch_dft<float, 2, 1>(l); touch_dft<float, 2, 2>(l); touch_dft<float, 2, 3>(l); touch_dft<float, 2, 4>(l);
+            touch_dft<float, 1, 1>(l); touch_dft<float, 1, 2>(l); touch_dft<float, 1, 3>(l); touch_dft<float, 1, 4>(l);
+        } else if (dtype == FDTD_F64) {
+            touch_dft<double, 2, 1>(l); touch_dft<double, 2, 2>(l); touch_dft<double, 2, 3>(l); touch_dft<double, 2, 4>(l);
+            touch_dft<double, 1, 1>(l); touch_dft<double, 1, 2>(l); touch_dft<double, 1, 3>(l); touch_dft<double, 1, 4>(l);
+        }
+    }
+    lossy &= 1;
     if (dtype == FDTD_F32) {
         touch_V<float, 4>(lossy != 0);
         touch_V<float, 2>(lossy != 0);

@@ -253,7 +253,7 @@ class Fdtd2D:
                 self._hxi_hist = z1(self.max_tblock * 2)
             else:
                 self.ezi = self.hxi = self.bc = self._ezi_hist = self._hxi_hist = None
-            check(lib().fdtd2d_preload(code, self.ny, int(self.lossy)), "fdtd2d_preload")
+            check(lib().fdtd2d_preload(code, self.ny, int(self.lossy) | (2 if freqs is not None else 0)), "fdtd2d_preload")
             if self.check_identity() != 0:
                 raise _lib.FdtdError("PML vectors violate the identity-coefficient promise outside the layer")
             # running DFT (program 3_4): accumulators over the stored rows, updated after every step
@@ -361,8 +361,8 @@ class Fdtd2D:
         the slab driver between ghost exchanges) and leaves ``ez`` stale until a later non-lazy ``advance``."""
         if nsteps <= 0:
             return
-        if self.ft is not None:
-            # the DFT samples Ez after EVERY step: one fused single-step pass + the fourier kernel per step
+        if self.ft is not None and len(self.freqs) > 3:
+            # more frequencies than the fused kernels carry: one fused single-step pass + the fourier kernel per step
             for _ in range(int(nsteps)):
                 self._advance_fused(1, 1, False)
                 self._fourier(self.t)
@@ -384,6 +384,17 @@ class Fdtd2D:
         p = self._problem()
         if lazy_ez:
             p.flags |= _lib.LAZY_EZ
+        if self.ft is not None:
+            # running DFT fused into the passes: per-step phase factors, evaluated as the reference evaluates them
+            nf = len(self.freqs)
+            ph = [_phases(self.freqs, self.dt, self.t + 1 + k, False, self.np_dtype) for k in range(int(nsteps))]
+            cos_t = np.ascontiguousarray(np.stack([c for c, _ in ph]).reshape(-1), dtype=np.float64)
+            sin_t = np.ascontiguousarray(np.stack([s for _, s in ph]).reshape(-1), dtype=np.float64)
+            D = C.POINTER(C.c_double)
+            p.nf, p.ft = nf, self.ft.as_struct()
+            if not self.tfsf:
+                p.ft.r_in = p.ft.i_in = None
+            p.dft_cos, p.dft_sin = cos_t.ctypes.data_as(D), sin_t.ctypes.data_as(D)
         out = C.c_int(-1)
         with torch.cuda.device(self.device):
             check(lib().fdtd2d_advance(C.byref(p), self._cur, int(nsteps),

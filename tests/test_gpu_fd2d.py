@@ -195,6 +195,40 @@ def test_running_dft_matches_oracle(dtype):
         assert b.get(name).tobytes() == getattr(g, name).tobytes(), name
 
 
+@pytest.mark.parametrize("tblock", [1, 2, 3, 4, None])
+@pytest.mark.parametrize("nx,ny,npml", [(60, 72, 8), (300, 420, 10)])
+def test_fused_dft_all_depths(nx, ny, npml, tblock):
+    """The DFT fused into the passes (accumulators travel with the rows): every depth, a grid with a true interior
+    (interior + edge kernels), split advance calls -- bitwise equal to the per-step oracle."""
+    from simulation_b200 import fd2d, surface
+    ns = 57
+    g, src = cases.grid_program("3_4", nx, ny, ns, np.float32, npml=npml, radius=0.2, dft=True)
+    sim = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)),
+                      naz=g.naz.copy(), nbz=g.nbz.copy(), freqs=g.freqs)
+    sim.advance(20, tblock=tblock)
+    sim.advance(ns - 20, tblock=tblock)
+    orc.advance_2d(g, src)
+    for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy", "r_pt", "i_pt", "r_in", "i_in"):
+        got, want = sim.get(name), getattr(g, name)
+        assert got.tobytes() == want.tobytes(), (name, np.argwhere(got != want)[:4].tolist())
+
+
+def test_fused_dft_lossless_point_source_fp64():
+    """DFT on a lossless problem without TFSF (no source-sample accumulators), float64."""
+    from simulation_b200 import fd2d, surface
+    nx, ny, npml, ns = 90, 130, 8, 40
+    freqs = np.array((100e6, 900e6, 1500e6))
+    g = orc.Grid2D(nx, ny, npml, np.float64, point=(nx // 2 - 5, ny // 2 - 5), freqs=freqs)
+    g.ezi = np.zeros(ny)                      # the oracle's fourier samples ezi[6]; none here
+    src = orc.source_table("sine", ns, freq=1500e6)
+    sim = fd2d.Fdtd2D(nx, ny, npml, np.float64, source=fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6)),
+                      freqs=freqs)
+    sim.advance(ns)
+    orc.advance_2d(g, src)
+    for name in ("ez", "hx", "r_pt", "i_pt"):
+        assert sim.get(name).tobytes() == getattr(g, name).tobytes(), name
+
+
 def test_running_dft_numba_golden():
     """Program 3_4 as driven through the reference's numba functions (fastmath: tolerance, not bits)."""
     from simulation_b200 import fd2d, surface
