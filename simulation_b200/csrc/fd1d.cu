@@ -85,32 +85,34 @@ struct LineParams {
     double src[T1MAX];        // waveform samples of this pass (by value: no staging buffer to manage)
 };
 
-template <typename real, bool FLUX, bool DEBYE>
-__global__ void __launch_bounds__(NT) k1_advance(const __grid_constant__ LineParams<real> p) {
-    __shared__ real s_ex[NT * KC + 2];
-    __shared__ real s_hy[NT * KC + 2];
-    __shared__ real s_bc[4];
+// The T leap-frog steps of one CTA.  Every thread keeps the Ex / Hy of its own KC cells (slot c = k*NT + tid) in
+// registers next to the pointwise state; shared memory only carries values to the neighbouring cell
+// (hy[c-1] for the E half step, ex[c+1] for the H half step): 2 LDS + 2 STS per cell-step.  Both shared arrays are
+// shifted by one slot so that c-1 / c+1 of the first / last staged cell stay in bounds (halo garbage, never used).
+// EDGE: the staged range touches an end of the line (cells outside the line, the never-updated ex[0], ex[nx-1],
+// hy[nx-1], the ABC); interior CTAs run without any mask.
+template <typename real, bool FLUX, bool DEBYE, bool EDGE>
+__device__ __forceinline__ void line_body(const LineParams<real> &p, real *s_ex, real *s_hy, real *s_bc) {
     const int tid = threadIdx.x;
     const int seg_lo = blockIdx.x * p.seg;
     const int seg_hi = min(seg_lo + p.seg, p.nx);
     const int base = seg_lo - p.T;                 // global cell of staged slot 0 (may be negative)
     const real half = real(0.5);
 
-    // pointwise state / coefficients of the cells this thread owns: slot c = k*NT + tid
-    real dx[KC], ix[KC], sx[KC], c0[KC], c1[KC], c2[KC], c3[KC];
+    real ex[KC], hy[KC], dx[KC], ix[KC], sx[KC], c0[KC], c1[KC], c2[KC], c3[KC];
+    int src_k = -1;                                // which of this thread's cells carries the source (-1: none)
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         const int c = k * NT + tid, g = base + c;
-        const bool in = (g >= 0) && (g < p.nx);
-        s_ex[c] = in ? p.in[0][g] : real(0);
-        s_hy[c] = in ? p.in[1][g] : real(0);
-        dx[k] = ix[k] = sx[k] = real(0);
+        const bool in = !EDGE || ((g >= 0) && (g < p.nx));
+        ex[k] = in ? p.in[0][g] : real(0);
+        hy[k] = in ? p.in[1][g] : real(0);
+        dx[k] = ix[k] = sx[k] = c2[k] = c3[k] = real(0);
         if (FLUX) {
             dx[k] = in ? p.in[2][g] : real(0);
             ix[k] = in ? p.in[3][g] : real(0);
             c0[k] = in ? p.nax[g] : real(1);
             c1[k] = in ? p.nbx[g] : real(0);
-            c2[k] = c3[k] = real(0);
             if (DEBYE) {
                 sx[k] = in ? p.in[4][g] : real(0);
                 c2[k] = in ? p.ncx[g] : real(0);
@@ -119,83 +121,102 @@ __global__ void __launch_bounds__(NT) k1_advance(const __grid_constant__ LinePar
         } else {
             c0[k] = (in && p.ca) ? p.ca[g] : real(1);
             c1[k] = (in && p.cb) ? p.cb[g] : real(0.5);
-            c2[k] = c3[k] = real(0);
         }
+        if (p.src_index >= 0 && g == p.src_index) src_k = k;
+        s_hy[c + 1] = hy[k];
+        s_ex[c + 1] = ex[k];
     }
+    if (tid == 0) { s_hy[0] = s_ex[0] = real(0); s_hy[NT * KC + 1] = s_ex[NT * KC + 1] = real(0); }
     if (tid < 4) s_bc[tid] = p.abc ? p.bc_in[tid] : real(0);
     __syncthreads();
 
-    const bool has_left = p.abc && (base <= 0);                       // staged range contains cells 0, 1
-    const bool has_right = p.abc && (base + NT * KC >= p.nx);         // ... and cells nx-2, nx-1
+    const bool has_left = EDGE && p.abc && (base <= 0);                       // staged range contains cells 0, 1
+    const bool has_right = EDGE && p.abc && (base + NT * KC >= p.nx);         // ... and cells nx-2, nx-1
     for (int s = 0; s < p.T; ++s) {
-        const double sv = (p.src_index >= 0) ? p.src[s] : 0.0;
-        // ---- E half step on the owned cells (reads hy[i-1], hy[i])
-        real enew[KC];
+        // ---- E half step: ex (or dx -> ex) of the own cells; hy[i-1] comes from the neighbour through smem
+        real curl[KC];
 #pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            const int c = k * NT + tid, g = base + c;
-            real e = s_ex[c];
-            const bool upd = (g >= 1) && (g < p.nx) && (c >= 1);
-            const real curl = upd ? (s_hy[c - 1] - s_hy[c]) : real(0);
-            if (FLUX) {
-                real d = dx[k];
-                if (upd) d = d + half * curl;
-                if (p.src_field == 1 && g == p.src_index) d = inject<real>(d, sv, p.src_hard);
-                dx[k] = d;
-                if (upd) {
+        for (int k = 0; k < KC; ++k) curl[k] = s_hy[k * NT + tid] - hy[k];     // slot c-1 lives at index c
+        if (FLUX) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int g = base + k * NT + tid;
+                if (!EDGE || ((g >= 1) && (g < p.nx))) dx[k] = dx[k] + half * curl[k];
+            }
+            if (src_k >= 0 && p.src_field == 1) {          // at most one thread of the CTA
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (k == src_k) dx[k] = inject<real>(dx[k], p.src[s], p.src_hard);
+            }
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int g = base + k * NT + tid;
+                if (!EDGE || ((g >= 1) && (g < p.nx))) {
                     if (DEBYE) {
                         const real cs = c2[k] * sx[k];
-                        e = c0[k] * ((d - ix[k]) - cs);
-                        sx[k] = cs + (c3[k] * e);
+                        ex[k] = c0[k] * ((dx[k] - ix[k]) - cs);
+                        sx[k] = cs + (c3[k] * ex[k]);
                     } else {
-                        e = c0[k] * (d - ix[k]);
+                        ex[k] = c0[k] * (dx[k] - ix[k]);
                     }
-                    ix[k] = ix[k] + c1[k] * e;
+                    ix[k] = ix[k] + c1[k] * ex[k];
                 }
-            } else {
-                if (upd) e = (c0[k] * e) + (c1[k] * curl);
-                if (p.src_field == 0 && g == p.src_index) e = inject<real>(e, sv, p.src_hard);
             }
-            enew[k] = e;
+        } else {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int g = base + k * NT + tid;
+                if (!EDGE || ((g >= 1) && (g < p.nx))) ex[k] = (c0[k] * ex[k]) + (c1[k] * curl[k]);
+            }
+            if (src_k >= 0 && p.src_field == 0) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (k == src_k) ex[k] = inject<real>(ex[k], p.src[s], p.src_hard);
+            }
         }
 #pragma unroll
-        for (int k = 0; k < KC; ++k) s_ex[k * NT + tid] = enew[k];
+        for (int k = 0; k < KC; ++k) s_ex[k * NT + tid + 1] = ex[k];
         __syncthreads();
-        // ---- two-step-delay ABC (one thread; needs the finished E half step)
-        if (tid == 0) {
-            if (has_left) {
-                const int o = -base;                                   // slot of cell 0
-                const real e1 = s_ex[o + 1], b0 = s_bc[0], b1 = s_bc[1];
-                s_ex[o] = b0; s_bc[0] = b1; s_bc[1] = e1;
+        // ---- two-step-delay ABC (one thread; needs the finished E half step), then its owners re-read
+        if (EDGE && (has_left || has_right)) {
+            if (tid == 0) {
+                if (has_left) {
+                    const int o = -base + 1;                                   // index of cell 0
+                    const real e1 = s_ex[o + 1], b0 = s_bc[0], b1 = s_bc[1];
+                    s_ex[o] = b0; s_bc[0] = b1; s_bc[1] = e1;
+                }
+                if (has_right) {
+                    const int o = p.nx - 1 - base + 1;                         // index of cell nx-1
+                    const real e2 = s_ex[o - 1], b3 = s_bc[3], b2 = s_bc[2];
+                    s_ex[o] = b3; s_bc[3] = b2; s_bc[2] = e2;
+                }
             }
-            if (has_right) {
-                const int o = p.nx - 1 - base;                         // slot of cell nx-1
-                const real e2 = s_ex[o - 1], b3 = s_bc[3], b2 = s_bc[2];
-                s_ex[o] = b3; s_bc[3] = b2; s_bc[2] = e2;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int g = base + k * NT + tid;
+                if (g == 0 || g == p.nx - 1) ex[k] = s_ex[k * NT + tid + 1];
             }
         }
-        if (has_left || has_right) __syncthreads();
-        // ---- H half step (reads ex[i], ex[i+1])
-        real hnew[KC];
+        // ---- H half step: ex[i+1] comes from the neighbour through smem
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-            const int c = k * NT + tid, g = base + c;
-            real h = s_hy[c];
-            if (g >= 0 && g < p.nx - 1 && c + 1 < NT * KC) h = h + half * (s_ex[c] - s_ex[c + 1]);
-            hnew[k] = h;
+            const int g = base + k * NT + tid;
+            const real er = s_ex[k * NT + tid + 2];                            // slot c+1 lives at index c+2
+            if (!EDGE || ((g >= 0) && (g < p.nx - 1))) hy[k] = hy[k] + half * (ex[k] - er);
         }
 #pragma unroll
-        for (int k = 0; k < KC; ++k) s_hy[k * NT + tid] = hnew[k];
+        for (int k = 0; k < KC; ++k) s_hy[k * NT + tid + 1] = hy[k];
         __syncthreads();
     }
 
     // ---- write the owned segment to the other array set
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
-        const int c = k * NT + tid, g = base + c;
+        const int g = base + k * NT + tid;
         if (g >= seg_lo && g < seg_hi) {
-            p.out[0][g] = s_ex[c];
-            p.out[1][g] = s_hy[c];
+            p.out[0][g] = ex[k];
+            p.out[1][g] = hy[k];
             if (FLUX) {
                 p.out[2][g] = dx[k];
                 p.out[3][g] = ix[k];
@@ -208,6 +229,17 @@ __global__ void __launch_bounds__(NT) k1_advance(const __grid_constant__ LinePar
         const bool mine = (tid < 2) ? (seg_lo == 0) : (seg_hi == p.nx);
         if (mine) p.bc_out[tid] = s_bc[tid];
     }
+}
+
+template <typename real, bool FLUX, bool DEBYE>
+__global__ void __launch_bounds__(NT) k1_advance(const __grid_constant__ LineParams<real> p) {
+    __shared__ real s_ex[NT * KC + 2];
+    __shared__ real s_hy[NT * KC + 2];
+    __shared__ real s_bc[4];
+    const int base = blockIdx.x * p.seg - p.T;
+    const bool edge = (base < 1) || (base + NT * KC > p.nx - 1);      // CTA-uniform
+    if (edge) line_body<real, FLUX, DEBYE, true>(p, s_ex, s_hy, s_bc);
+    else      line_body<real, FLUX, DEBYE, false>(p, s_ex, s_hy, s_bc);
 }
 
 template <typename real>
