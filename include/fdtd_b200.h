@@ -172,6 +172,19 @@ typedef struct {
     int nf;
     fdtd_ftrans ft;
     const double *dft_cos, *dft_sin;
+    /* Halo exchange fused into the pass (multi-GPU slabs, one process per GPU; all zero = off).  The last pass of
+     * the call ALSO stores its first / last `halo` owned rows (dz, hx, hy, ihx, ihy[, iz]) into the neighbours'
+     * ghost rows through peer-mapped pointers (cudaIpcOpenMemHandle), row by row while it computes, and the last
+     * warp of the pass publishes `epoch` in the neighbours' sync words; the first pass of the next call spins on
+     * its own sync words until both neighbours have published epoch-1.  peer_up / peer_dn: the neighbours' two
+     * array sets (entries NULL where there is no neighbour); *_base: global row of their array row 0; sync_*: four
+     * zero-initialised 64-bit words per rank {from_up, from_down, counter, counter}; epoch: 1, 2, ... per call,
+     * the same on every rank.  nsteps <= halo. */
+    int halo;
+    void *peer_up[2][FDTD2D_NFIELDS], *peer_dn[2][FDTD2D_NFIELDS];
+    int peer_up_base, peer_dn_base;
+    void *sync_local, *sync_up, *sync_dn;
+    unsigned long long epoch;
 } fdtd2d_problem;
 
 /* Advance nsteps full time steps (reference order: ezinct, dfield+source, inctdz, efield, hxinct, hfield,

@@ -57,7 +57,11 @@ class Problem2D(C.Structure):
                 ("ezi_hist", C.c_void_p), ("hxi_hist", C.c_void_p),
                 ("src_i", C.c_int), ("src_j", C.c_int), ("src_hard", C.c_int),
                 ("ident_row_lo", C.c_int), ("ident_row_hi", C.c_int), ("ident_col_lo", C.c_int), ("ident_col_hi", C.c_int),
-                ("nf", C.c_int), ("ft", FTrans), ("dft_cos", C.POINTER(C.c_double)), ("dft_sin", C.POINTER(C.c_double))]
+                ("nf", C.c_int), ("ft", FTrans), ("dft_cos", C.POINTER(C.c_double)), ("dft_sin", C.POINTER(C.c_double)),
+                ("halo", C.c_int), ("peer_up", (C.c_void_p * NFIELDS) * 2), ("peer_dn", (C.c_void_p * NFIELDS) * 2),
+                ("peer_up_base", C.c_int), ("peer_dn_base", C.c_int),
+                ("sync_local", C.c_void_p), ("sync_up", C.c_void_p), ("sync_dn", C.c_void_p),
+                ("epoch", C.c_ulonglong)]
 
 
 # every symbol include/fdtd_b200.h declares: name -> (restype, argtypes)

@@ -42,6 +42,18 @@ struct MarchParams {
     real *r_pt, *i_pt;                         // [nf][rows_alloc][ny] accumulators, updated in place by the owner warp
     long long dft_plane;                       // elements per frequency plane
     double dft_c[TMAX][NFMAX], dft_s[TMAX][NFMAX];   // phase factors of every sub-step
+    // fused halo exchange over peer memory (multi-GPU): the rows within `halo` of the slab edges are ALSO stored into
+    // the neighbours' ghost rows; completion is announced through flags in the neighbours' memory
+    int push;                                  // this pass pushes its edge rows
+    int push_up_end, push_dn_begin;            // rows ro < push_up_end go up, rows ro >= push_dn_begin go down
+    real *up_dz, *up_hx, *up_hy, *up_ihx, *up_ihy, *up_iz;   // neighbour above: its OUT-set arrays (NULL: none)
+    real *dn_dz, *dn_hx, *dn_hy, *dn_ihx, *dn_ihy, *dn_iz;   // neighbour below
+    long long up_shift, dn_shift;              // element offset of a global row in the neighbour's arrays minus mine
+    int wait_flags, signal;                    // first / last pass of a call
+    unsigned long long *sync_local;            // {flag written by up, flag written by down, counter[0], counter[1]}
+    unsigned long long *flag_at_up, *flag_at_dn;   // where this rank announces itself (peer memory)
+    unsigned long long epoch;                  // sequence number of this advance call (1, 2, ...)
+    unsigned total_warps;                      // warps of both kernels of the pass
     int write_ez;                              // 0: this pass leaves ez untouched (it is never read by a pass)
     int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
     int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
@@ -388,6 +400,22 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
                         VecIO<real, V>::st(p.i_pt + f * p.dft_plane + off_s, O.iacc[f]);
                     }
             }
+            if (p.push) {        // halo exchange fused into the pass: peer stores over NVLink, row by row
+                if (ro < p.push_up_end && p.up_dz != nullptr) {
+                    const long long o = off_s + p.up_shift;
+                    VecIO<real, V>::st(p.up_dz + o, O.dz);   VecIO<real, V>::st(p.up_hx + o, O.hx);
+                    VecIO<real, V>::st(p.up_hy + o, O.hy);   VecIO<real, V>::st(p.up_ihx + o, O.ihx);
+                    VecIO<real, V>::st(p.up_ihy + o, O.ihy);
+                    if (LOSSY) VecIO<real, V>::st(p.up_iz + o, O.iz);
+                }
+                if (ro >= p.push_dn_begin && p.dn_dz != nullptr) {
+                    const long long o = off_s + p.dn_shift;
+                    VecIO<real, V>::st(p.dn_dz + o, O.dz);   VecIO<real, V>::st(p.dn_hx + o, O.hx);
+                    VecIO<real, V>::st(p.dn_hy + o, O.hy);   VecIO<real, V>::st(p.dn_ihx + o, O.ihx);
+                    VecIO<real, V>::st(p.dn_ihy + o, O.ihy);
+                    if (LOSSY) VecIO<real, V>::st(p.dn_iz + o, O.iz);
+                }
+            }
         }
         off_s += p.ny;
     };
@@ -428,6 +456,15 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         }
     }
     cp_async_wait<0>();
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // k-th id (0-based) of the ascending sequence 0,1,2,... with the sorted ids in `skip` removed
@@ -473,7 +510,32 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
             chunk = p.schunks[x / nsf];
         }
     }
+    if (p.wait_flags) {
+        // neighbours must have finished their previous call: their pushes into my ghost rows have landed, and they no
+        // longer read the ghost rows this call's pushes will overwrite
+        if (lane == 0) {
+            const unsigned long long need = p.epoch - 1;
+            if (p.flag_at_up != nullptr) while (ld_acquire_sys(p.sync_local + 0) < need) { }
+            if (p.flag_at_dn != nullptr) while (ld_acquire_sys(p.sync_local + 1) < need) { }
+        }
+        __syncwarp();
+    }
     march_body<real, V, T, MODE, FAST>(p, strip, chunk, lane, ring);
+    if (p.signal) {
+        // the last warp of the pass (both kernels counted) announces completion to the neighbours
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            unsigned long long *counter = p.sync_local + 2 + (p.epoch & 1ull);
+            const unsigned long long done = atomicAdd(counter, 1ull);
+            if (done + 1 == (unsigned long long)p.total_warps) {
+                atomicExch(counter, 0ull);
+                __threadfence_system();
+                if (p.flag_at_up != nullptr) st_release_sys(p.flag_at_up, p.epoch);
+                if (p.flag_at_dn != nullptr) st_release_sys(p.flag_at_dn, p.epoch);
+            }
+        }
+    }
 }
 
 // ---- incident line: T steps of the 1D auxiliary FDTD (ezinct ... hxinct), recording what the 2D pass
@@ -600,11 +662,13 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     }
     if (overflow) {                                      // tiny grids: everything through the careful kernel
         mp.n_sstrips = mp.n_schunks = 0;
+        mp.total_warps = (unsigned)(mp.nstrips * mp.nchunks);
         return launch_one<real, V, T, MODE, false>(mp, mp.nstrips * mp.nchunks, 1, st);
     }
     mp.n_sstrips = ns; mp.n_schunks = nc;
     const int nsf = mp.nstrips - ns, ncf = mp.nchunks - nc;
     const int n_careful = ns * mp.nchunks + nsf * nc, n_fast = nsf * ncf;
+    mp.total_warps = (unsigned)(n_careful + n_fast);
     // The careful kernel is small (edges only) and would run alone at a fraction of a wave: fork it onto a side
     // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
     SideStream *side = (n_careful > 0 && n_fast > 0 && g_serial == 2) ? side_stream() : nullptr;
@@ -753,6 +817,29 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.ezi_hist = (const real *)q->ezi_hist; mp.hxi_hist = (const real *)q->hxi_hist;
         mp.src_i = tfsf ? -1 : q->src_i; mp.src_j = q->src_j; mp.src_hard = q->src_hard;
         for (int s = 0; s < TMAX; ++s) mp.src[s] = (src && s < T) ? src[done + s] : 0.0;
+        {   // fused halo exchange: wait on the first pass of the call, push + announce on the last
+            const bool on = q->halo > 0;
+            void *const *up = q->peer_up[cur ^ 1];
+            void *const *dn = q->peer_dn[cur ^ 1];
+            mp.push = on && rem == 0;
+            mp.wait_flags = on && done == 0;
+            mp.signal = on && rem == 0;
+            mp.push_up_end = q->row_lo + q->halo;
+            mp.push_dn_begin = q->row_hi - q->halo;
+            mp.up_dz = on ? (real *)up[FDTD2D_DZ] : nullptr;   mp.up_hx = on ? (real *)up[FDTD2D_HX] : nullptr;
+            mp.up_hy = on ? (real *)up[FDTD2D_HY] : nullptr;   mp.up_ihx = on ? (real *)up[FDTD2D_IHX] : nullptr;
+            mp.up_ihy = on ? (real *)up[FDTD2D_IHY] : nullptr; mp.up_iz = on ? (real *)up[FDTD2D_IZ] : nullptr;
+            mp.dn_dz = on ? (real *)dn[FDTD2D_DZ] : nullptr;   mp.dn_hx = on ? (real *)dn[FDTD2D_HX] : nullptr;
+            mp.dn_hy = on ? (real *)dn[FDTD2D_HY] : nullptr;   mp.dn_ihx = on ? (real *)dn[FDTD2D_IHX] : nullptr;
+            mp.dn_ihy = on ? (real *)dn[FDTD2D_IHY] : nullptr; mp.dn_iz = on ? (real *)dn[FDTD2D_IZ] : nullptr;
+            mp.up_shift = (long long)(q->row_base - q->peer_up_base) * q->ny;
+            mp.dn_shift = (long long)(q->row_base - q->peer_dn_base) * q->ny;
+            mp.sync_local = (unsigned long long *)q->sync_local;
+            mp.flag_at_up = (on && up[FDTD2D_DZ]) ? (unsigned long long *)q->sync_up + 1 : nullptr;   // I am its "down"
+            mp.flag_at_dn = (on && dn[FDTD2D_DZ]) ? (unsigned long long *)q->sync_dn + 0 : nullptr;   // I am its "up"
+            mp.epoch = q->epoch;
+            mp.total_warps = 0;
+        }
         mp.nf = q->nf;
         mp.r_pt = (real *)q->ft.r_pt; mp.i_pt = (real *)q->ft.i_pt;
         mp.dft_plane = (long long)q->rows_alloc * q->ny;
@@ -814,8 +901,6 @@ extern "C" {
 int fdtd2d_check_identity(const fdtd2d_problem *q, long long *violations) {
     FDTD_REQUIRE(q && violations, "fdtd2d_check_identity: null argument");
     FDTD_REQUIRE(q->dtype == FDTD_F32 || q->dtype == FDTD_F64, "fdtd2d_check_identity: unknown dtype %d", q->dtype);
-    FDTD_REQUIRE(q->nf >= 0 && q->nf <= NFMAX, "fdtd2d_advance: nf=%d outside [0, %d] (use fdtd2d_fourier per step beyond)", q->nf, NFMAX);
-    FDTD_REQUIRE(q->nf == 0 || (q->ft.r_pt && q->ft.i_pt && q->dft_cos && q->dft_sin), "fdtd2d_advance: running DFT needs r_pt, i_pt and the phase tables");
     FDTD_REQUIRE(q->ident_row_lo >= 0 && q->ident_row_hi <= q->nx && q->ident_col_lo >= 0 && q->ident_col_hi <= q->ny,
                  "fdtd2d_check_identity: identity ranges outside the grid");
     unsigned long long *bad = nullptr, host = 0;
@@ -897,6 +982,13 @@ int fdtd2d_advance(const fdtd2d_problem *q, int cur, int nsteps, const double *s
                      "fdtd2d_advance: %d steps need ghost rows [%d,%d) but only [%d,%d) are stored", nsteps, need_lo,
                      need_hi, q->row_base, q->row_base + q->rows_alloc);
     }
+    if (q->halo > 0) {
+        FDTD_REQUIRE(q->halo <= q->row_hi - q->row_lo && q->sync_local && q->epoch >= 1, "fdtd2d_advance: fused halo exchange needs halo <= owned rows, sync_local and epoch >= 1");
+        FDTD_REQUIRE(!q->peer_up[0][FDTD2D_DZ] == !q->sync_up && !q->peer_dn[0][FDTD2D_DZ] == !q->sync_dn, "fdtd2d_advance: a peer needs both its arrays and its sync words");
+        FDTD_REQUIRE(nsteps <= q->halo, "fdtd2d_advance: %d steps but only %d halo rows are exchanged", nsteps, q->halo);
+    }
+    FDTD_REQUIRE(q->nf >= 0 && q->nf <= NFMAX, "fdtd2d_advance: nf=%d outside [0, %d] (use fdtd2d_fourier per step beyond)", q->nf, NFMAX);
+    FDTD_REQUIRE(q->nf == 0 || (q->ft.r_pt && q->ft.i_pt && q->dft_cos && q->dft_sin), "fdtd2d_advance: running DFT needs r_pt, i_pt and the phase tables");
     FDTD_REQUIRE(q->ident_row_lo >= 0 && q->ident_row_hi <= q->nx && q->ident_col_lo >= 0 && q->ident_col_hi <= q->ny,
                  "fdtd2d_advance: identity ranges outside the grid");
     const bool lossy = (q->flags & FDTD_LOSSY) != 0, tfsf = (q->flags & FDTD_TFSF) != 0;

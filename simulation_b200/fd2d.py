@@ -354,7 +354,7 @@ class Fdtd2D:
             check(lib().fdtd2d_check_identity(C.byref(p), C.byref(bad)), "fdtd2d_check_identity")
         return int(bad.value)
 
-    def advance(self, nsteps: int, tblock: Optional[int] = None, lazy_ez: bool = False) -> None:
+    def advance(self, nsteps: int, tblock: Optional[int] = None, lazy_ez: bool = False, epoch: Optional[int] = None) -> None:
         """``nsteps`` full time steps through the fused, temporally blocked kernel (asynchronous).
 
         ``ez`` is an output only, so just the last pass stores it; ``lazy_ez=True`` skips even that (used by
@@ -364,17 +364,17 @@ class Fdtd2D:
         if self.ft is not None and len(self.freqs) > 3:
             # more frequencies than the fused kernels carry: one fused single-step pass + the fourier kernel per step
             for _ in range(int(nsteps)):
-                self._advance_fused(1, 1, False)
+                self._advance_fused(1, 1, False, None)
                 self._fourier(self.t)
             return
-        self._advance_fused(int(nsteps), tblock, lazy_ez)
+        self._advance_fused(int(nsteps), tblock, lazy_ez, epoch)
 
     def _fourier(self, t: int) -> None:
         with torch.cuda.device(self.device):
             fourier(t, len(self.freqs), self.rows_alloc, self.ny, self.dt, self.freqs, self.ezi,
                     self.tensor("ez", stored=True), self.ft)
 
-    def _advance_fused(self, nsteps: int, tblock, lazy_ez: bool) -> None:
+    def _advance_fused(self, nsteps: int, tblock, lazy_ez: bool, epoch: Optional[int] = None) -> None:
         tb = int(tblock if tblock is not None else self.tblock)
         if tb > self.max_tblock:
             raise _lib.FdtdError(f"tblock {tb} exceeds the deepest supported time block {self.max_tblock}")
@@ -384,6 +384,21 @@ class Fdtd2D:
         p = self._problem()
         if lazy_ez:
             p.flags |= _lib.LAZY_EZ
+        if epoch is not None and getattr(self, "p2p", None) is not None:
+            # halo exchange fused into the pass: peer-mapped neighbour arrays + sync words (see slab.py)
+            x = self.p2p
+            p.halo, p.epoch = int(x["halo"]), int(epoch)
+            p.sync_local = x["sync"].data_ptr()
+            for side, key in (("up", "peer_up"), ("dn", "peer_dn")):
+                nb = x[side]
+                if nb is None:
+                    continue
+                for s in range(2):
+                    for k, n in enumerate(FIELD_NAMES):
+                        tt = nb["sets"][s].get(n)
+                        getattr(p, key)[s][k] = None if tt is None else tt.data_ptr()
+                setattr(p, key + "_base", int(nb["row_base"]))
+                setattr(p, "sync_" + side, nb["sync"].data_ptr())
         if self.ft is not None:
             # running DFT fused into the passes: per-step phase factors, evaluated as the reference evaluates them
             nf = len(self.freqs)

@@ -13,6 +13,7 @@ Result: every rank's owned rows are bit-identical to the same rows of a single-d
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import numpy as np
@@ -56,6 +57,19 @@ class SlabFdtd2D:
         self.down = self.rank + 1 if self.rank < self.world - 1 else None
         self.exchanges = 0
         self._ghost_dirty = False
+        self._epoch = 0
+        self.halo_mode = "nccl"
+        want = os.environ.get("FDTD_SLAB_HALO", "p2p")
+        if self.world > 1 and want == "p2p" and hasattr(self.engine, "_sets") and self.engine.ft is None:
+            try:
+                self._enable_p2p()
+            except Exception as e:                      # no peer access / IPC: the grouped NCCL exchange still works
+                self.halo_mode = f"nccl (p2p unavailable: {type(e).__name__}: {e})"
+            ok = torch.tensor([1 if self.halo_mode == "p2p" else 0], device=self.engine.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0 and self.halo_mode == "p2p":
+                self.halo_mode = "nccl (a peer could not map this rank)"
+                self.engine.p2p = None
 
     # ---- delegation ---------------------------------------------------------------------------------
     @property
@@ -82,6 +96,31 @@ class SlabFdtd2D:
 
     def synchronize(self):
         self.engine.synchronize()
+
+    # ---- fused halo exchange over peer memory ------------------------------------------------------------
+    def _enable_p2p(self) -> None:
+        """Map the neighbours' state arrays and sync words into this process (CUDA IPC through torch's tensor
+        sharing) so that the pass itself stores its edge rows into their ghost rows and flags completion there."""
+        from torch.multiprocessing.reductions import reduce_tensor
+        eng = self.engine
+        names = self._names()
+        sync = torch.zeros(4, dtype=torch.int64, device=eng.device)
+        mine = {"row_base": eng.row_base, "sync": reduce_tensor(sync),
+                "sets": [{n: reduce_tensor(eng._sets[s][n]) for n in names} for s in range(2)]}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+
+        def open_peer(r):
+            if r is None:
+                return None
+            d = everyone[r]
+            rebuild = lambda pair: pair[0](*pair[1])
+            return {"row_base": d["row_base"], "sync": rebuild(d["sync"]),
+                    "sets": [{n: rebuild(d["sets"][s][n]) for n in names} for s in range(2)]}
+
+        eng.p2p = {"halo": self.ghost, "sync": sync, "up": open_peer(self.up), "dn": open_peer(self.down)}
+        self.halo_mode = "p2p"
+        dist.barrier(group=self.group)
 
     # ---- ghost exchange ------------------------------------------------------------------------------
     def _names(self):
@@ -111,13 +150,27 @@ class SlabFdtd2D:
         """``nsteps`` steps: blocks of at most ``ghost`` steps, a ghost exchange after every block."""
         left = int(nsteps)
         if self._ghost_dirty:
+            if self.halo_mode == "p2p":
+                # NCCL refresh of uploaded state: every rank must be idle on both sides of it
+                torch.cuda.synchronize(self.engine.device)
+                dist.barrier(group=self.group)
             self.exchange_ghosts()
+            self.exchanges -= 1
+            if self.halo_mode == "p2p":
+                torch.cuda.synchronize(self.engine.device)
+                dist.barrier(group=self.group)
             self._ghost_dirty = False
         while left > 0:
             n = min(left, self.ghost) if self.world > 1 else left
             left -= n
-            self.engine.advance(n, tblock=tblock, lazy_ez=left > 0)    # ez is stored by the last block only
-            self.exchange_ghosts()
+            if self.halo_mode == "p2p":
+                # the pass pushes its edge rows into the neighbours' ghost rows and waits on their flags itself
+                self._epoch += 1
+                self.engine.advance(n, tblock=tblock, lazy_ez=left > 0, epoch=self._epoch)
+                self.exchanges += 1
+            else:
+                self.engine.advance(n, tblock=tblock, lazy_ez=left > 0)    # ez is stored by the last block only
+                self.exchange_ghosts()
 
     def gather(self, name: str) -> Optional[np.ndarray]:
         """Whole-grid field on rank 0 (tests / small grids only)."""

@@ -44,7 +44,11 @@ def main():
                 ok = False
         assert np.abs(fields["ez"]).max() > 1e-3
         print(f"slab x{dist.get_world_size()} {prog} {nx}x{ny} ns={ns} T={tblock}: {'OK' if ok else 'FAIL'}, "
-              f"{s.exchanges} exchanges", flush=True)
+              f"{s.exchanges} exchanges, halo mode: {s.halo_mode}", flush=True)
+        want = os.environ.get("FDTD_SLAB_HALO", "p2p")
+        if want == "p2p" and s.halo_mode != "p2p":
+            print("P2P halo exchange was requested but is not active", flush=True)
+            ok = False
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

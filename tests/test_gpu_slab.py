@@ -23,7 +23,8 @@ def _free_port():
     ("3_3", 900, 1200, 24, 80, 4),       # TFSF: every rank replicates the incident line
     ("3_2", 517, 640, 16, 33, 1),        # uneven split, exchange every step
 ])
-def test_slab_equals_single_device(prog, nx, ny, npml, ns, tblock):
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+def test_slab_equals_single_device(prog, nx, ny, npml, ns, tblock, halo):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -31,5 +32,5 @@ def test_slab_equals_single_device(prog, nx, ny, npml, ns, tblock):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "slab_nccl_worker.py"), prog, str(nx), str(ny), str(npml), str(ns), str(tblock)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, FDTD_SLAB_HALO=halo))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
