@@ -71,6 +71,8 @@ int fdtd_memset0(void *dptr, size_t bytes, void *stream);
 int fdtd_upload(void *dptr, const void *hptr, size_t bytes, void *stream);
 int fdtd_download(void *hptr, const void *dptr, size_t bytes, void *stream);
 int fdtd_stream_sync(void *stream);
+/* let kernels of the current device dereference memory of `peer_device` (needed for the fused halo exchange) */
+int fdtd_enable_peer_access(int peer_device);
 
 /* ------------------------------------------------------------- 1D: reference-named step functions */
 /* ex[1:nx] = ca*ex + cb*(hy[i-1]-hy[i]); then the source.  ca == NULL means 1, cb == NULL means 0.5.

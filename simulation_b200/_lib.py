@@ -76,6 +76,7 @@ SYMBOLS = {
     "fdtd_upload": (_I, [_P, _P, C.c_size_t, _P]),
     "fdtd_download": (_I, [_P, _P, C.c_size_t, _P]),
     "fdtd_stream_sync": (_I, [_P]),
+    "fdtd_enable_peer_access": (_I, [_I]),
     "fdtd1d_exfield": (_I, [_I, _I, _P, _P, _P, _P, C.POINTER(Source), _P]),
     "fdtd1d_hyfield": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "fdtd1d_dxfield": (_I, [_I, _I, _P, _P, C.POINTER(Source), _P]),

@@ -76,6 +76,19 @@ int fdtd_download(void *hptr, const void *dptr, size_t bytes, void *stream) {
     return FDTD_OK;
 }
 
+int fdtd_enable_peer_access(int peer_device) {
+    int dev = 0;
+    FDTD_CUDA(cudaGetDevice(&dev));
+    if (peer_device == dev) return FDTD_OK;
+    int can = 0;
+    FDTD_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    FDTD_REQUIRE(can, "device %d cannot access device %d over P2P", dev, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return FDTD_OK; }
+    if (e != cudaSuccess) return fdtd::cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+    return FDTD_OK;
+}
+
 int fdtd_stream_sync(void *stream) {
     FDTD_CUDA(cudaStreamSynchronize(fdtd::as_stream(stream)));
     return FDTD_OK;

@@ -118,7 +118,13 @@ class SlabFdtd2D:
             return {"row_base": d["row_base"], "sync": rebuild(d["sync"]),
                     "sets": [{n: rebuild(d["sets"][s][n]) for n in names} for s in range(2)]}
 
-        eng.p2p = {"halo": self.ghost, "sync": sync, "up": open_peer(self.up), "dn": open_peer(self.down)}
+        from ._lib import check, lib
+        peers = {"up": open_peer(self.up), "dn": open_peer(self.down)}
+        with torch.cuda.device(eng.device):
+            for nb in peers.values():
+                if nb is not None:       # the mapping lives on the neighbour's device: let my kernels dereference it
+                    check(lib().fdtd_enable_peer_access(int(nb["sync"].device.index)), "fdtd_enable_peer_access")
+        eng.p2p = {"halo": self.ghost, "sync": sync, "up": peers["up"], "dn": peers["dn"]}
         self.halo_mode = "p2p"
         dist.barrier(group=self.group)
 
