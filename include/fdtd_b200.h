@@ -71,7 +71,13 @@ int fdtd_memset0(void *dptr, size_t bytes, void *stream);
 int fdtd_upload(void *dptr, const void *hptr, size_t bytes, void *stream);
 int fdtd_download(void *hptr, const void *dptr, size_t bytes, void *stream);
 int fdtd_stream_sync(void *stream);
-/* let kernels of the current device dereference memory of `peer_device` (needed for the fused halo exchange) */
+/* CUDA IPC for the fused halo exchange (one process per GPU): export a 64-byte handle of an allocation made with
+ * fdtd_malloc, open it in the neighbour's process (with ITS device current) and get a pointer its kernels can store
+ * through; close before the owner frees */
+int fdtd_ipc_export(const void *dptr, void *handle64);
+int fdtd_ipc_open(const void *handle64, void **mapped);
+int fdtd_ipc_close(void *mapped);
+/* let kernels of the current device dereference memory of `peer_device` */
 int fdtd_enable_peer_access(int peer_device);
 
 /* ------------------------------------------------------------- 1D: reference-named step functions */

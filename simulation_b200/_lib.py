@@ -77,6 +77,9 @@ SYMBOLS = {
     "fdtd_download": (_I, [_P, _P, C.c_size_t, _P]),
     "fdtd_stream_sync": (_I, [_P]),
     "fdtd_enable_peer_access": (_I, [_I]),
+    "fdtd_ipc_export": (_I, [_P, _P]),
+    "fdtd_ipc_open": (_I, [_P, C.POINTER(_P)]),
+    "fdtd_ipc_close": (_I, [_P]),
     "fdtd1d_exfield": (_I, [_I, _I, _P, _P, _P, _P, C.POINTER(Source), _P]),
     "fdtd1d_hyfield": (_I, [_I, _I, _P, _P, _P, _I, _P]),
     "fdtd1d_dxfield": (_I, [_I, _I, _P, _P, C.POINTER(Source), _P]),
@@ -132,3 +135,42 @@ def dtype_code(np_dtype) -> int:
     if dt == np.float64:
         return F64
     raise FdtdError(f"unsupported dtype {dt}: the path computes in float32 or float64")
+
+
+class DeviceBuffer:
+    """Device memory from the library's own allocator (cudaMalloc), exportable over CUDA IPC; torch wraps it without
+    a copy through ``__cuda_array_interface__``.  Freed with the object."""
+
+    def __init__(self, shape, np_dtype):
+        import numpy as np
+        self.shape = tuple(int(x) for x in shape)
+        self.np_dtype = np.dtype(np_dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.np_dtype.itemsize
+        p = C.c_void_p()
+        check(lib().fdtd_malloc(C.byref(p), max(self.nbytes, 16)), "fdtd_malloc")
+        self.ptr = p.value
+        check(lib().fdtd_memset0(C.c_void_p(self.ptr), max(self.nbytes, 16), None), "fdtd_memset0")
+        check(lib().fdtd_stream_sync(None), "fdtd_stream_sync")
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": self.np_dtype.str, "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(lib().fdtd_ipc_export(C.c_void_p(self.ptr), buf), "fdtd_ipc_export")
+        return buf.raw
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None):
+                lib().fdtd_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def ipc_open(handle: bytes) -> int:
+    out = C.c_void_p()
+    check(lib().fdtd_ipc_open(C.create_string_buffer(handle, 64), C.byref(out)), "fdtd_ipc_open")
+    return int(out.value)

@@ -1,5 +1,6 @@
 // Error reporting, device facts and the optional allocator / copy helpers of the C ABI.
 #include "common.cuh"
+#include <string.h>
 
 namespace fdtd {
 
@@ -73,6 +74,28 @@ int fdtd_upload(void *dptr, const void *hptr, size_t bytes, void *stream) {
 
 int fdtd_download(void *hptr, const void *dptr, size_t bytes, void *stream) {
     FDTD_CUDA(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, fdtd::as_stream(stream)));
+    return FDTD_OK;
+}
+
+int fdtd_ipc_export(const void *dptr, void *handle64) {
+    FDTD_REQUIRE(dptr && handle64, "fdtd_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    FDTD_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), const_cast<void *>(dptr)));
+    return FDTD_OK;
+}
+
+int fdtd_ipc_open(const void *handle64, void **mapped) {
+    FDTD_REQUIRE(handle64 && mapped, "fdtd_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    // opened with the CONSUMER's device current: the mapping belongs to this device's context and peer access to
+    // the exporting GPU is enabled on demand, so kernels of this device can store into it over NVLink
+    FDTD_CUDA(cudaIpcOpenMemHandle(mapped, h, cudaIpcMemLazyEnablePeerAccess));
+    return FDTD_OK;
+}
+
+int fdtd_ipc_close(void *mapped) {
+    FDTD_CUDA(cudaIpcCloseMemHandle(mapped));
     return FDTD_OK;
 }
 

@@ -217,7 +217,8 @@ class Fdtd2D:
     """
 
     def __init__(self, nx: int, ny: int, npml: int = 0, dtype=np.float32, *, source=None, naz=None, nbz=None,
-                 device=None, tblock: Optional[int] = None, rows=None, ghost: int = 0, freqs=None, dt: float = surface.DT):
+                 device=None, tblock: Optional[int] = None, rows=None, ghost: int = 0, freqs=None, dt: float = surface.DT,
+                 ipc: bool = False):
         if not torch.cuda.is_available():
             raise _lib.FdtdError("Fdtd2D needs a CUDA device: the product has no CPU path")
         lib()
@@ -240,8 +241,19 @@ class Fdtd2D:
         with torch.cuda.device(self.device):
             shape = (self.rows_alloc, self.ny)
             names = FIELD_NAMES if self.lossy else FIELD_NAMES[:-1]
-            self._sets = [{n: torch.zeros(shape, dtype=self.dtype, device=self.device) for n in names}
-                          for _ in range(2)]
+            # ipc=True: state arrays come from the library's allocator so that the neighbour ranks can map them
+            # (fused halo exchange, slab.py); torch wraps them in place
+            self._buffers = []
+
+            def new_state():
+                if not ipc:
+                    return torch.zeros(shape, dtype=self.dtype, device=self.device)
+                buf = _lib.DeviceBuffer(shape, self.np_dtype)
+                self._buffers.append(buf)
+                return torch.as_tensor(buf, device=self.device)
+            self._sets = [{n: new_state() for n in names} for _ in range(2)]
+            self._ipc_handles = None if not ipc else [
+                {n: self._buffers[s * len(names) + k].ipc_handle() for k, n in enumerate(names)} for s in range(2)]
             self._cur = 0
             self.naz = self._to_dev_rows(naz, fill=1.0)
             self.nbz = self._to_dev_rows(nbz, fill=0.0) if self.lossy else None
@@ -388,17 +400,16 @@ class Fdtd2D:
             # halo exchange fused into the pass: peer-mapped neighbour arrays + sync words (see slab.py)
             x = self.p2p
             p.halo, p.epoch = int(x["halo"]), int(epoch)
-            p.sync_local = x["sync"].data_ptr()
+            p.sync_local = x["sync"].ptr
             for side, key in (("up", "peer_up"), ("dn", "peer_dn")):
                 nb = x[side]
                 if nb is None:
                     continue
                 for s in range(2):
                     for k, n in enumerate(FIELD_NAMES):
-                        tt = nb["sets"][s].get(n)
-                        getattr(p, key)[s][k] = None if tt is None else tt.data_ptr()
+                        getattr(p, key)[s][k] = nb["sets"][s].get(n)          # peer-mapped raw pointers
                 setattr(p, key + "_base", int(nb["row_base"]))
-                setattr(p, "sync_" + side, nb["sync"].data_ptr())
+                setattr(p, "sync_" + side, nb["sync"])
         if self.ft is not None:
             # running DFT fused into the passes: per-step phase factors, evaluated as the reference evaluates them
             nf = len(self.freqs)

@@ -47,9 +47,13 @@ class SlabFdtd2D:
         self.row_lo, self.row_hi = partition(self.nx, self.world, self.rank)
         if self.world > 1 and (self.row_hi - self.row_lo) < self.ghost:
             raise ValueError(f"slab of {self.row_hi - self.row_lo} rows is thinner than the ghost band {self.ghost}")
+        want = os.environ.get("FDTD_SLAB_HALO", "p2p")
+        p2p_wanted = self.world > 1 and want == "p2p" and engine_factory is None and engine_kw.get("freqs") is None
         if engine_factory is None:
             from .fd2d import Fdtd2D
             engine_factory = Fdtd2D
+        if p2p_wanted:
+            engine_kw = dict(engine_kw, ipc=True)
         self.engine = engine_factory(self.nx, self.ny, npml, dtype, rows=(self.row_lo, self.row_hi),
                                      ghost=self.ghost if self.world > 1 else 0, tblock=tblock, **engine_kw)
         self.row_base = self.engine.row_base
@@ -59,8 +63,7 @@ class SlabFdtd2D:
         self._ghost_dirty = False
         self._epoch = 0
         self.halo_mode = "nccl"
-        want = os.environ.get("FDTD_SLAB_HALO", "p2p")
-        if self.world > 1 and want == "p2p" and hasattr(self.engine, "_sets") and self.engine.ft is None:
+        if p2p_wanted:
             try:
                 self._enable_p2p()
             except Exception as e:                      # no peer access / IPC: the grouped NCCL exchange still works
@@ -99,34 +102,27 @@ class SlabFdtd2D:
 
     # ---- fused halo exchange over peer memory ------------------------------------------------------------
     def _enable_p2p(self) -> None:
-        """Map the neighbours' state arrays and sync words into this process (CUDA IPC through torch's tensor
-        sharing) so that the pass itself stores its edge rows into their ghost rows and flags completion there."""
-        from torch.multiprocessing.reductions import reduce_tensor
+        """Map the neighbours' state arrays and sync words into this process (CUDA IPC, opened with THIS rank's
+        device current) so that the pass itself stores its edge rows into their ghost rows and flags completion."""
+        from . import _lib
         eng = self.engine
         names = self._names()
-        sync = torch.zeros(4, dtype=torch.int64, device=eng.device)
-        mine = {"row_base": eng.row_base, "sync": reduce_tensor(sync),
-                "sets": [{n: reduce_tensor(eng._sets[s][n]) for n in names} for s in range(2)]}
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine, group=self.group)
-
-        def open_peer(r):
-            if r is None:
-                return None
-            d = everyone[r]
-            rebuild = lambda pair: pair[0](*pair[1])
-            return {"row_base": d["row_base"], "sync": rebuild(d["sync"]),
-                    "sets": [{n: rebuild(d["sets"][s][n]) for n in names} for s in range(2)]}
-
-        from ._lib import check, lib
-        peers = {"up": open_peer(self.up), "dn": open_peer(self.down)}
         with torch.cuda.device(eng.device):
-            for nb in peers.values():
-                if nb is not None:       # the mapping lives on the neighbour's device: let my kernels dereference it
-                    check(lib().fdtd_enable_peer_access(int(nb["sync"].device.index)), "fdtd_enable_peer_access")
-        eng.p2p = {"halo": self.ghost, "sync": sync, "up": peers["up"], "dn": peers["dn"]}
-        self.halo_mode = "p2p"
-        dist.barrier(group=self.group)
+            sync = _lib.DeviceBuffer((4,), np.int64)
+            mine = {"row_base": eng.row_base, "sync": sync.ipc_handle(),
+                    "sets": [{n: eng._ipc_handles[s][n] for n in names} for s in range(2)]}
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=self.group)
+
+            def open_peer(r):
+                if r is None:
+                    return None
+                d = everyone[r]
+                return {"row_base": d["row_base"], "sync": _lib.ipc_open(d["sync"]),
+                        "sets": [{n: _lib.ipc_open(d["sets"][s][n]) for n in names} for s in range(2)]}
+
+            eng.p2p = {"halo": self.ghost, "sync": sync, "up": open_peer(self.up), "dn": open_peer(self.down)}
+        self.halo_mode = "p2p"            # the caller's all_reduce doubles as the barrier after the mapping
 
     # ---- ghost exchange ------------------------------------------------------------------------------
     def _names(self):
