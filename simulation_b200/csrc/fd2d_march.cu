@@ -45,6 +45,7 @@ struct MarchParams {
     // fused halo exchange over peer memory (multi-GPU): the rows within `halo` of the slab edges are ALSO stored into
     // the neighbours' ghost rows; completion is announced through flags in the neighbours' memory
     int push;                                  // this pass pushes its edge rows
+    int halo_on, own_lo, own_hi;               // fused exchange enabled; rows this rank owns (host-side classification)
     int push_up_end, push_dn_begin;            // rows ro < push_up_end go up, rows ro >= push_dn_begin go down
     real *up_dz, *up_hx, *up_hy, *up_ihx, *up_ihy, *up_iz;   // neighbour above: its OUT-set arrays (NULL: none)
     real *dn_dz, *dn_hx, *dn_hy, *dn_ihx, *dn_ihy, *dn_iz;   // neighbour below
@@ -53,7 +54,7 @@ struct MarchParams {
     unsigned long long *sync_local;            // {flag written by up, flag written by down, counter[0], counter[1]}
     unsigned long long *flag_at_up, *flag_at_dn;   // where this rank announces itself (peer memory)
     unsigned long long epoch;                  // sequence number of this advance call (1, 2, ...)
-    unsigned total_warps;                      // warps of both kernels of the pass
+    unsigned total_warps;                      // warps of the careful kernel of the pass (the only ones that touch ghosts)
     int write_ez;                              // 0: this pass leaves ez untouched (it is never read by a pass)
     int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
     int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
@@ -400,7 +401,9 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
                         VecIO<real, V>::st(p.i_pt + f * p.dft_plane + off_s, O.iacc[f]);
                     }
             }
-            if (p.push) {        // halo exchange fused into the pass: peer stores over NVLink, row by row
+            // halo exchange fused into the pass: peer stores over NVLink, row by row.  Only the careful kernel
+            // pushes: the host lists every chunk that owns a pushed row (or reads a ghost row) as special.
+            if (!FAST && p.push) {
                 if (ro < p.push_up_end && p.up_dz != nullptr) {
                     const long long o = off_s + p.up_shift;
                     VecIO<real, V>::st(p.up_dz + o, O.dz);   VecIO<real, V>::st(p.up_hx + o, O.hx);
@@ -510,7 +513,9 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
             chunk = p.schunks[x / nsf];
         }
     }
-    if (p.wait_flags) {
+    // Fused halo exchange (multi-GPU).  Ghost rows are read, and edge rows pushed, by careful warps only (the host
+    // lists those chunks as special), so the handshake lives in the careful kernel; the interior kernel carries none.
+    if (!FAST && p.wait_flags) {
         // neighbours must have finished their previous call: their pushes into my ghost rows have landed, and they no
         // longer read the ghost rows this call's pushes will overwrite
         if (lane == 0) {
@@ -521,8 +526,8 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
         __syncwarp();
     }
     march_body<real, V, T, MODE, FAST>(p, strip, chunk, lane, ring);
-    if (p.signal) {
-        // the last warp of the pass (both kernels counted) announces completion to the neighbours
+    if (!FAST && p.signal) {
+        // the last careful warp of the pass announces completion to the neighbours
         __threadfence_system();
         __syncwarp();
         if (lane == 0) {
@@ -655,6 +660,8 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
         const int lo = i0 - T - 1, hi = i1 + 2 * T + RING + 2; // rows touched (fetch run-ahead included): [lo, hi)
         bool special = (lo < max(max(1, mp.in_lo), mp.ident_row_lo)) || (hi > min(min(mp.nx - 1, mp.in_hi), mp.ident_row_hi));
         if (mp.tfsf) special = special || (ia - 1 >= lo && ia - 1 < hi) || (iz_ >= lo && iz_ < hi);
+        // fused halo exchange: chunks that touch a ghost row or own a pushed row carry the handshake
+        if (mp.halo_on) special = special || lo < mp.own_lo || hi > mp.own_hi || i0 < mp.push_up_end || i1 > mp.push_dn_begin;
         if (special) {
             if (nc == MAX_SPECIAL) overflow = true;
             else mp.schunks[nc++] = k;
@@ -668,7 +675,7 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     mp.n_sstrips = ns; mp.n_schunks = nc;
     const int nsf = mp.nstrips - ns, ncf = mp.nchunks - nc;
     const int n_careful = ns * mp.nchunks + nsf * nc, n_fast = nsf * ncf;
-    mp.total_warps = (unsigned)(n_careful + n_fast);
+    mp.total_warps = (unsigned)n_careful;
     // The careful kernel is small (edges only) and would run alone at a fraction of a wave: fork it onto a side
     // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
     SideStream *side = (n_careful > 0 && n_fast > 0 && g_serial == 2) ? side_stream() : nullptr;
@@ -822,6 +829,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
             void *const *up = q->peer_up[cur ^ 1];
             void *const *dn = q->peer_dn[cur ^ 1];
             mp.push = on && rem == 0;
+            mp.halo_on = on; mp.own_lo = q->row_lo; mp.own_hi = q->row_hi;
             mp.wait_flags = on && done == 0;
             mp.signal = on && rem == 0;
             mp.push_up_end = q->row_lo + q->halo;
