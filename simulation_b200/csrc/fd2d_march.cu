@@ -59,6 +59,7 @@ struct MarchParams {
     int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
     int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
     double src[TMAX];
+    unsigned long long negzero2;               // two float -0.0 (0x8000000080000000), opaque to the compiler: see pk_mul
 };
 
 // ---- vector global access: V consecutive elements, naturally aligned
@@ -143,11 +144,13 @@ struct ColCoef {       // per-column PML coefficients and update masks, fixed fo
 
 // One pipeline stage at sub-step s: finish D,E of the arriving row A (global row rs) and H of the held row Hd
 // (global row rs-1), both in place.  FAST: interior warp -- no edge masks, no TFSF / source cells.
-template <typename real, int V, int MODE, bool FAST>
+template <typename real, int V, int MODE, bool FAST, bool NAZR = false>
 __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const ColCoef<real, V> &c, RowSet<real, V> &A,
                                             RowSet<real, V> &Hd, const int rs, const int s, const int jb,
-                                            const bool tf_cols, const bool src_cols) {
+                                            const bool tf_cols, const bool src_cols, const void *naz_smem = nullptr,
+                                            const void *naz_held_smem = nullptr) {
     constexpr bool LOSSY = (MODE & 1) != 0, DFT = (MODE & 2) != 0;
+    static_assert(!NAZR || (FAST && !LOSSY), "the naz ring serves the plain interior kernel only");
     constexpr unsigned FULL = 0xffffffffu;
     const real half = real(0.5);
     const int hr = rs - 1;
@@ -190,13 +193,29 @@ __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const Co
         }
     }
     // ---- E of row rs
+    real ezA[V], ezH[V];           // Ez of the arriving row (fresh) and of the held row (from the previous row trip)
+    if constexpr (NAZR) {
+        // deep pipelines: naz comes from its shared-memory ring and Ez is not kept in the row sets at all -- the
+        // held row's Ez is the same product naz*dz evaluated again (same operands, same bits)
+        real nzA[V], nzH[V];
+        lds_vec<real, V>(naz_smem, nzA);
+        lds_vec<real, V>(naz_held_smem, nzH);
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        if (LOSSY) {
-            A.ez[v] = A.naz[v] * (A.dz[v] - A.iz[v]);
-            A.iz[v] = A.iz[v] + A.nbz[v] * A.ez[v];
-        } else {
-            A.ez[v] = A.naz[v] * A.dz[v];
+        for (int v = 0; v < V; ++v) {
+            ezA[v] = nzA[v] * A.dz[v];
+            ezH[v] = nzH[v] * Hd.dz[v];
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (LOSSY) {
+                A.ez[v] = A.naz[v] * (A.dz[v] - A.iz[v]);
+                A.iz[v] = A.iz[v] + A.nbz[v] * A.ez[v];
+            } else {
+                A.ez[v] = A.naz[v] * A.dz[v];
+            }
+            ezA[v] = A.ez[v];
+            ezH[v] = Hd.ez[v];
         }
     }
     if (DFT) {       // fourier of sub-step s on the fresh Ez: float64 product and sum, rounded into the array type
@@ -212,12 +231,12 @@ __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const Co
             }
     }
     // ---- H of the held row hr (needs ez[hr][j+1] and ez[rs][j]), in place
-    const real ez_right = __shfl_down_sync(FULL, Hd.ez[0], 1);
+    const real ez_right = __shfl_down_sync(FULL, ezH[0], 1);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        const real er = (v == V - 1) ? ez_right : Hd.ez[v == V - 1 ? v : v + 1];
-        const real cm = Hd.ez[v] - er;
-        const real cn = Hd.ez[v] - A.ez[v];
+        const real er = (v == V - 1) ? ez_right : ezH[v == V - 1 ? v : v + 1];
+        const real cm = ezH[v] - er;
+        const real cn = ezH[v] - ezA[v];
         const real sx = Hd.ihx[v] + cm;
         const real sy = Hd.ihy[v] + cn;
         const real fy1 = FAST ? real(0) : c.fy1[v], fy2 = FAST ? real(1) : c.fy2[v], fy3 = FAST ? real(1) : c.fy3[v];
@@ -259,22 +278,104 @@ __device__ __forceinline__ void march_stage(const MarchParams<real> &p, const Co
     }
 }
 
+// ---- packed fp32 (sm_100 FADD2 / FFMA2: two IEEE operations per instruction, half the issue slots and code size).
+// Each half rounds exactly like the scalar instruction, so results stay bit-identical to the reference order.  One trap:
+// ptxas contracts a packed multiply with a following packed add into FFMA2 even with --fmad=false (observed with
+// CUDA 12.9: __fmul2_rn + __fadd2_rn -> one FFMA2), which would drop a rounding.  A product is therefore issued as
+// FFMA2(a, b, -0.0) with the -0.0 pair taken from a kernel parameter the compiler cannot see through:
+// a*b + (-0) rounds once, to exactly RN(a*b) (signed zeros included), and an FFMA2 cannot absorb the next add.
+__device__ __forceinline__ float2 pk_add(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pk_sub(const float2 a, const float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 pk_mul(const float2 a, const float2 b, const float2 negzero) { return __ffma2_rn(a, b, negzero); }
+
+// Interior stage in packed arithmetic (float, even V): same operations in the same order as march_stage<.., FAST>.
+template <int V, bool NAZR>
+__device__ __forceinline__ void march_stage_pk(RowSet<float, V> &A, RowSet<float, V> &Hd, const float2 negzero,
+                                               const void *naz_smem, const void *naz_held_smem) {
+    static_assert(V % 2 == 0, "packed stage needs column pairs");
+    constexpr unsigned FULL = 0xffffffffu;
+    const float2 half2 = make_float2(0.5f, 0.5f), zero2 = make_float2(0.f, 0.f);
+    // ---- D of the arriving row: dz = dz + 0.5*(((hy - hy[i-1]) - hx) + hx[j-1])
+    const float hx_left = __shfl_up_sync(FULL, A.hx[V - 1], 1);
+#pragma unroll
+    for (int v = 0; v < V; v += 2) {
+        const float2 a1 = pk_sub(make_float2(A.hy[v], A.hy[v + 1]), make_float2(Hd.hy[v], Hd.hy[v + 1]));
+        const float2 a2 = pk_sub(a1, make_float2(A.hx[v], A.hx[v + 1]));
+        const float2 curl = make_float2(a2.x + (v == 0 ? hx_left : A.hx[v == 0 ? 0 : v - 1]), a2.y + A.hx[v]);   // shifted pair: scalar
+        const float2 dn = pk_add(make_float2(A.dz[v], A.dz[v + 1]), pk_mul(half2, curl, negzero));
+        A.dz[v] = dn.x; A.dz[v + 1] = dn.y;
+    }
+    // ---- E of both rows
+    float ezA[V], ezH[V];
+    if constexpr (NAZR) {
+        float nzA[V], nzH[V];
+        lds_vec<float, V>(naz_smem, nzA);
+        lds_vec<float, V>(naz_held_smem, nzH);
+#pragma unroll
+        for (int v = 0; v < V; v += 2) {
+            const float2 a = pk_mul(make_float2(nzA[v], nzA[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
+            const float2 h = pk_mul(make_float2(nzH[v], nzH[v + 1]), make_float2(Hd.dz[v], Hd.dz[v + 1]), negzero);
+            ezA[v] = a.x; ezA[v + 1] = a.y; ezH[v] = h.x; ezH[v + 1] = h.y;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; v += 2) {
+            const float2 a = pk_mul(make_float2(A.naz[v], A.naz[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
+            A.ez[v] = a.x; A.ez[v + 1] = a.y;
+            ezA[v] = a.x; ezA[v + 1] = a.y; ezH[v] = Hd.ez[v]; ezH[v + 1] = Hd.ez[v + 1];
+        }
+    }
+    // ---- H of the held row: ihx += cm; ihy += cn; hx = hx + (0.5*cm + 0*ihx); hy = hy - (0.5*cn + 0*ihy)
+    const float ez_right = __shfl_down_sync(FULL, ezH[0], 1);
+#pragma unroll
+    for (int v = 0; v < V; v += 2) {
+        const float2 e = make_float2(ezH[v], ezH[v + 1]);
+        const float2 cm = make_float2(ezH[v] - ezH[v + 1], ezH[v + 1] - (v + 2 < V ? ezH[v + 2 < V ? v + 2 : v] : ez_right));   // shifted pair: scalar
+        const float2 cn = pk_sub(e, make_float2(ezA[v], ezA[v + 1]));
+        const float2 sx = pk_add(make_float2(Hd.ihx[v], Hd.ihx[v + 1]), cm);
+        const float2 sy = pk_add(make_float2(Hd.ihy[v], Hd.ihy[v + 1]), cn);
+        const float2 tx = pk_add(pk_mul(half2, cm, negzero), pk_mul(zero2, sx, negzero));
+        const float2 ty = pk_add(pk_mul(half2, cn, negzero), pk_mul(zero2, sy, negzero));
+        const float2 hx2 = pk_add(make_float2(Hd.hx[v], Hd.hx[v + 1]), tx);
+        const float2 hy2 = pk_sub(make_float2(Hd.hy[v], Hd.hy[v + 1]), ty);
+        Hd.ihx[v] = sx.x; Hd.ihx[v + 1] = sx.y; Hd.ihy[v] = sy.x; Hd.ihy[v + 1] = sy.y;
+        Hd.hx[v] = hx2.x; Hd.hx[v + 1] = hx2.y; Hd.hy[v] = hy2.x; Hd.hy[v + 1] = hy2.y;
+    }
+}
+
 // The march of one warp over its (strip, chunk).  Rows are staged through a per-lane ring of RING rows in
 // shared memory filled by cp.async (each lane reads back only the 16 B it copied itself: no barrier, no
 // register cost), keeping RING-1 rows x 6 arrays in flight per warp to cover the HBM latency.
 constexpr int RING = 4;
 
+// Compile-time shape of one instantiation: register row sets, ring slots, shared memory per warp.
+// NAZR (deep interior pipelines, T >= 7): a row set of 7 arrays x 4 columns x 9 sets does not fit the register
+// file, so naz -- read once per stage, never written -- stays in shared memory: its own ring of 2*(T+1) rows,
+// addressed with compile-time slots (the row loop is unrolled T+1 times; the two halves alternate per trip).
+template <typename real, int V, int T, int MODE, bool FAST>
+struct MarchShape {
+    static constexpr bool LOSSY = (MODE & 1) != 0, DFT = (MODE & 2) != 0;
+    static constexpr bool NAZR = FAST && !LOSSY && !DFT && T >= 7;
+    static constexpr bool PACKED = FAST && !LOSSY && !DFT && sizeof(real) == 4 && V % 2 == 0;   // FADD2 / FFMA2 stage
+    static constexpr int NS = T + 1;                                   // register row sets
+    static constexpr int NARR = (LOSSY ? 8 : 6) + (DFT ? 2 * NFMAX : 0) - (NAZR ? 1 : 0);   // arrays per main-ring row
+    static constexpr int LB = V * (int)sizeof(real);                   // bytes per lane per array row
+    static constexpr int ROWB = 32 * LB;                               // bytes per array row (per warp)
+    static constexpr int SLOT = NARR * ROWB;                           // main-ring bytes per row
+    static constexpr int NAZ_ROWS = NAZR ? 2 * NS : 0;
+    static constexpr int WARP_SMEM = RING * SLOT + NAZ_ROWS * ROWB;
+};
+
 template <typename real, int V, int T, int MODE, bool FAST>
 __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int strip, const int chunk, const int lane,
                                            unsigned char *const ring) {
-    constexpr bool LOSSY = (MODE & 1) != 0, DFT = (MODE & 2) != 0;
+    using Shape = MarchShape<real, V, T, MODE, FAST>;
+    constexpr bool LOSSY = Shape::LOSSY, DFT = Shape::DFT, NAZR = Shape::NAZR;
     constexpr int W = 32 * V;            // columns per strip
     constexpr int HALO = ((T + V - 1) / V) * V;   // recomputed columns per side: >= T, multiple of V (aligned vectors)
     constexpr int USE = W - 2 * HALO;    // columns a strip produces
-    constexpr int NS = T + 1;            // register row sets
-    constexpr int NARR = (LOSSY ? 8 : 6) + (DFT ? 2 * NFMAX : 0);  // arrays staged per row
-    constexpr int LB = V * (int)sizeof(real);
-    constexpr int SLOT = NARR * 32 * LB; // ring bytes per row (per warp)
+    constexpr int NS = Shape::NS;
+    constexpr int LB = Shape::LB, ROWB = Shape::ROWB, SLOT = Shape::SLOT;
 
     const int c0 = strip * USE - HALO;               // first column of the strip (halo included)
     const int jb = c0 + lane * V;                    // first column of this lane
@@ -320,6 +421,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         }
 
     unsigned char *const lane_ring = ring + lane * LB;
+    unsigned char *const lane_naz = ring + RING * SLOT + lane * LB;      // NAZR: this lane's column of the naz ring
     const int r_begin = i0 - T, r_end = i1 + T;      // rows fed to stage 0: [r_begin, r_end)
     // element offsets (row-major, local array rows) of the row fetched next / stored next; advanced by ny per row
     long long off_f = (long long)(r_begin - p.row_base) * p.ny + jb;
@@ -327,7 +429,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
     int g_f = r_begin;                                // global row fetched next
     // asynchronous copies of global row g_f into ring slot k (zero fill outside the stored rows / the grid;
     // FAST warps only ever touch stored interior rows, so their copies are unconditional)
-    auto fetch = [&](const int k) {
+    auto fetch = [&](const int k, const int naz_off) {
         const bool ok = FAST || ((g_f >= p.in_lo) && (g_f < p.in_hi) && (g_f < r_end) && col_in);
         const long long off = ok ? off_f : 0;
         const int nb = ok ? LB : 0;
@@ -337,7 +439,8 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         cp_async<LB>(dst + 2 * 32 * LB, p.in_hy + off, nb);
         cp_async<LB>(dst + 3 * 32 * LB, p.in_ihx + off, nb);
         cp_async<LB>(dst + 4 * 32 * LB, p.in_ihy + off, nb);
-        cp_async<LB>(dst + 5 * 32 * LB, p.naz + off, nb);
+        if (NAZR) cp_async<LB>(lane_naz + naz_off, p.naz + off, nb);
+        else cp_async<LB>(dst + 5 * 32 * LB, p.naz + off, nb);
         if (LOSSY) {
             cp_async<LB>(dst + 6 * 32 * LB, p.in_iz + off, nb);
             cp_async<LB>(dst + 7 * 32 * LB, p.nbz + off, nb);
@@ -365,7 +468,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         lds_vec<real, V>(src + 2 * 32 * LB, row.hy);
         lds_vec<real, V>(src + 3 * 32 * LB, row.ihx);
         lds_vec<real, V>(src + 4 * 32 * LB, row.ihy);
-        lds_vec<real, V>(src + 5 * 32 * LB, row.naz);
+        if (!NAZR) lds_vec<real, V>(src + 5 * 32 * LB, row.naz);
         if (LOSSY) {
             lds_vec<real, V>(src + 6 * 32 * LB, row.iz);
             lds_vec<real, V>(src + 7 * 32 * LB, row.nbz);
@@ -380,18 +483,44 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         }
     };
 
+    if (NAZR) {        // rows above the chunk (pipeline warm-up) read naz slots no copy has filled yet
 #pragma unroll
-    for (int k = 0; k < RING - 1; ++k) fetch(k);
+        for (int k = 0; k < Shape::NAZ_ROWS; ++k)
+#pragma unroll
+            for (int b = 0; b < LB; b += 4) *reinterpret_cast<float *>(lane_naz + k * ROWB + b) = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < RING - 1; ++k) fetch(k, k * ROWB);
     int slot = 0;                                     // ring slot of the row consumed next
 
-    auto store_row = [&](const RowSet<real, V> &O, const int ro) {
+    // packed kernels keep values in register PAIRS: storing a row as two 64-bit halves spares the moves that
+    // assembling aligned quads for 128-bit stores would cost (same sectors, same bytes)
+    auto st_vec = [&](real *dst, const real (&d)[V]) {
+        if constexpr (Shape::PACKED && V == 4) {
+            *reinterpret_cast<float2 *>(dst) = make_float2(d[0], d[1]);
+            *reinterpret_cast<float2 *>(dst + 2) = make_float2(d[2], d[3]);
+        } else {
+            VecIO<real, V>::st(dst, d);
+        }
+    };
+    auto store_row = [&](const RowSet<real, V> &O, const int ro, const int naz_off) {
         if (ro >= i0 && ro < i1 && col_store) {
-            VecIO<real, V>::st(p.out_dz + off_s, O.dz);
-            if (p.write_ez) VecIO<real, V>::st(p.out_ez + off_s, O.ez);
-            VecIO<real, V>::st(p.out_hx + off_s, O.hx);
-            VecIO<real, V>::st(p.out_hy + off_s, O.hy);
-            VecIO<real, V>::st(p.out_ihx + off_s, O.ihx);
-            VecIO<real, V>::st(p.out_ihy + off_s, O.ihy);
+            st_vec(p.out_dz + off_s, O.dz);
+            if (p.write_ez) {
+                if constexpr (NAZR) {     // Ez is not carried by the sets: the last pass evaluates naz*dz once more
+                    real nz[V], e[V];
+                    lds_vec<real, V>(lane_naz + naz_off, nz);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) e[v] = nz[v] * O.dz[v];
+                    st_vec(p.out_ez + off_s, e);
+                } else {
+                    st_vec(p.out_ez + off_s, O.ez);
+                }
+            }
+            st_vec(p.out_hx + off_s, O.hx);
+            st_vec(p.out_hy + off_s, O.hy);
+            st_vec(p.out_ihx + off_s, O.ihx);
+            st_vec(p.out_ihy + off_s, O.ihy);
             if (LOSSY) VecIO<real, V>::st(p.out_iz + off_s, O.iz);
             if (DFT) {
 #pragma unroll
@@ -425,20 +554,37 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
 
     if constexpr (FAST) {
         // interior: row loop unrolled NS times, the register sets rotate through the roles (no moves)
+        float2 negzero;
+        {
+            const unsigned long long z = p.negzero2;
+            negzero = make_float2(__uint_as_float((unsigned)z), __uint_as_float((unsigned)(z >> 32)));
+        }
+        int nz_here = 0, nz_other = NS * ROWB;        // NAZR: byte offsets of this trip's / the other half of the naz ring
+#pragma unroll 1                                      // the body is T*(T+1) stages already: a second copy only costs i-cache
         for (int r = r_begin; r < r_end; r += NS) {
 #pragma unroll
             for (int u = 0; u < NS; ++u) {
                 const int rr = r + u;                 // global row arriving at stage 0 (may overrun r_end)
                 cp_async_wait<RING - 2>();            // the oldest of the RING-1 pending rows has landed
                 take(slot, S[u]);
-                fetch(slot == 0 ? RING - 1 : slot - 1);   // refill the slot consumed one sub-iteration ago
+                // refill the slot consumed one sub-iteration ago with row rr + RING - 1
+                fetch(slot == 0 ? RING - 1 : slot - 1,
+                      (u + RING - 1 < NS) ? nz_here + (u + RING - 1) * ROWB : nz_other + (u + RING - 1 - NS) * ROWB);
                 slot = (slot + 1 == RING) ? 0 : slot + 1;
 #pragma unroll
-                for (int s = 0; s < T; ++s)
-                    march_stage<real, V, MODE, FAST>(p, c, S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], rr - s,
-                                                      s, jb, tf_cols, src_cols);
-                store_row(S[(u + 1) % NS], rr - T);   // the set held by the last stage: row rr-T at time t+T
+                for (int s = 0; s < T; ++s) {     // row rr-s: fetched this trip (u >= s) or by the previous one
+                    const void *nzA = lane_naz + ((u >= s) ? nz_here + (u - s) * ROWB : nz_other + (NS + u - s) * ROWB);
+                    const void *nzH = lane_naz + ((u >= s + 1) ? nz_here + (u - s - 1) * ROWB : nz_other + (NS + u - s - 1) * ROWB);
+                    if constexpr (Shape::PACKED)
+                        march_stage_pk<V, NAZR>(S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], negzero, nzA, nzH);
+                    else
+                        march_stage<real, V, MODE, FAST, NAZR>(p, c, S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], rr - s,
+                                                                s, jb, tf_cols, src_cols, nzA, nzH);
+                }
+                // the set held by the last stage: row rr-T at time t+T
+                store_row(S[(u + 1) % NS], rr - T, (u >= T) ? nz_here + (u - T) * ROWB : nz_other + (NS + u - T) * ROWB);
             }
+            const int t = nz_here; nz_here = nz_other; nz_other = t;
         }
     } else {
         // edges: compact code matters more than instruction count (this kernel is a fraction of a wave and
@@ -448,12 +594,12 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
         for (int rr = r_begin; rr < r_end; ++rr) {
             cp_async_wait<RING - 2>();
             take(slot, S[0]);
-            fetch(slot == 0 ? RING - 1 : slot - 1);
+            fetch(slot == 0 ? RING - 1 : slot - 1, 0);
             slot = (slot + 1 == RING) ? 0 : slot + 1;
 #pragma unroll
             for (int s = 0; s < T; ++s)
                 march_stage<real, V, MODE, FAST>(p, c, S[s], S[s + 1], rr - s, s, jb, tf_cols, src_cols);
-            store_row(S[T], rr - T);
+            store_row(S[T], rr - T, 0);
 #pragma unroll
             for (int k = T; k >= 1; --k) S[k] = S[k - 1];
         }
@@ -487,10 +633,9 @@ template <typename real, int V, int T, int MODE, bool FAST>
 __global__ void __launch_bounds__(MAX_WARPS * 32)
 k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
     extern __shared__ __align__(16) unsigned char ring_smem[];
-    constexpr int SLOT = (((MODE & 1) ? 8 : 6) + ((MODE & 2) ? 2 * NFMAX : 0)) * 32 * V * (int)sizeof(real);
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    unsigned char *const ring = ring_smem + (size_t)(threadIdx.x >> 5) * RING * SLOT;
+    unsigned char *const ring = ring_smem + (size_t)(threadIdx.x >> 5) * MarchShape<real, V, T, MODE, FAST>::WARP_SMEM;
     const int nsf = p.nstrips - p.n_sstrips, ncf = p.nchunks - p.n_schunks;   // ordinary strips / chunks
     int strip, chunk;
     if (FAST) {
@@ -621,12 +766,11 @@ SideStream *side_stream() {
 template <typename real, int V, int T, int MODE, bool FAST>
 int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStream_t st) {
     if (items <= 0) return FDTD_OK;
-    const int ring = RING;
-    const size_t slot = (size_t)(((MODE & 1) ? 8 : 6) + ((MODE & 2) ? 2 * NFMAX : 0)) * 32 * V * sizeof(real);
+    const size_t per_warp = MarchShape<real, V, T, MODE, FAST>::WARP_SMEM;
     // 8 independent warps per CTA on big grids; fewer when there are not enough warps to fill every SM
     int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : (items >= 32 * fdtd::sm_count() ? 8 : (items >= 8 * fdtd::sm_count() ? 4 : 2));
-    while (warps > 1 && (size_t)warps * ring * slot > 200 * 1024) --warps;
-    const size_t smem = (size_t)warps * ring * slot;
+    while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) --warps;
+    const size_t smem = (size_t)warps * per_warp;
     static size_t configured = 0;                       // per instantiation: largest dynamic smem opted in so far
     if (smem > 48 * 1024 && smem > configured) {
         FDTD_CUDA(cudaFuncSetAttribute(k_march<real, V, T, MODE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -710,15 +854,24 @@ int launch_march(MarchParams<real> &mp, bool lossy, cudaStream_t st) {
 
 template <typename real, int V>
 int launch_march_T(int T, MarchParams<real> &mp, bool lossy, cudaStream_t st) {
+#ifdef FDTD_DEV_ONLY        // development builds: one instantiation family (seconds instead of minutes of ptxas)
+    if constexpr (sizeof(real) == 4 && V == 4) {
+        if (T == 6) return launch_march<real, V, 6>(mp, lossy, st);
+        if (T == 8) return launch_march<real, V, 8>(mp, lossy, st);
+    }
+    fdtd::set_error("development build: float, V=4, T in {6, 8} only");
+    return FDTD_EUNSUPPORTED;
+#else
     switch (T) {
         case 1: return launch_march<real, V, 1>(mp, lossy, st);
         case 2: return launch_march<real, V, 2>(mp, lossy, st);
         case 3: return launch_march<real, V, 3>(mp, lossy, st);
         case 4: return launch_march<real, V, 4>(mp, lossy, st);
         case 6: return launch_march<real, V, 6>(mp, lossy, st);
-        case 8: if constexpr (V <= 2) return launch_march<real, V, 8>(mp, lossy, st);
+        case 8: return launch_march<real, V, 8>(mp, lossy, st);
         default: fdtd::set_error("unsupported time-block depth %d for vector width %d", T, V); return FDTD_EUNSUPPORTED;
     }
+#endif
 }
 
 // CUDA loads kernels lazily: the first launch of every instantiation pays a module load of several ms.
@@ -750,7 +903,7 @@ template <typename real, int V>
 void touch_V(bool lossy) {
     touch_T<real, V, 1>(lossy); touch_T<real, V, 2>(lossy); touch_T<real, V, 3>(lossy);
     touch_T<real, V, 4>(lossy); touch_T<real, V, 6>(lossy);
-    if constexpr (V <= 2) touch_T<real, V, 8>(lossy);
+    touch_T<real, V, 8>(lossy);
 }
 
 // vector width: widest V dividing ny (rows start V-aligned; the strip halo is rounded up to a multiple of V)
@@ -824,6 +977,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.ezi_hist = (const real *)q->ezi_hist; mp.hxi_hist = (const real *)q->hxi_hist;
         mp.src_i = tfsf ? -1 : q->src_i; mp.src_j = q->src_j; mp.src_hard = q->src_hard;
         for (int s = 0; s < TMAX; ++s) mp.src[s] = (src && s < T) ? src[done + s] : 0.0;
+        mp.negzero2 = 0x8000000080000000ull;
         {   // fused halo exchange: wait on the first pass of the call, push + announce on the last
             const bool on = q->halo > 0;
             void *const *up = q->peer_up[cur ^ 1];
@@ -862,7 +1016,6 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         if (q->nf > 0 && V == 4) V = 2;                 // fused-DFT kernels: vector width <= 2
         if (q->nf > 0 && sizeof(real) == 8) V = 1;      // ... and 1 in float64 (register row sets)
         if (q->ny % V != 0 || (sizeof(real) == 8 && V == 4)) V = 1;
-        if (T == 8 && V == 4) V = 2;                    // 9 register row sets of 4 columns do not fit
         if (T == 8 && sizeof(real) == 8) V = 1;         // ... nor do 9 sets of 2 doubles
         const int halo = ((T + V - 1) / V) * V;
         const int use = 32 * V - 2 * halo;
@@ -933,6 +1086,10 @@ int fdtd2d_check_identity(const fdtd2d_problem *q, long long *violations) {
 
 int fdtd2d_preload(int dtype, int ny, int lossy) {
     (void)ny;
+#ifdef FDTD_DEV_ONLY
+    (void)dtype; (void)lossy;
+    return FDTD_OK;
+#else
     if (lossy & 2) {           // bit 1: the fused-DFT kernels as well
         const bool l = (lossy & 1) != 0;
         if (dtype == FDTD_F32) {
@@ -957,6 +1114,7 @@ int fdtd2d_preload(int dtype, int ny, int lossy) {
     }
     FDTD_LAUNCH_CHECK("fdtd2d_preload");
     return FDTD_OK;
+#endif
 }
 
 int fdtd2d_max_tblock(int dtype, int ny) {
