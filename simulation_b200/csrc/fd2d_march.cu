@@ -20,6 +20,7 @@ namespace {
 constexpr int TMAX = 8;          // deepest pipeline instantiated
 constexpr int NFMAX = 3;         // frequencies of the fused running DFT (the reference uses 3 everywhere)
 constexpr int MAX_SPECIAL = 12;  // most edge / TFSF / source strips (or chunks) a split launch can list
+constexpr int MAX_PAIRS = 8;     // most single (strip, chunk) cells handed to the careful kernel (the point source)
 constexpr int MAX_WARPS = 8;     // warps per CTA are independent; a CTA only groups neighbouring strips for L1 locality
 
 template <typename real>
@@ -58,6 +59,8 @@ struct MarchParams {
     int write_ez;                              // 0: this pass leaves ez untouched (it is never read by a pass)
     int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
     int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
+    int n_spairs;                              // single (strip, chunk) cells of otherwise ordinary strips and chunks that the
+    int spairs[MAX_PAIRS][2];                  // careful kernel owns as well: the ones whose rows and columns see the point source
     double src[TMAX];
     unsigned long long negzero2;               // two float -0.0 (0x8000000080000000), opaque to the compiler: see pk_mul
 };
@@ -642,6 +645,8 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
         if (w >= nsf * ncf) return;
         strip = kth_not_in(w % nsf, p.sstrips, p.n_sstrips);
         chunk = kth_not_in(w / nsf, p.schunks, p.n_schunks);
+        for (int q = 0; q < p.n_spairs; ++q)
+            if (strip == p.spairs[q][0] && chunk == p.spairs[q][1]) return;     // the careful kernel has this one
     } else if (all_careful) {
         if (w >= p.nstrips * p.nchunks) return;
         strip = w % p.nstrips;
@@ -652,10 +657,15 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
             strip = p.sstrips[w % p.n_sstrips];
             chunk = w / p.n_sstrips;
         } else {
-            const int x = w - na;
-            if (x >= nsf * p.n_schunks) return;
-            strip = kth_not_in(x % nsf, p.sstrips, p.n_sstrips);
-            chunk = p.schunks[x / nsf];
+            const int x = w - na, nb = nsf * p.n_schunks;
+            if (x < nb) {
+                strip = kth_not_in(x % nsf, p.sstrips, p.n_sstrips);
+                chunk = p.schunks[x / nsf];
+            } else {
+                if (x - nb >= p.n_spairs) return;
+                strip = p.spairs[x - nb][0];
+                chunk = p.spairs[x - nb][1];
+            }
         }
     }
     // Fused halo exchange (multi-GPU).  Ghost rows are read, and edge rows pushed, by careful warps only (the host
@@ -793,7 +803,6 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
         const int c0 = k * USE - HALO, c1 = c0 + W;     // columns [c0, c1)
         bool special = (c0 < max(1, mp.ident_col_lo)) || (c1 > min(mp.ny - 1, mp.ident_col_hi));
         if (mp.tfsf) special = special || (ja - 1 >= c0 && ja - 1 < c1) || (ja >= c0 && ja < c1) || (jz >= c0 && jz < c1);
-        if (mp.src_i >= 0) special = special || (mp.src_j >= c0 && mp.src_j < c1);
         if (special) {
             if (ns == MAX_SPECIAL) overflow = true;
             else mp.sstrips[ns++] = k;
@@ -811,6 +820,24 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
             else mp.schunks[nc++] = k;
         }
     }
+    // The point source is ONE cell: only the (strip, chunk) cells whose columns and rows see it go to the careful kernel,
+    // not its whole strip and its whole chunk.
+    int np = 0;
+    if (mp.src_i >= 0 && !overflow) {
+        auto listed = [](const int *a, int n, int k) { for (int q = 0; q < n; ++q) if (a[q] == k) return true; return false; };
+        for (int k = 0; k < mp.nstrips && !overflow; ++k) {
+            const int c0 = k * USE - HALO, c1 = c0 + W;
+            if (!(mp.src_j >= c0 && mp.src_j < c1) || listed(mp.sstrips, ns, k)) continue;
+            for (int c = 0; c < mp.nchunks && !overflow; ++c) {
+                const int i0 = mp.out_lo + c * mp.chunk_rows, i1 = min(i0 + mp.chunk_rows, mp.out_hi);
+                const int lo = i0 - T - 1, hi = i1 + 2 * T + RING + 2;
+                if (!(mp.src_i >= lo && mp.src_i < hi) || listed(mp.schunks, nc, c)) continue;
+                if (np == MAX_PAIRS) overflow = true;
+                else { mp.spairs[np][0] = k; mp.spairs[np][1] = c; ++np; }
+            }
+        }
+    }
+    mp.n_spairs = overflow ? 0 : np;
     if (overflow) {                                      // tiny grids: everything through the careful kernel
         mp.n_sstrips = mp.n_schunks = 0;
         mp.total_warps = (unsigned)(mp.nstrips * mp.nchunks);
@@ -818,7 +845,7 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     }
     mp.n_sstrips = ns; mp.n_schunks = nc;
     const int nsf = mp.nstrips - ns, ncf = mp.nchunks - nc;
-    const int n_careful = ns * mp.nchunks + nsf * nc, n_fast = nsf * ncf;
+    const int n_careful = ns * mp.nchunks + nsf * nc + np, n_fast = nsf * ncf;      // (np of the n_fast warps exit at once)
     mp.total_warps = (unsigned)n_careful;
     // The careful kernel is small (edges only) and would run alone at a fraction of a wave: fork it onto a side
     // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
