@@ -35,6 +35,7 @@ struct MarchParams {
     int in_lo, in_hi;                          // global rows readable in the input set
     int out_lo, out_hi;                        // global rows this pass must produce
     int chunk_rows, nstrips, nchunks;
+    int cchunk_rows, ncchunks;                 // row partition of the SPECIAL strips (careful kernel): finer on small launches
     int tfsf, npml;
     const real *ezi_hist, *hxi_hist;           // [T][ny], [T][2]
     int src_i, src_j, src_hard;                // point source on dz (src_i < 0: none)
@@ -370,8 +371,8 @@ struct MarchShape {
 };
 
 template <typename real, int V, int T, int MODE, bool FAST>
-__device__ __forceinline__ void march_body(const MarchParams<real> &p, const int strip, const int chunk, const int lane,
-                                           unsigned char *const ring) {
+__device__ __forceinline__ void march_body(const MarchParams<real> &p, const int strip, const int i0, const int i1,
+                                           const int lane, unsigned char *const ring) {
     using Shape = MarchShape<real, V, T, MODE, FAST>;
     constexpr bool LOSSY = Shape::LOSSY, DFT = Shape::DFT, NAZR = Shape::NAZR;
     constexpr int W = 32 * V;            // columns per strip
@@ -384,8 +385,6 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
     const int jb = c0 + lane * V;                    // first column of this lane
     const bool col_in = FAST || ((jb >= 0) && (jb + V <= p.ny));
     const bool col_store = col_in && (lane * V >= HALO) && (lane * V + V <= W - HALO);
-    const int i0 = p.out_lo + chunk * p.chunk_rows;
-    const int i1 = min(i0 + p.chunk_rows, p.out_hi);
 
     ColCoef<real, V> c;
     c.dmask = c.hmask = 0;
@@ -640,7 +639,7 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned char *const ring = ring_smem + (size_t)(threadIdx.x >> 5) * MarchShape<real, V, T, MODE, FAST>::WARP_SMEM;
     const int nsf = p.nstrips - p.n_sstrips, ncf = p.nchunks - p.n_schunks;   // ordinary strips / chunks
-    int strip, chunk;
+    int strip, chunk, crows = p.chunk_rows;     // rows [out_lo + chunk*crows, ...) of the strip
     if (FAST) {
         if (w >= nsf * ncf) return;
         strip = kth_not_in(w % nsf, p.sstrips, p.n_sstrips);
@@ -652,10 +651,11 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
         strip = w % p.nstrips;
         chunk = w / p.nstrips;
     } else {
-        const int na = p.n_sstrips * p.nchunks;
+        const int na = p.n_sstrips * p.ncchunks;        // special strips: all rows, in their own (finer) row partition
         if (w < na) {
             strip = p.sstrips[w % p.n_sstrips];
             chunk = w / p.n_sstrips;
+            crows = p.cchunk_rows;
         } else {
             const int x = w - na, nb = nsf * p.n_schunks;
             if (x < nb) {
@@ -668,6 +668,7 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
             }
         }
     }
+    const int i0 = p.out_lo + chunk * crows, i1 = min(i0 + crows, p.out_hi);
     // Fused halo exchange (multi-GPU).  Ghost rows are read, and edge rows pushed, by careful warps only (the host
     // lists those chunks as special), so the handshake lives in the careful kernel; the interior kernel carries none.
     if (!FAST && p.wait_flags) {
@@ -680,7 +681,7 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
         }
         __syncwarp();
     }
-    march_body<real, V, T, MODE, FAST>(p, strip, chunk, lane, ring);
+    march_body<real, V, T, MODE, FAST>(p, strip, i0, i1, lane, ring);
     if (!FAST && p.signal) {
         // the last careful warp of the pass announces completion to the neighbours
         __threadfence_system();
@@ -756,21 +757,28 @@ int g_serial = 2;            // 2 = fork the edge kernel onto a side stream (mea
 
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
 
-// one high-priority side stream + fork/join events per device, created on first use
-SideStream *side_stream() {
-    static SideStream table[64];
-    static bool ready[64] = {false};
+// one high-priority side stream + fork/join events per (device, launch stream), created on first use: callers that
+// drive several launch streams at once (Fdtd2D.run_streamed) must not queue behind each other's edge kernels
+SideStream *side_stream(cudaStream_t launch) {
+    struct Entry { int dev; cudaStream_t launch; SideStream side; };
+    constexpr int CAP = 64;
+    static Entry table[CAP];
+    static int used = 0;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!ready[dev]) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&table[dev].stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&table[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&table[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        ready[dev] = true;
-    }
-    return &table[dev];
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (int k = 0; k < used; ++k)
+        if (table[k].dev == dev && table[k].launch == launch) return &table[k].side;
+    if (used == CAP) return nullptr;                    // callers fall back to the in-order launch
+    Entry &e = table[used];
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&e.side.stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&e.side.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&e.side.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    e.dev = dev;
+    e.launch = launch;
+    ++used;
+    return &e.side;
 }
 
 template <typename real, int V, int T, int MODE, bool FAST>
@@ -840,16 +848,25 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     mp.n_spairs = overflow ? 0 : np;
     if (overflow) {                                      // tiny grids: everything through the careful kernel
         mp.n_sstrips = mp.n_schunks = 0;
+        mp.cchunk_rows = mp.chunk_rows; mp.ncchunks = mp.nchunks;
         mp.total_warps = (unsigned)(mp.nstrips * mp.nchunks);
         return launch_one<real, V, T, MODE, false>(mp, mp.nstrips * mp.nchunks, 1, st);
     }
     mp.n_sstrips = ns; mp.n_schunks = nc;
     const int nsf = mp.nstrips - ns, ncf = mp.nchunks - nc;
-    const int n_careful = ns * mp.nchunks + nsf * nc + np, n_fast = nsf * ncf;      // (np of the n_fast warps exit at once)
+    const int n_fast = nsf * ncf;                        // (np of them exit at once)
+    // A careful warp is ~3x slower per row than an interior warp, and a launch cannot end before its slowest warp.
+    // On big launches (tens of interior waves) that is hidden; on small ones (row blocks of a streamed run, small
+    // grids) the special strips get a finer row partition so that their warps finish with the interior's.
+    const int rows = mp.out_hi - mp.out_lo;
+    const bool small_launch = n_fast < 16 * MAX_WARPS * fdtd::sm_count();
+    mp.cchunk_rows = small_launch ? max(1, min(mp.chunk_rows, max(4 * T, 32))) : mp.chunk_rows;
+    mp.ncchunks = (rows + mp.cchunk_rows - 1) / mp.cchunk_rows;
+    const int n_careful = ns * mp.ncchunks + nsf * nc + np;
     mp.total_warps = (unsigned)n_careful;
     // The careful kernel is small (edges only) and would run alone at a fraction of a wave: fork it onto a side
     // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
-    SideStream *side = (n_careful > 0 && n_fast > 0 && g_serial == 2) ? side_stream() : nullptr;
+    SideStream *side = (n_careful > 0 && n_fast > 0 && g_serial == 2) ? side_stream(st) : nullptr;
     if (side == nullptr) {
         int rc = launch_one<real, V, T, MODE, false>(mp, n_careful, 0, st);
         if (rc != FDTD_OK) return rc;
@@ -946,11 +963,10 @@ struct Plan { int V, T, chunk; };
 template <typename real>
 Plan choose_plan(long cells, int ny, bool lossy) {
     Plan p;
-    if (sizeof(real) == 4) {
-        if (cells < 1500000L)        p = {1, 4, 16};
-        else if (cells < 6000000L)   p = {2, 4, 16};
+    if (sizeof(real) == 4) {                            // profiles/r1_v18_sweep_grid_sizes.txt
+        if (cells < 6000000L)        p = {2, 4, 16};
         else if (cells < 24000000L)  p = {2, 6, 64};
-        else if (cells < 100000000L) p = {2, 6, 128};
+        else if (cells < 100000000L) p = {lossy ? 2 : 4, 6, 64};
         else                         p = {lossy ? 2 : 4, 6, 128};   // 7 row sets x 4 columns x 9 lossy fields spill
     } else {
         if (cells < 1500000L)        p = {1, 4, 16};           // profiles/r1_sweep_fp64.txt

@@ -135,6 +135,30 @@ class Fdtd1D:
     def set(self, name: str, host) -> None:
         self.tensor(name).copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(host, dtype=self.np_dtype))))
 
+    def checkpoint(self) -> dict:
+        """State arrays, ABC delay line, running-DFT accumulators and step counter as host arrays (see Fdtd2D.checkpoint)."""
+        out = {n: self.get(n) for n in self._sets[self._cur]}
+        out["bc"] = self.get("bc")
+        if self.ft is not None:
+            out.update({n: self.get(n) for n in ("r_pt", "i_pt", "r_in", "i_in")})
+        out["t"] = np.int64(self.t)
+        return out
+
+    def restore(self, ckpt: dict) -> None:
+        need = list(self._sets[self._cur]) + ["bc"] + (["r_pt", "i_pt", "r_in", "i_in"] if self.ft is not None else [])
+        missing = [n for n in need if n not in ckpt]
+        if missing:
+            raise _lib.FdtdError(f"restore: checkpoint lacks {missing}")
+        for n in list(self._sets[self._cur]) + ["bc"]:
+            a = np.asarray(ckpt[n])
+            if a.shape != tuple(self.tensor(n).shape) or a.dtype != self.np_dtype:
+                raise _lib.FdtdError(f"restore: {n} has shape {a.shape} / {a.dtype}")
+            self.set(n, a)
+        if self.ft is not None:
+            for n in ("r_pt", "i_pt", "r_in", "i_in"):
+                getattr(self.ft, n).copy_(torch.from_numpy(np.ascontiguousarray(ckpt[n], dtype=self.np_dtype)).reshape(getattr(self.ft, n).shape))
+        self.t = int(ckpt["t"])
+
     def _problem(self) -> _lib.Problem1D:
         p = _lib.Problem1D()
         p.dtype, p.nx = _lib.dtype_code(self.np_dtype), self.nx

@@ -442,36 +442,50 @@ class Fdtd2D:
             left -= d
         return out
 
-    def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, blocks: int = 24,
-                     tblock=None) -> None:
+    def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, blocks: Optional[int] = None,
+                     tblock=None, streams: int = 16, trace: Optional[list] = None, block_rows: Optional[int] = None) -> None:
         """The whole job a reference ``main()`` does -- medium from the host, ``nsteps`` steps from zero fields,
         Ez back on the host -- with the PCIe transfers hidden behind the kernels.
 
-        The grid is cut into ``blocks`` row blocks (24 measured best at 32768 rows: enough skew between the first and
-        the last block to cover both transfers) and the passes are issued as a wavefront: while block b of the
-        medium is still uploading, pass 1 runs on block b-1, pass 2 on block b-2, ... (pass p on a block needs pass
-        p-1 on that block and its two neighbours, which the single compute stream guarantees in wave order); the
-        last pass of each block is followed by the download of that block's Ez.  Same kernels, same arithmetic,
-        same result as ``set naz; advance(nsteps); get ez``.  ``naz_host`` / ``ez_host``: pinned CPU tensors of
-        shape (nx, ny).  Point source or no source only (the TFSF incident line is advanced once per whole-grid
-        pass); single device."""
+        The grid is cut into row blocks (``block_rows`` rows each, default 1024 on big grids: a whole number of
+        interior waves per launch, and enough skew between the first and the last block to cover both transfers; or
+        ``blocks`` equal blocks) and the passes are issued as a wavefront: while block b of the medium is still
+        uploading, pass 1 runs on block b-1, pass 2 on block b-2, ...  Pass p on block b needs pass p-1 on blocks
+        b-1, b, b+1 (it reads their rows and overwrites the set they read).  Each pass level runs its blocks in order
+        on its own stream (``p % streams``) and waits for the event of (b+1, p-1), which -- same stream, later block --
+        implies the other two: the pass levels form a systolic pipeline whose launches overlap, so the ramp and tail
+        of every small launch (0.1 ms of a 0.35 ms launch when one stream drains between them) is filled by its
+        neighbours (measured at 32768^2 x 96 steps: 195 -> 176 ms).  The last pass of each block is
+        followed by the download of that block's Ez.  Same kernels, same arithmetic, same result as
+        ``set naz; advance(nsteps); get ez``.  ``naz_host`` / ``ez_host``: pinned CPU tensors of shape (nx, ny).
+        Point source or no source only (the TFSF incident line is advanced once per whole-grid pass); single device."""
         if self.tfsf or self.ft is not None or self.rows_alloc != self.nx:
             raise _lib.FdtdError("run_streamed: single-device grids with a point source (or none) and no running DFT")
         if tuple(naz_host.shape) != (self.nx, self.ny) or tuple(ez_host.shape) != (self.nx, self.ny):
             raise _lib.FdtdError("run_streamed: host tensors must have shape (nx, ny)")
         depths = self._depths(nsteps, tblock)
-        P, B = len(depths), max(1, min(int(blocks), self.nx // max(4 * max(depths), 1)))
-        edges = [self.nx * k // B for k in range(B + 1)]
+        P = len(depths)
+        S = max(1, min(int(streams), P))
+        if blocks is None and block_rows is None:
+            block_rows = 1024 if self.nx >= 8192 else max(4 * max(depths), -(-self.nx // 8))
+        if block_rows:                                   # explicit block height (the last block takes the remainder)
+            edges = list(range(0, self.nx, max(int(block_rows), 4 * max(depths)))) + [self.nx]
+        else:
+            B = max(1, min(int(blocks), self.nx // max(4 * max(depths), 1)))
+            edges = [self.nx * k // B for k in range(B + 1)]
+        B = len(edges) - 1
         src = None
         if self.source is not None:
             src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)
         first_step = np.concatenate(([0], np.cumsum(depths)))          # step offset of every pass
         D = C.POINTER(C.c_double)
         with torch.cuda.device(self.device):
-            compute = torch.cuda.current_stream()
-            up, down = torch.cuda.Stream(), torch.cuda.Stream()
-            up.wait_stream(compute)
-            down.wait_stream(compute)
+            caller = torch.cuda.current_stream()
+            if getattr(self, "_lanes", None) is None or len(self._lanes) < S + 2:
+                self._lanes = [torch.cuda.Stream() for _ in range(S + 2)]
+            lanes, up, down = self._lanes[:S], self._lanes[S], self._lanes[S + 1]
+            for st in lanes + [up, down]:
+                st.wait_stream(caller)
             uploaded = []
             with torch.cuda.stream(up):
                 for b in range(B):
@@ -480,34 +494,124 @@ class Fdtd2D:
                     ev.record(up)
                     uploaded.append(ev)
             cur0 = self._cur
+            done = {}                                                      # (b, p) -> event
             for w in range(B + P - 1):
-                for p_idx in range(P):                                     # increasing p inside a wave (see docstring)
+                for p_idx in range(P):                                     # issue order: by wave, increasing p inside
                     b = w - p_idx
                     if not (0 <= b < B):
                         continue
+                    lane = lanes[p_idx % S]
                     if p_idx == 0:
-                        compute.wait_event(uploaded[min(b + 1, B - 1)])    # the pass reads naz up to depth rows below
+                        lane.wait_event(uploaded[min(b + 1, B - 1)])       # the pass reads naz up to depth rows below
+                    else:
+                        lane.wait_event(done[(min(b + 1, B - 1), p_idx - 1)])
                     prob = self._problem()
                     prob.row_lo, prob.row_hi = edges[b], edges[b + 1]
                     if p_idx < P - 1:
                         prob.flags |= _lib.LAZY_EZ
                     out = C.c_int(-1)
                     k0 = int(first_step[p_idx])
+                    if trace is not None:                                  # timeline probe (tools/probe_streamed.py)
+                        t0 = torch.cuda.Event(enable_timing=True)
+                        t0.record(lane)
                     check(lib().fdtd2d_advance(C.byref(prob), (cur0 + p_idx) % 2, depths[p_idx],
                                                None if src is None else src[k0:].ctypes.data_as(D),
-                                               depths[p_idx], C.c_void_p(compute.cuda_stream), C.byref(out)),
+                                               depths[p_idx], C.c_void_p(lane.cuda_stream), C.byref(out)),
                           "fdtd2d_advance (streamed)")
+                    ev = torch.cuda.Event(enable_timing=trace is not None)
+                    ev.record(lane)
+                    done[(b, p_idx)] = ev
+                    if trace is not None:
+                        trace.append((b, p_idx, t0, ev))
                     if p_idx == P - 1:
-                        done = torch.cuda.Event()
-                        done.record(compute)
-                        down.wait_event(done)
+                        down.wait_event(ev)
                         with torch.cuda.stream(down):
                             ez_dev = self._sets[(cur0 + P) % 2]["ez"]
                             ez_host[edges[b]:edges[b + 1]].copy_(ez_dev[edges[b]:edges[b + 1]], non_blocking=True)
-            compute.wait_stream(down)
-            compute.wait_stream(up)
+            for st in lanes + [up, down]:
+                caller.wait_stream(st)
         self._cur = (cur0 + P) % 2
         self.t += int(nsteps)
+
+    # ---- checkpoint / restore, snapshots --------------------------------------------------
+    def checkpoint(self) -> dict:
+        """Everything ``advance`` carries from step to step, as host arrays: the state arrays (owned rows), the
+        incident line, the running-DFT accumulators and the step counter.  The reference keeps this state in
+        local arrays of ``main()`` and has no checkpointing; ``restore`` on a problem built with the
+        same setup continues bit-identically."""
+        names = FIELD_NAMES if self.lossy else FIELD_NAMES[:-1]
+        out = {n: self.get(n) for n in names}
+        if self.tfsf:
+            out.update({n: self.get(n) for n in ("ezi", "hxi", "bc")})
+        if self.ft is not None:
+            out.update({n: self.get(n) for n in ("r_pt", "i_pt", "r_in", "i_in")})
+        out["t"] = np.int64(self.t)
+        return out
+
+    def restore(self, ckpt: dict) -> None:
+        """Inverse of :meth:`checkpoint` (same grid, rows, dtype and features)."""
+        names = FIELD_NAMES if self.lossy else FIELD_NAMES[:-1]
+        need = list(names) + (["ezi", "hxi", "bc"] if self.tfsf else []) + \
+            (["r_pt", "i_pt", "r_in", "i_in"] if self.ft is not None else [])
+        missing = [n for n in need if n not in ckpt]
+        if missing:
+            raise _lib.FdtdError(f"restore: checkpoint lacks {missing}")
+        rows = self.row_hi - self.row_lo
+        for n in names:
+            a = np.asarray(ckpt[n])
+            if a.shape != (rows, self.ny) or a.dtype != self.np_dtype:
+                raise _lib.FdtdError(f"restore: {n} has shape {a.shape} / {a.dtype}, expected {(rows, self.ny)} / {self.np_dtype}")
+            self.set(n, a)
+        if self.tfsf:
+            for n in ("ezi", "hxi", "bc"):
+                self.set(n, ckpt[n])
+        if self.ft is not None:
+            o = self.row_lo - self.row_base
+            for n in ("r_pt", "i_pt"):
+                getattr(self.ft, n)[:, o:o + rows].copy_(torch.from_numpy(np.ascontiguousarray(ckpt[n], dtype=self.np_dtype)))
+            for n in ("r_in", "i_in"):
+                getattr(self.ft, n).copy_(torch.from_numpy(np.ascontiguousarray(ckpt[n], dtype=self.np_dtype)))
+        self.t = int(ckpt["t"])
+
+    def advance_with_snapshots(self, nsteps: int, every: int, out_host: Optional[torch.Tensor] = None,
+                               tblock: Optional[int] = None) -> torch.Tensor:
+        """``nsteps`` steps, keeping Ez (owned rows) after every ``every``-th step in pinned host memory -- what the
+        reference's animation scripts do with ``ez.copy()`` per frame (fd2d/animation/fd2d_3_3.py:156-166) -- with the
+        device-to-host copies overlapped with the following steps: each frame is first copied on the device into one
+        of two staging buffers (stream-ordered, so the passes never race with it) and leaves over PCIe on a second
+        stream while the next ``every`` steps run.  Returns the ``(nsteps // every, rows, ny)`` pinned tensor; call
+        :meth:`synchronize` (or sync the current stream) before reading it.  Steps beyond the last frame are taken too."""
+        every, nsteps = int(every), int(nsteps)
+        if every <= 0:
+            raise _lib.FdtdError("advance_with_snapshots: every must be positive")
+        rows, frames = self.row_hi - self.row_lo, nsteps // every
+        if out_host is None:
+            out_host = torch.empty((frames, rows, self.ny), dtype=self.dtype).pin_memory()
+        if tuple(out_host.shape) != (frames, rows, self.ny) or out_host.dtype != self.dtype or not out_host.is_pinned():
+            raise _lib.FdtdError("advance_with_snapshots: out_host must be a pinned (nsteps // every, rows, ny) tensor of the field dtype")
+        with torch.cuda.device(self.device):
+            compute = torch.cuda.current_stream()
+            if getattr(self, "_snap", None) is None:
+                self._snap = {"stream": torch.cuda.Stream(),
+                              "stage": [torch.empty((rows, self.ny), dtype=self.dtype, device=self.device) for _ in range(2)],
+                              "free": [None, None]}
+            snap = self._snap
+            for k in range(frames):
+                self.advance(every, tblock=tblock)
+                b = k & 1
+                if snap["free"][b] is not None:
+                    compute.wait_event(snap["free"][b])          # frame k-2 has left this staging buffer
+                snap["stage"][b].copy_(self.tensor("ez"), non_blocking=True)
+                staged = torch.cuda.Event()
+                staged.record(compute)
+                snap["stream"].wait_event(staged)
+                with torch.cuda.stream(snap["stream"]):
+                    out_host[k].copy_(snap["stage"][b], non_blocking=True)
+                    snap["free"][b] = torch.cuda.Event()
+                    snap["free"][b].record(snap["stream"])
+            self.advance(nsteps - frames * every, tblock=tblock)
+            compute.wait_stream(snap["stream"])                  # the frames are complete once the caller's stream is
+        return out_host
 
     # ---- the unfused path: the reference loop body, one kernel per reference function ----------------
     def step(self) -> None:

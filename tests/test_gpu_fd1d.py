@@ -150,3 +150,15 @@ def test_dft_amplitude_goldens(prog):
         sim.advance(ns)
         amp, _ = orc.dft_amplitude_phase(sim.get("r_pt"), sim.get("i_pt"), sim.get("r_in"), sim.get("i_in"))
         assert amp[2].tobytes() == g["amplt2"].tobytes(), tag
+
+
+@pytest.mark.parametrize("prog", ["1_2", "1_5", "2_3"])
+def test_checkpoint_restore_continues_bit_identically(prog):
+    nx, a_steps, b_steps = 300, 130, 170
+    one = _sim_for(prog, nx, np.float32)
+    one.advance(a_steps)
+    two = _sim_for(prog, nx, np.float32)
+    two.restore(one.checkpoint())
+    assert two.t == a_steps
+    two.advance(b_steps)
+    _assert_same(two, _oracle(prog, nx, a_steps + b_steps, np.float32))

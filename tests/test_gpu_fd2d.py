@@ -370,9 +370,10 @@ def test_device_dielectric_equals_host_setup(dtype):
     assert sim.naz.shape == (100, 100)
 
 
-def test_streamed_run_equals_plain_run():
-    """run_streamed (block wavefront, transfers overlapped) == set naz; advance; get ez -- bit for bit, and the
-    whole state with it."""
+@pytest.mark.parametrize("blocks,streams", [(5, 1), (5, 4), (9, 3), (2, 2)])
+def test_streamed_run_equals_plain_run(blocks, streams):
+    """run_streamed (block wavefront over several streams, transfers overlapped) == set naz; advance; get ez -- bit
+    for bit, and the whole state with it."""
     from simulation_b200 import fd2d, surface
     rng = np.random.default_rng(5)
     nx, ny, npml, ns = 1500, 1152, 16, 52
@@ -383,7 +384,7 @@ def test_streamed_run_equals_plain_run():
     b = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src)
     host_naz = torch.from_numpy(naz).pin_memory()
     host_ez = torch.empty((nx, ny), dtype=torch.float32).pin_memory()
-    b.run_streamed(ns, host_naz, host_ez, blocks=5)
+    b.run_streamed(ns, host_naz, host_ez, blocks=blocks, streams=streams)
     b.synchronize()
     assert torch.equal(host_ez, a.tensor("ez").cpu())
     for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
@@ -402,3 +403,56 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(_lib.FdtdError):
         fd2d.hfield(64, 64, sim.pml, sim.tensor("ez").cpu(), sim.tensor("ihx"), sim.tensor("ihy"),
                     sim.tensor("hx"), sim.tensor("hy"))           # host tensor: no CPU path
+
+
+# ------------------------------------------------------------------ checkpoint / restore, snapshots
+@pytest.mark.parametrize("prog", ["3_2", "3_3", "3_4"])
+def test_checkpoint_restore_continues_bit_identically(prog):
+    nx, ny, npml, a_steps, b_steps = 90, 132, 8, 37, 41
+    one = _sim_for(prog, nx, ny, np.float32, npml=npml)
+    one.advance(a_steps)
+    ck = one.checkpoint()
+    one.advance(b_steps)
+    two = _sim_for(prog, nx, ny, np.float32, npml=npml)
+    two.restore(ck)
+    assert two.t == a_steps
+    two.advance(b_steps)
+    g, src = cases.grid_program(prog, nx, ny, a_steps + b_steps, np.float32, npml=npml, dft=False)
+    orc.advance_2d(g, src)
+    _assert_same(one, g, prog)
+    _assert_same(two, g, prog)
+    with pytest.raises(Exception):
+        two.restore({"t": 0})                                           # incomplete checkpoint
+
+
+def test_checkpoint_restore_with_running_dft():
+    from simulation_b200 import fd2d, surface
+    nx, ny, npml, a_steps, b_steps = 60, 72, 8, 33, 30
+    g, src = cases.grid_program("3_4", nx, ny, a_steps + b_steps, np.float32, npml=npml, radius=0.12, dft=True)
+    mk = lambda: fd2d.Fdtd2D(nx, ny, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)),
+                             naz=g.naz.copy(), nbz=g.nbz.copy(), freqs=g.freqs)
+    one = mk()
+    one.advance(a_steps)
+    two = mk()
+    two.restore(one.checkpoint())
+    two.advance(b_steps)
+    orc.advance_2d(g, src)
+    for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy", "r_pt", "i_pt", "r_in", "i_in"):
+        assert two.get(name).tobytes() == getattr(g, name).tobytes(), name
+
+
+@pytest.mark.parametrize("prog,every,tblock", [("3_3", 10, None), ("3_2", 7, 6), ("3_2", 12, 6), ("3_4", 1, None)])
+def test_snapshots_match_oracle_frames(prog, every, tblock):
+    """Frames staged on the device and streamed to pinned host memory behind the following steps == the oracle's Ez
+    after the same steps (the reference animation keeps ez.copy() per frame, fd2d/animation/fd2d_3_3.py:156-166)."""
+    nx, ny, npml, ns = 70, 96, 8, 45
+    sim = _sim_for(prog, nx, ny, np.float32, npml=npml)
+    frames = sim.advance_with_snapshots(ns, every, tblock=tblock)
+    sim.synchronize()
+    assert tuple(frames.shape) == (ns // every, nx, ny) and sim.t == ns
+    g, src = cases.grid_program(prog, nx, ny, ns, np.float32, npml=npml, dft=False)
+    for k, t in enumerate(orc.step_indices(ns)):
+        orc.step_2d(g, t, src[k])
+        if (k + 1) % every == 0:
+            assert frames[(k + 1) // every - 1].numpy().tobytes() == g.ez.tobytes(), f"frame after step {k + 1}"
+    _assert_same(sim, g, prog)
