@@ -114,7 +114,10 @@ typedef struct {
     int src_index, src_hard;           /* src_index < 0: no source */
 } fdtd1d_problem;
 /* advance nsteps steps starting from state set `cur`; src[k] is the float64 waveform sample of the k-th of
- * these steps (HOST pointer, may be NULL without a source).  *cur_out = set holding the result. */
+ * these steps (HOST pointer, may be NULL without a source).  *cur_out = set holding the result.
+ * tblock (1..64): most steps per kernel pass; passes deeper than the kernel's register budget allows (32 steps in
+ * float32, 16 in float64) are split.  All arrays 16-byte aligned.  Replaces the time loop of
+ * fd1d/program/fd1d_1_5.py:63-72 / fd1d_2_3.py:132-142 (CUDA: fd1d/cuda/test_1_5.cu main loop). */
 int fdtd1d_advance(const fdtd1d_problem *p, int cur, int nsteps, const double *src, int tblock,
                    void *stream, int *cur_out);
 

@@ -2,9 +2,9 @@
 // advance.  Update rules, ranges and evaluation order follow the reference numpy programs
 // (fd1d/program/fd1d_1_5.py:63-72 FDTD form, fd1d_2_3.py:73-94 flux/Debye form); no FMA contraction.
 //
-// Fused path: every CTA owns SEG cells, loads them plus T halo cells per side into shared memory (Ex, Hy)
-// and registers (pointwise state and coefficients), runs T leap-frog steps on chip and writes its SEG cells
-// to the other (ping-pong) array set -- 2*T-cell recompute per CTA instead of a grid-wide barrier per step.
+// Fused path: every WARP owns a segment, keeps it plus T halo cells per side in registers (consecutive cells per
+// lane, neighbours by warp shuffle), runs T leap-frog steps on chip and writes its segment to the other
+// (ping-pong) array set -- 2*T-cell recompute per warp instead of a grid-wide barrier per step.
 #include "common.cuh"
 
 namespace {
@@ -69,9 +69,20 @@ __global__ void k1_hy(int nx, const real *ex, real *hy) {
 }
 
 // --------------------------------------------------------------------------------- fused advance
-constexpr int NT = 256;       // threads per CTA
-constexpr int KC = 8;         // cells per thread  -> NT*KC cells staged per CTA
-constexpr int T1MAX = 64;     // deepest time block
+// One WARP owns a segment of the line and marches it T steps forward entirely in registers: every lane keeps KC
+// CONSECUTIVE cells (Ex, Hy, the pointwise state and the coefficients), so a cell's neighbours are registers of
+// the same lane except at the lane's two ends, which take one warp shuffle per half step (hy[i-1] from the lane
+// below, ex[i+1] from the lane above).  No shared memory, no barrier; warps are independent and recompute T halo
+// cells per side (the 1D twin of the 2D march kernel).  A pass = one launch = T steps = one trip of the state
+// through memory; the ping-pong array sets make the warps order-free.
+constexpr int T1MAX = 64;     // most steps per call of the time-block argument (deeper requests are split)
+
+template <typename real> struct LineShape {
+    static constexpr int KC = sizeof(real) == 4 ? 16 : 8;     // cells per lane (registers: 9 arrays x KC x words)
+    static constexpr int VEC = 16 / (int)sizeof(real);        // cells per 16-byte vector access
+    static constexpr int W = 32 * KC;                         // cells staged per warp
+    static constexpr int TMAX = 2 * KC;                       // deepest pass: halo <= W/8 per side
+};
 
 template <typename real>
 struct LineParams {
@@ -80,78 +91,99 @@ struct LineParams {
     const real *bc_in;
     real *bc_out;
     const real *ca, *cb, *nax, *nbx, *ncx, *ndx;
-    int nx, T, seg;           // seg = cells produced per CTA = NT*KC - 2*T
+    int nx, T, halo, useful;  // halo = T rounded up to whole vectors; useful = W - 2*halo cells produced per warp
+    int nwarps;
     int abc, src_field, src_index, src_hard;
     double src[T1MAX];        // waveform samples of this pass (by value: no staging buffer to manage)
 };
 
-// The T leap-frog steps of one CTA.  Every thread keeps the Ex / Hy of its own KC cells (slot c = k*NT + tid) in
-// registers next to the pointwise state; shared memory only carries values to the neighbouring cell
-// (hy[c-1] for the E half step, ex[c+1] for the H half step): 2 LDS + 2 STS per cell-step.  Both shared arrays are
-// shifted by one slot so that c-1 / c+1 of the first / last staged cell stay in bounds (halo garbage, never used).
+template <typename real, int KC>
+__device__ __forceinline__ void ld_cells(const real *base, long long g0, bool vec_ok, int nx, real (&d)[KC], real fill) {
+    constexpr int VEC = LineShape<real>::VEC;
+    if (vec_ok) {
+#pragma unroll
+        for (int v = 0; v < KC / VEC; ++v) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(base + g0 + v * VEC));
+            const real *q = reinterpret_cast<const real *>(&t);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) d[v * VEC + e] = q[e];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const long long g = g0 + k;
+            d[k] = (g >= 0 && g < nx) ? __ldg(base + g) : fill;
+        }
+    }
+}
+
 // EDGE: the staged range touches an end of the line (cells outside the line, the never-updated ex[0], ex[nx-1],
-// hy[nx-1], the ABC); interior CTAs run without any mask.
+// hy[nx-1], the ABC) or is not vector-aligned; interior warps run without any mask.
 template <typename real, bool FLUX, bool DEBYE, bool EDGE>
-__device__ __forceinline__ void line_body(const LineParams<real> &p, real *s_ex, real *s_hy, real *s_bc) {
-    const int tid = threadIdx.x;
-    const int seg_lo = blockIdx.x * p.seg;
-    const int seg_hi = min(seg_lo + p.seg, p.nx);
-    const int base = seg_lo - p.T;                 // global cell of staged slot 0 (may be negative)
+__device__ __forceinline__ void line_body(const LineParams<real> &p, const int w, const int lane) {
+    constexpr int KC = LineShape<real>::KC, VEC = LineShape<real>::VEC, W = LineShape<real>::W;
+    constexpr unsigned FULL = 0xffffffffu;
     const real half = real(0.5);
+    const int seg_lo = w * p.useful, seg_hi = min(seg_lo + p.useful, p.nx);
+    const int base = seg_lo - p.halo;              // global cell of the warp's first staged cell (may be negative)
+    const int g0 = base + lane * KC;               // first cell of this lane
+    const bool vec_ok = !EDGE;                     // interior warps: every staged cell exists and rows are 16-byte aligned
 
     real ex[KC], hy[KC], dx[KC], ix[KC], sx[KC], c0[KC], c1[KC], c2[KC], c3[KC];
-    int src_k = -1;                                // which of this thread's cells carries the source (-1: none)
 #pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        const int c = k * NT + tid, g = base + c;
-        const bool in = !EDGE || ((g >= 0) && (g < p.nx));
-        ex[k] = in ? p.in[0][g] : real(0);
-        hy[k] = in ? p.in[1][g] : real(0);
-        dx[k] = ix[k] = sx[k] = c2[k] = c3[k] = real(0);
-        if (FLUX) {
-            dx[k] = in ? p.in[2][g] : real(0);
-            ix[k] = in ? p.in[3][g] : real(0);
-            c0[k] = in ? p.nax[g] : real(1);
-            c1[k] = in ? p.nbx[g] : real(0);
-            if (DEBYE) {
-                sx[k] = in ? p.in[4][g] : real(0);
-                c2[k] = in ? p.ncx[g] : real(0);
-                c3[k] = in ? p.ndx[g] : real(0);
-            }
-        } else {
-            c0[k] = (in && p.ca) ? p.ca[g] : real(1);
-            c1[k] = (in && p.cb) ? p.cb[g] : real(0.5);
+    for (int k = 0; k < KC; ++k) dx[k] = ix[k] = sx[k] = c2[k] = c3[k] = real(0);
+    ld_cells<real, KC>(p.in[0], g0, vec_ok, p.nx, ex, real(0));
+    ld_cells<real, KC>(p.in[1], g0, vec_ok, p.nx, hy, real(0));
+    if (FLUX) {
+        ld_cells<real, KC>(p.in[2], g0, vec_ok, p.nx, dx, real(0));
+        ld_cells<real, KC>(p.in[3], g0, vec_ok, p.nx, ix, real(0));
+        ld_cells<real, KC>(p.nax, g0, vec_ok, p.nx, c0, real(1));
+        ld_cells<real, KC>(p.nbx, g0, vec_ok, p.nx, c1, real(0));
+        if (DEBYE) {
+            ld_cells<real, KC>(p.in[4], g0, vec_ok, p.nx, sx, real(0));
+            ld_cells<real, KC>(p.ncx, g0, vec_ok, p.nx, c2, real(0));
+            ld_cells<real, KC>(p.ndx, g0, vec_ok, p.nx, c3, real(0));
         }
-        if (p.src_index >= 0 && g == p.src_index) src_k = k;
-        s_hy[c + 1] = hy[k];
-        s_ex[c + 1] = ex[k];
+    } else {
+        if (p.ca) ld_cells<real, KC>(p.ca, g0, vec_ok, p.nx, c0, real(1));
+        else {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) c0[k] = real(1);
+        }
+        if (p.cb) ld_cells<real, KC>(p.cb, g0, vec_ok, p.nx, c1, real(0.5));
+        else {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) c1[k] = real(0.5);
+        }
     }
-    if (tid == 0) { s_hy[0] = s_ex[0] = real(0); s_hy[NT * KC + 1] = s_ex[NT * KC + 1] = real(0); }
-    if (tid < 4) s_bc[tid] = p.abc ? p.bc_in[tid] : real(0);
-    __syncthreads();
+    const int src_k = (p.src_index >= g0 && p.src_index < g0 + KC) ? p.src_index - g0 : -1;   // -1: not in this lane
 
-    const bool has_left = EDGE && p.abc && (base <= 0);                       // staged range contains cells 0, 1
-    const bool has_right = EDGE && p.abc && (base + NT * KC >= p.nx);         // ... and cells nx-2, nx-1
+    // ABC state (EDGE warps whose staged range contains an end of the line; every such warp runs its own copy)
+    const bool has_left = EDGE && p.abc && (base <= 0);
+    const bool has_right = EDGE && p.abc && (base + W >= p.nx);
+    const int k_first = (has_left && 0 >= g0 && 0 < g0 + KC) ? -g0 : -1;                       // my index of cell 0
+    const int k_last = (has_right && p.nx - 1 >= g0 && p.nx - 1 < g0 + KC) ? p.nx - 1 - g0 : -1;   // ... of cell nx-1
+    real b0 = real(0), b1 = real(0), b2 = real(0), b3 = real(0);
+    if (EDGE && p.abc) { b0 = p.bc_in[0]; b1 = p.bc_in[1]; b2 = p.bc_in[2]; b3 = p.bc_in[3]; }
+
     for (int s = 0; s < p.T; ++s) {
-        // ---- E half step: ex (or dx -> ex) of the own cells; hy[i-1] comes from the neighbour through smem
+        // ---- E half step: hy[i-1] of a lane's first cell comes from the lane below
+        const real hy_left = __shfl_up_sync(FULL, hy[KC - 1], 1);
         real curl[KC];
 #pragma unroll
-        for (int k = 0; k < KC; ++k) curl[k] = s_hy[k * NT + tid] - hy[k];     // slot c-1 lives at index c
+        for (int k = 0; k < KC; ++k) curl[k] = ((k == 0) ? hy_left : hy[k == 0 ? 0 : k - 1]) - hy[k];
         if (FLUX) {
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const int g = base + k * NT + tid;
-                if (!EDGE || ((g >= 1) && (g < p.nx))) dx[k] = dx[k] + half * curl[k];
-            }
-            if (src_k >= 0 && p.src_field == 1) {          // at most one thread of the CTA
+            for (int k = 0; k < KC; ++k)
+                if (!EDGE || ((g0 + k >= 1) && (g0 + k < p.nx))) dx[k] = dx[k] + half * curl[k];
+            if (src_k >= 0 && p.src_field == 1) {
 #pragma unroll
                 for (int k = 0; k < KC; ++k)
                     if (k == src_k) dx[k] = inject<real>(dx[k], p.src[s], p.src_hard);
             }
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-                const int g = base + k * NT + tid;
-                if (!EDGE || ((g >= 1) && (g < p.nx))) {
+                if (!EDGE || ((g0 + k >= 1) && (g0 + k < p.nx))) {
                     if (DEBYE) {
                         const real cs = c2[k] * sx[k];
                         ex[k] = c0[k] * ((dx[k] - ix[k]) - cs);
@@ -164,92 +196,94 @@ __device__ __forceinline__ void line_body(const LineParams<real> &p, real *s_ex,
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const int g = base + k * NT + tid;
-                if (!EDGE || ((g >= 1) && (g < p.nx))) ex[k] = (c0[k] * ex[k]) + (c1[k] * curl[k]);
-            }
+            for (int k = 0; k < KC; ++k)
+                if (!EDGE || ((g0 + k >= 1) && (g0 + k < p.nx))) ex[k] = (c0[k] * ex[k]) + (c1[k] * curl[k]);
             if (src_k >= 0 && p.src_field == 0) {
 #pragma unroll
                 for (int k = 0; k < KC; ++k)
                     if (k == src_k) ex[k] = inject<real>(ex[k], p.src[s], p.src_hard);
             }
         }
-#pragma unroll
-        for (int k = 0; k < KC; ++k) s_ex[k * NT + tid + 1] = ex[k];
-        __syncthreads();
-        // ---- two-step-delay ABC (one thread; needs the finished E half step), then its owners re-read
+        // ---- two-step-delay ABC on the finished E half step (fd1d_1_2.py:47-48: the right-hand sides are read first)
         if (EDGE && (has_left || has_right)) {
-            if (tid == 0) {
-                if (has_left) {
-                    const int o = -base + 1;                                   // index of cell 0
-                    const real e1 = s_ex[o + 1], b0 = s_bc[0], b1 = s_bc[1];
-                    s_ex[o] = b0; s_bc[0] = b1; s_bc[1] = e1;
-                }
-                if (has_right) {
-                    const int o = p.nx - 1 - base + 1;                         // index of cell nx-1
-                    const real e2 = s_ex[o - 1], b3 = s_bc[3], b2 = s_bc[2];
-                    s_ex[o] = b3; s_bc[3] = b2; s_bc[2] = e2;
-                }
-            }
-            __syncthreads();
+            const real e_above = __shfl_down_sync(FULL, ex[0], 1);          // ex of the cell after my last one
+            const real e_below = __shfl_up_sync(FULL, ex[KC - 1], 1);       // ex of the cell before my first one
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-                const int g = base + k * NT + tid;
-                if (g == 0 || g == p.nx - 1) ex[k] = s_ex[k * NT + tid + 1];
+                if (k == k_first) {
+                    const real e1 = (k == KC - 1) ? e_above : ex[k == KC - 1 ? k : k + 1];
+                    ex[k] = b0; b0 = b1; b1 = e1;
+                }
+                if (k == k_last) {
+                    const real e2 = (k == 0) ? e_below : ex[k == 0 ? 0 : k - 1];
+                    ex[k] = b3; b3 = b2; b2 = e2;
+                }
             }
         }
-        // ---- H half step: ex[i+1] comes from the neighbour through smem
+        // ---- H half step: ex[i+1] of a lane's last cell comes from the lane above
+        const real ex_right = __shfl_down_sync(FULL, ex[0], 1);
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-            const int g = base + k * NT + tid;
-            const real er = s_ex[k * NT + tid + 2];                            // slot c+1 lives at index c+2
-            if (!EDGE || ((g >= 0) && (g < p.nx - 1))) hy[k] = hy[k] + half * (ex[k] - er);
+            const real er = (k == KC - 1) ? ex_right : ex[k == KC - 1 ? k : k + 1];
+            if (!EDGE || ((g0 + k >= 0) && (g0 + k < p.nx - 1))) hy[k] = hy[k] + half * (ex[k] - er);
         }
-#pragma unroll
-        for (int k = 0; k < KC; ++k) s_hy[k * NT + tid + 1] = hy[k];
-        __syncthreads();
     }
 
-    // ---- write the owned segment to the other array set
+    // ---- write the owned segment to the other array set (whole vectors: halo and useful are multiples of VEC)
+    auto st_cells = [&](real *dst, const real (&d)[KC]) {
+        if (!EDGE) {
 #pragma unroll
-    for (int k = 0; k < KC; ++k) {
-        const int g = base + k * NT + tid;
-        if (g >= seg_lo && g < seg_hi) {
-            p.out[0][g] = ex[k];
-            p.out[1][g] = hy[k];
-            if (FLUX) {
-                p.out[2][g] = dx[k];
-                p.out[3][g] = ix[k];
-                if (DEBYE) p.out[4][g] = sx[k];
+            for (int v = 0; v < KC / VEC; ++v) {
+                const int g = g0 + v * VEC;
+                if (g >= seg_lo && g + VEC <= seg_hi) {
+                    float4 t;
+                    real *q = reinterpret_cast<real *>(&t);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) q[e] = d[v * VEC + e];
+                    *reinterpret_cast<float4 *>(dst + g) = t;
+                }
             }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KC; ++k)
+                if (g0 + k >= seg_lo && g0 + k < seg_hi) dst[g0 + k] = d[k];
         }
+    };
+    st_cells(p.out[0], ex);
+    st_cells(p.out[1], hy);
+    if (FLUX) {
+        st_cells(p.out[2], dx);
+        st_cells(p.out[3], ix);
+        if (DEBYE) st_cells(p.out[4], sx);
     }
-    if (p.abc && tid < 4) {
-        // bc[0..1] belong to the CTA owning cell 0, bc[2..3] to the one owning cell nx-1
-        const bool mine = (tid < 2) ? (seg_lo == 0) : (seg_hi == p.nx);
-        if (mine) p.bc_out[tid] = s_bc[tid];
+    if (EDGE && p.abc) {
+        // bc[0..1] belong to the warp owning cell 0, bc[2..3] to the one owning cell nx-1
+        if (seg_lo == 0 && k_first >= 0) { p.bc_out[0] = b0; p.bc_out[1] = b1; }
+        if (seg_hi == p.nx && k_last >= 0) { p.bc_out[2] = b2; p.bc_out[3] = b3; }
     }
 }
 
 template <typename real, bool FLUX, bool DEBYE>
-__global__ void __launch_bounds__(NT) k1_advance(const __grid_constant__ LineParams<real> p) {
-    __shared__ real s_ex[NT * KC + 2];
-    __shared__ real s_hy[NT * KC + 2];
-    __shared__ real s_bc[4];
-    const int base = blockIdx.x * p.seg - p.T;
-    const bool edge = (base < 1) || (base + NT * KC > p.nx - 1);      // CTA-uniform
-    if (edge) line_body<real, FLUX, DEBYE, true>(p, s_ex, s_hy, s_bc);
-    else      line_body<real, FLUX, DEBYE, false>(p, s_ex, s_hy, s_bc);
+__global__ void __launch_bounds__(128) k1_advance(const __grid_constant__ LineParams<real> p) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= p.nwarps) return;
+    const int base = w * p.useful - p.halo;
+    // warp-uniform: whole staged range strictly inside the line (so no end effects) -- vector accesses are then aligned
+    const bool edge = (base < 1) || (base + LineShape<real>::W > p.nx - 1);
+    if (edge) line_body<real, FLUX, DEBYE, true>(p, w, lane);
+    else      line_body<real, FLUX, DEBYE, false>(p, w, lane);
 }
 
 template <typename real>
 int advance1d(const fdtd1d_problem *q, int cur, int nsteps, const double *src, int tblock, cudaStream_t st,
               int *cur_out) {
+    using Shape = LineShape<real>;
     const bool flux = (q->flags & (FDTD_FLUX | FDTD_DEBYE)) != 0, debye = (q->flags & FDTD_DEBYE) != 0;
     const bool has_src = q->src_index >= 0 && src != nullptr;
+    // vector accesses need 16-byte aligned arrays and nx a multiple of the vector (every interior row start is then aligned)
     int done = 0;
     while (done < nsteps) {
-        const int T = min(tblock, nsteps - done);
+        const int T = min(min(tblock, Shape::TMAX), nsteps - done);
         LineParams<real> lp;
         for (int f = 0; f < 5; ++f) {
             lp.in[f] = (const real *)q->state[cur][f];
@@ -260,14 +294,19 @@ int advance1d(const fdtd1d_problem *q, int cur, int nsteps, const double *src, i
         lp.ca = (const real *)q->ca; lp.cb = (const real *)q->cb;
         lp.nax = (const real *)q->md.nax; lp.nbx = (const real *)q->md.nbx;
         lp.ncx = (const real *)q->md.ncx; lp.ndx = (const real *)q->md.ndx;
-        lp.nx = q->nx; lp.T = T; lp.seg = NT * KC - 2 * T;
+        lp.nx = q->nx; lp.T = T;
+        lp.halo = ((T + Shape::VEC - 1) / Shape::VEC) * Shape::VEC;
+        lp.useful = Shape::W - 2 * lp.halo;
+        lp.nwarps = (q->nx + lp.useful - 1) / lp.useful;
         lp.abc = (q->flags & FDTD_ABC) != 0;
         lp.src_field = q->src_field; lp.src_index = has_src ? q->src_index : -1; lp.src_hard = q->src_hard;
         for (int k = 0; k < T1MAX; ++k) lp.src[k] = (has_src && k < T) ? src[done + k] : 0.0;
-        const int grid = (q->nx + lp.seg - 1) / lp.seg;
-        if (debye)     k1_advance<real, true, true><<<grid, NT, 0, st>>>(lp);
-        else if (flux) k1_advance<real, true, false><<<grid, NT, 0, st>>>(lp);
-        else           k1_advance<real, false, false><<<grid, NT, 0, st>>>(lp);
+        // short lines: one warp per CTA spreads the few warps over the SMs; long lines: 4 warps per CTA
+        const int wpc = lp.nwarps >= 8 * fdtd::sm_count() ? 4 : 1;
+        const int grid = (lp.nwarps + wpc - 1) / wpc;
+        if (debye)     k1_advance<real, true, true><<<grid, 32 * wpc, 0, st>>>(lp);
+        else if (flux) k1_advance<real, true, false><<<grid, 32 * wpc, 0, st>>>(lp);
+        else           k1_advance<real, false, false><<<grid, 32 * wpc, 0, st>>>(lp);
         FDTD_LAUNCH_CHECK("k1_advance");
         cur ^= 1;
         done += T;
@@ -349,10 +388,15 @@ int fdtd1d_advance(const fdtd1d_problem *q, int cur, int nsteps, const double *s
     const bool flux = (q->flags & (FDTD_FLUX | FDTD_DEBYE)) != 0, debye = (q->flags & FDTD_DEBYE) != 0;
     const int nfields = debye ? 5 : (flux ? 4 : 2);
     for (int s = 0; s < 2; ++s) {
-        for (int f = 0; f < nfields; ++f) FDTD_REQUIRE(q->state[s][f], "fdtd1d_advance: state[%d][%d] is null", s, f);
+        for (int f = 0; f < nfields; ++f)
+            FDTD_REQUIRE(q->state[s][f] && fdtd::aligned16(q->state[s][f]), "fdtd1d_advance: state[%d][%d] null or not 16-byte aligned", s, f);
         FDTD_REQUIRE(!(q->flags & FDTD_ABC) || q->bc[s], "fdtd1d_advance: FDTD_ABC needs bc[%d]", s);
     }
     FDTD_REQUIRE(!flux || (q->md.nax && q->md.nbx), "fdtd1d_advance: flux form needs nax/nbx");
+    {
+        const void *coef[6] = {q->ca, q->cb, q->md.nax, q->md.nbx, q->md.ncx, q->md.ndx};
+        for (int k = 0; k < 6; ++k) FDTD_REQUIRE(fdtd::aligned16(coef[k]), "fdtd1d_advance: coefficient array %d not 16-byte aligned", k);
+    }
     FDTD_REQUIRE(!debye || (q->md.ncx && q->md.ndx), "fdtd1d_advance: Debye form needs ncx/ndx");
     FDTD_REQUIRE(q->src_index < q->nx, "fdtd1d_advance: source index %d outside the line", q->src_index);
     FDTD_REQUIRE(q->src_field == 0 || (q->src_field == 1 && flux), "fdtd1d_advance: src_field %d invalid for this form", q->src_field);
