@@ -10,10 +10,11 @@ def build(prog, n, npml):
     if prog == "3_3":
         return fd2d.Fdtd2D(n, n, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)))
     naz, nbz = surface.dielectric_cylinder(n, n, npml, int(n * 0.15), surface.DT, 30.0, 0.30, np.float32)
-    return fd2d.Fdtd2D(n, n, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=naz, nbz=nbz)
+    freqs = np.array([50e6, 300e6, 700e6]) if prog.endswith("dft") else None       # program 3_4 with its running DFT
+    return fd2d.Fdtd2D(n, n, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=naz, nbz=nbz, freqs=freqs)
 
 for prog, n, npml, steps in [("3_2", 1024, 80, 1200), ("3_3", 1024, 80, 1200), ("3_4", 1024, 80, 1200), ("3_2", 2048, 80, 600),
-                             ("3_2", 4096, 80, 240), ("3_4", 4096, 80, 240), ("3_2", 8192, 80, 96), ("3_2", 16384, 80, 48),
+                             ("3_2", 4096, 80, 240), ("3_4", 4096, 80, 240), ("3_4dft", 1024, 80, 600), ("3_4dft", 4096, 80, 120), ("3_2", 8192, 80, 96), ("3_2", 16384, 80, 48),
                              ("3_2", 32768, 80, 96)]:
     sim = build(prog, n, npml)
     sim.advance(24); torch.cuda.synchronize()
