@@ -95,7 +95,13 @@ struct LineParams {
     int nwarps;
     int abc, src_field, src_index, src_hard;
     double src[T1MAX];        // waveform samples of this pass (by value: no staging buffer to manage)
+    unsigned long long negzero2;   // two float -0.0, opaque to the compiler (packed products, see fd2d_march.cu pk_mul)
 };
+
+// packed fp32 (FADD2 / FFMA2): each half rounds like the scalar instruction; a product is FFMA2(a, b, -0.0) with the
+// -0.0 pair from a kernel parameter, because ptxas contracts a packed multiply + add even under --fmad=false
+__device__ __forceinline__ float2 pk_add(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pk_mul(const float2 a, const float2 b, const float2 nz) { return __ffma2_rn(a, b, nz); }
 
 template <typename real, int KC>
 __device__ __forceinline__ void ld_cells(const real *base, long long g0, bool vec_ok, int nx, real (&d)[KC], real fill) {
@@ -166,6 +172,34 @@ __device__ __forceinline__ void line_body(const LineParams<real> &p, const int w
     real b0 = real(0), b1 = real(0), b2 = real(0), b3 = real(0);
     if (EDGE && p.abc) { b0 = p.bc_in[0]; b1 = p.bc_in[1]; b2 = p.bc_in[2]; b3 = p.bc_in[3]; }
 
+    if constexpr (!EDGE && !FLUX && sizeof(real) == 4) {
+        // interior warps of the FDTD form in packed arithmetic: the same operations in the same order, two cells per
+        // instruction except the two shifted-neighbour differences
+        const float2 nz = make_float2(__uint_as_float((unsigned)p.negzero2), __uint_as_float((unsigned)(p.negzero2 >> 32)));
+        const float2 half2 = make_float2(0.5f, 0.5f);
+        for (int s = 0; s < p.T; ++s) {
+            const float hy_left = __shfl_up_sync(FULL, hy[KC - 1], 1);
+#pragma unroll
+            for (int k = 0; k < KC; k += 2) {
+                const float2 curl = make_float2((k == 0 ? hy_left : hy[k == 0 ? 0 : k - 1]) - hy[k], hy[k] - hy[k + 1]);
+                const float2 e = pk_add(pk_mul(make_float2(c0[k], c0[k + 1]), make_float2(ex[k], ex[k + 1]), nz),
+                                        pk_mul(make_float2(c1[k], c1[k + 1]), curl, nz));
+                ex[k] = e.x; ex[k + 1] = e.y;
+            }
+            if (src_k >= 0 && p.src_field == 0) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (k == src_k) ex[k] = inject<real>(ex[k], p.src[s], p.src_hard);
+            }
+            const float ex_right = __shfl_down_sync(FULL, ex[0], 1);
+#pragma unroll
+            for (int k = 0; k < KC; k += 2) {
+                const float2 d = make_float2(ex[k] - ex[k + 1], ex[k + 1] - (k + 2 < KC ? ex[k + 2 < KC ? k + 2 : k] : ex_right));
+                const float2 h = pk_add(make_float2(hy[k], hy[k + 1]), pk_mul(half2, d, nz));
+                hy[k] = h.x; hy[k + 1] = h.y;
+            }
+        }
+    } else
     for (int s = 0; s < p.T; ++s) {
         // ---- E half step: hy[i-1] of a lane's first cell comes from the lane below
         const real hy_left = __shfl_up_sync(FULL, hy[KC - 1], 1);
@@ -301,6 +335,7 @@ int advance1d(const fdtd1d_problem *q, int cur, int nsteps, const double *src, i
         lp.abc = (q->flags & FDTD_ABC) != 0;
         lp.src_field = q->src_field; lp.src_index = has_src ? q->src_index : -1; lp.src_hard = q->src_hard;
         for (int k = 0; k < T1MAX; ++k) lp.src[k] = (has_src && k < T) ? src[done + k] : 0.0;
+        lp.negzero2 = 0x8000000080000000ull;
         // short lines: one warp per CTA spreads the few warps over the SMs; long lines: 4 warps per CTA
         const int wpc = lp.nwarps >= 8 * fdtd::sm_count() ? 4 : 1;
         const int grid = (lp.nwarps + wpc - 1) / wpc;
