@@ -255,6 +255,7 @@ def run_ours(args, emit=print):
                 "config": {"workload": f"fd2d TM+PML {nx_global}x{n} fp32 npml={NPML} point sinusoid 1500 MHz "
                                        f"(BASELINE config 5{'' if world == 1 else ', weak-scaled row slabs'})",
                            "grid_per_gpu": [n, n], "tblock": T, "parallelism": f"slab{world}",
+                           "halo_exchange": getattr(sim, "halo_mode", "none"),
                            "l2": "inputs (52 GB per GPU) far exceed the 126 MB L2; no flush needed",
                            "timing": "CUDA events on the launch stream, barrier+sync both sides, max over ranks"},
                 "gpu_launches": 2 * launches,
