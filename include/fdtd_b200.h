@@ -47,6 +47,9 @@ extern "C" {
 #define FDTD_DEBYE 16          /* 1D Debye medium Sx (program 2_3) */
 #define FDTD_LAZY_EZ 32        /* 2D advance: do not store ez at all (caller finishes with a non-lazy advance
                                   or fdtd2d_efield); ignored with FDTD_LOSSY.  Default: the last pass stores ez. */
+#define FDTD_GHOST_DECAY 64    /* 2D advance on a slab: rows beyond the stored ones are read as zero instead of being
+                                  required -- every step then invalidates one more stored row from each open end
+                                  (communication-avoiding runs: k steps with k ghost rows and no exchange) */
 
 /* structs of device pointers, in the reference's declaration order
  * (fd2d/cuda/test_3_4.cu:20-36, fd1d/cuda/test_2_3.cu:17-27) */

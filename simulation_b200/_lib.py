@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libfdtd_b200.so")
 
 F32, F64 = 0, 1
-TFSF, LOSSY, ABC, FLUX, DEBYE, LAZY_EZ = 1, 2, 4, 8, 16, 32
+TFSF, LOSSY, ABC, FLUX, DEBYE, LAZY_EZ, GHOST_DECAY = 1, 2, 4, 8, 16, 32, 64
 DZ, EZ, HX, HY, IHX, IHY, IZ, NFIELDS = range(8)
 
 
@@ -168,6 +168,10 @@ class DeviceBuffer:
                 self.ptr = None
         except Exception:
             pass
+
+
+def ipc_close(mapped: int) -> None:
+    check(lib().fdtd_ipc_close(C.c_void_p(mapped)), "fdtd_ipc_close")
 
 
 def ipc_open(handle: bytes) -> int:

@@ -990,6 +990,12 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         int T = min(tblock, nsteps - done);
         if (q->nf > 0) T = min(T, 4);                   // fused-DFT kernels: depth <= 4
         if (T == 5 || T == 7) --T;                      // instantiated depths: 1, 2, 3, 4, 6, 8
+        if (q->halo > 0 && T < nsteps) {
+            // the handshake orders whole calls: the last pass pushes into the array set that the neighbour's earlier
+            // passes of the same call would still be reading
+            fdtd::set_error("fdtd2d_advance: the fused halo exchange takes one pass per call (%d steps asked, pass depth %d)", nsteps, T);
+            return FDTD_EINVAL;
+        }
         const int rem = nsteps - done - T;              // steps still to come after this pass
         MarchParams<real> mp;
         void *const *in = q->state[cur];
@@ -1184,7 +1190,7 @@ int fdtd2d_advance(const fdtd2d_problem *q, int cur, int nsteps, const double *s
     FDTD_REQUIRE(nsteps >= 0, "fdtd2d_advance: nsteps < 0");
     FDTD_REQUIRE(q->row_lo >= 0 && q->row_hi <= q->nx && q->row_lo < q->row_hi, "fdtd2d_advance: bad owned rows [%d,%d)", q->row_lo, q->row_hi);
     FDTD_REQUIRE(q->row_base <= q->row_lo && q->row_base + q->rows_alloc >= q->row_hi, "fdtd2d_advance: owned rows outside the stored rows");
-    {   // every row within nsteps of the owned range (clipped to the grid) must be stored
+    if (!(q->flags & FDTD_GHOST_DECAY)) {   // every row within nsteps of the owned range (clipped to the grid) must be stored
         const int need_lo = q->row_lo - nsteps > 0 ? q->row_lo - nsteps : 0;
         const int need_hi = q->row_hi + nsteps < q->nx ? q->row_hi + nsteps : q->nx;
         FDTD_REQUIRE(q->row_base <= need_lo && q->row_base + q->rows_alloc >= need_hi,

@@ -457,22 +457,32 @@ class Fdtd2D:
         of every small launch (0.1 ms of a 0.35 ms launch when one stream drains between them) is filled by its
         neighbours (measured at 32768^2 x 96 steps: 195 -> 176 ms).  The last pass of each block is
         followed by the download of that block's Ez.  Same kernels, same arithmetic, same result as
-        ``set naz; advance(nsteps); get ez``.  ``naz_host`` / ``ez_host``: pinned CPU tensors of shape (nx, ny).
-        Point source or no source only (the TFSF incident line is advanced once per whole-grid pass); single device."""
-        if self.tfsf or self.ft is not None or self.rows_alloc != self.nx:
-            raise _lib.FdtdError("run_streamed: single-device grids with a point source (or none) and no running DFT")
-        if tuple(naz_host.shape) != (self.nx, self.ny) or tuple(ez_host.shape) != (self.nx, self.ny):
-            raise _lib.FdtdError("run_streamed: host tensors must have shape (nx, ny)")
+        ``set naz; advance(nsteps); get ez``.  ``naz_host``: pinned CPU tensor over the stored rows, ``ez_host`` over the
+        owned rows (both (nx, ny) on a single device).  Point source or no source only (the TFSF incident line is
+        advanced once per whole-grid pass).
+
+        On a slab (``rows=``, ``ghost=g``) the run is communication-avoiding: at most g steps, during which the
+        ghost band is consumed one row per step instead of being exchanged (``FDTD_GHOST_DECAY``) -- the owned rows come
+        out exact, the ghost rows must be refreshed before stepping on (``SlabFdtd2D.run_streamed`` does)."""
+        if self.tfsf or self.ft is not None:
+            raise _lib.FdtdError("run_streamed: point source (or none) and no running DFT")
+        slab = self.rows_alloc != self.nx
+        rows_own = self.row_hi - self.row_lo
+        if slab and int(nsteps) > self.ghost:
+            raise _lib.FdtdError(f"run_streamed on a slab: {nsteps} steps without an exchange need {nsteps} ghost rows, have {self.ghost}")
+        if tuple(naz_host.shape) != (self.rows_alloc, self.ny) or tuple(ez_host.shape) != (rows_own, self.ny):
+            raise _lib.FdtdError("run_streamed: naz_host must cover the stored rows (rows_alloc, ny), ez_host the owned rows")
         depths = self._depths(nsteps, tblock)
         P = len(depths)
         S = max(1, min(int(streams), P))
+        lo_all, hi_all = self.row_base, self.row_base + self.rows_alloc           # global rows stored here
         if blocks is None and block_rows is None:
-            block_rows = 1024 if self.nx >= 8192 else max(4 * max(depths), -(-self.nx // 8))
+            block_rows = 1024 if self.rows_alloc >= 8192 else max(4 * max(depths), -(-self.rows_alloc // 8))
         if block_rows:                                   # explicit block height (the last block takes the remainder)
-            edges = list(range(0, self.nx, max(int(block_rows), 4 * max(depths)))) + [self.nx]
+            edges = list(range(lo_all, hi_all, max(int(block_rows), 4 * max(depths)))) + [hi_all]
         else:
-            B = max(1, min(int(blocks), self.nx // max(4 * max(depths), 1)))
-            edges = [self.nx * k // B for k in range(B + 1)]
+            B = max(1, min(int(blocks), self.rows_alloc // max(4 * max(depths), 1)))
+            edges = [lo_all + self.rows_alloc * k // B for k in range(B + 1)]
         B = len(edges) - 1
         src = None
         if self.source is not None:
@@ -489,7 +499,8 @@ class Fdtd2D:
             uploaded = []
             with torch.cuda.stream(up):
                 for b in range(B):
-                    self.naz[edges[b]:edges[b + 1]].copy_(naz_host[edges[b]:edges[b + 1]], non_blocking=True)
+                    a, z = edges[b] - lo_all, edges[b + 1] - lo_all
+                    self.naz[a:z].copy_(naz_host[a:z], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(up)
                     uploaded.append(ev)
@@ -509,6 +520,8 @@ class Fdtd2D:
                     prob.row_lo, prob.row_hi = edges[b], edges[b + 1]
                     if p_idx < P - 1:
                         prob.flags |= _lib.LAZY_EZ
+                    if slab:
+                        prob.flags |= _lib.GHOST_DECAY          # the ghost band is consumed instead of exchanged
                     out = C.c_int(-1)
                     k0 = int(first_step[p_idx])
                     if trace is not None:                                  # timeline probe (tools/probe_streamed.py)
@@ -525,9 +538,11 @@ class Fdtd2D:
                         trace.append((b, p_idx, t0, ev))
                     if p_idx == P - 1:
                         down.wait_event(ev)
-                        with torch.cuda.stream(down):
-                            ez_dev = self._sets[(cur0 + P) % 2]["ez"]
-                            ez_host[edges[b]:edges[b + 1]].copy_(ez_dev[edges[b]:edges[b + 1]], non_blocking=True)
+                        a, z = max(edges[b], self.row_lo), min(edges[b + 1], self.row_hi)     # owned rows of this block
+                        if z > a:
+                            with torch.cuda.stream(down):
+                                ez_dev = self._sets[(cur0 + P) % 2]["ez"]
+                                ez_host[a - self.row_lo:z - self.row_lo].copy_(ez_dev[a - lo_all:z - lo_all], non_blocking=True)
             for st in lanes + [up, down]:
                 caller.wait_stream(st)
         self._cur = (cur0 + P) % 2

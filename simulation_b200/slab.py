@@ -38,7 +38,8 @@ class SlabFdtd2D:
     logic under gloo without a GPU)."""
 
     def __init__(self, nx: int, ny: int, npml: int = 0, dtype=np.float32, *, ghost: Optional[int] = None,
-                 tblock: int = 4, group=None, engine_factory: Optional[Callable] = None, **engine_kw):
+                 tblock: int = 4, group=None, engine_factory: Optional[Callable] = None, halo: Optional[str] = None,
+                 **engine_kw):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -47,7 +48,7 @@ class SlabFdtd2D:
         self.row_lo, self.row_hi = partition(self.nx, self.world, self.rank)
         if self.world > 1 and (self.row_hi - self.row_lo) < self.ghost:
             raise ValueError(f"slab of {self.row_hi - self.row_lo} rows is thinner than the ghost band {self.ghost}")
-        want = os.environ.get("FDTD_SLAB_HALO", "p2p")
+        want = halo or os.environ.get("FDTD_SLAB_HALO", "p2p")          # "p2p" (fused into the pass) or "nccl"
         p2p_wanted = self.world > 1 and want == "p2p" and engine_factory is None and engine_kw.get("freqs") is None
         if engine_factory is None:
             from .fd2d import Fdtd2D
@@ -124,6 +125,32 @@ class SlabFdtd2D:
             eng.p2p = {"halo": self.ghost, "sync": sync, "up": open_peer(self.up), "dn": open_peer(self.down)}
         self.halo_mode = "p2p"            # the caller's all_reduce doubles as the barrier after the mapping
 
+    def close(self) -> None:
+        """Collective teardown: unmap the neighbours' arrays before anybody frees them (CUDA IPC rule), then drop the
+        engine.  Needed only when another problem is built afterwards in the same process."""
+        from . import _lib
+        eng = self.engine
+        if eng is None:
+            return
+        torch.cuda.synchronize(eng.device)
+        p2p = getattr(eng, "p2p", None)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if p2p is not None:
+            with torch.cuda.device(eng.device):
+                for side in ("up", "dn"):
+                    nb = p2p[side]
+                    if nb is None:
+                        continue
+                    _lib.ipc_close(nb["sync"])
+                    for st in nb["sets"]:
+                        for ptr in st.values():
+                            _lib.ipc_close(ptr)
+            eng.p2p = None
+            if self.world > 1:
+                dist.barrier(group=self.group)
+        self.engine = None
+
     # ---- ghost exchange ------------------------------------------------------------------------------
     def _names(self):
         return [n for n in EXCHANGED if n != "iz" or getattr(self.engine, "lossy", False)]
@@ -166,13 +193,26 @@ class SlabFdtd2D:
             n = min(left, self.ghost) if self.world > 1 else left
             left -= n
             if self.halo_mode == "p2p":
-                # the pass pushes its edge rows into the neighbours' ghost rows and waits on their flags itself
+                # the pass pushes its edge rows into the neighbours' ghost rows and waits on their flags itself.
+                # ONE pass per call: the push lands in the set the neighbour's earlier passes of a multi-pass call
+                # would still be reading (the per-call handshake only orders whole calls)
+                n_one = self.engine._depths(n, tblock)[0]
+                left += n - n_one
+                n = n_one
                 self._epoch += 1
                 self.engine.advance(n, tblock=tblock, lazy_ez=left > 0, epoch=self._epoch)
                 self.exchanges += 1
             else:
                 self.engine.advance(n, tblock=tblock, lazy_ez=left > 0)    # ez is stored by the last block only
                 self.exchange_ghosts()
+
+    def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, **kw) -> None:
+        """Host medium in, ``nsteps <= ghost`` steps, host Ez out, with the transfers hidden behind the kernels and NO
+        exchange at all: every rank runs the block wavefront of :meth:`fd2d.Fdtd2D.run_streamed` on its stored rows
+        and lets the ghost band decay (one row per step).  ``naz_host`` covers the stored rows, ``ez_host`` the owned
+        rows.  The ghost rows are refreshed (one exchange) before the next ``advance``."""
+        self.engine.run_streamed(nsteps, naz_host, ez_host, **kw)
+        self._ghost_dirty = self.world > 1
 
     def gather(self, name: str) -> Optional[np.ndarray]:
         """Whole-grid field on rank 0 (tests / small grids only)."""

@@ -21,15 +21,29 @@ def make_source(prog, nx, ny):
 
 def main():
     prog, nx, ny, npml, ns, tblock = sys.argv[1], *[int(x) for x in sys.argv[2:7]]
+    ghost = int(sys.argv[7]) if len(sys.argv) > 7 else None          # ghost rows (default: tblock); > tblock: several passes per exchange
+    streamed = len(sys.argv) > 8 and sys.argv[8] == "streamed"       # first block of steps through run_streamed (no exchange)
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     rank = dist.get_rank()
     rng = np.random.default_rng(11)
     naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
-    s = slab.SlabFdtd2D(nx, ny, npml, np.float32, tblock=tblock, source=make_source(prog, nx, ny), naz=naz)
-    s.advance(7)                       # ragged split of the step count across advance() calls
-    s.advance(ns - 7)
+    s = slab.SlabFdtd2D(nx, ny, npml, np.float32, tblock=tblock, ghost=ghost, source=make_source(prog, nx, ny),
+                        naz=None if streamed else naz)
+    if streamed:
+        e = s.engine
+        host_naz = torch.from_numpy(naz[e.row_base:e.row_base + e.rows_alloc].copy()).pin_memory()
+        host_ez = torch.empty((s.row_hi - s.row_lo, ny), dtype=torch.float32).pin_memory()
+        first = min(ns - 7, s.ghost)
+        s.run_streamed(first, host_naz, host_ez, blocks=3, streams=4)       # consumes the ghost band, no exchange
+        s.synchronize()
+        mine = s.tensor("ez").cpu()
+        assert torch.equal(host_ez, mine), "streamed Ez on the host differs from the device copy"
+        s.advance(ns - first)          # ghost rows are refreshed first
+    else:
+        s.advance(7)                   # ragged split of the step count across advance() calls
+        s.advance(ns - 7)
     s.synchronize()
     ok = True
     fields = {name: s.gather(name) for name in ("dz", "ez", "hx", "hy", "ihx", "ihy")}

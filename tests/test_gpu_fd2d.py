@@ -392,6 +392,31 @@ def test_streamed_run_equals_plain_run(blocks, streams):
     assert b.t == ns and float(host_ez.abs().max()) > 1e-3
 
 
+@pytest.mark.parametrize("rows,ghost,ns", [((300, 700), 48, 48), ((0, 500), 30, 24), ((900, 1500), 36, 36)])
+def test_streamed_run_on_a_slab_consumes_its_ghost_band(rows, ghost, ns):
+    """Communication-avoiding streamed run: a slab with g ghost rows takes <= g steps with no exchange (rows beyond
+    the stored ones read as zero, FDTD_GHOST_DECAY) and its OWNED rows equal the same rows of the whole-grid run."""
+    from simulation_b200 import fd2d, surface
+    rng = np.random.default_rng(9)
+    nx, ny, npml = 1500, 640, 16
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    src = fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6))
+    whole = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, naz=naz)
+    whole.advance(ns)
+    part = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, rows=rows, ghost=ghost)
+    lo, hi = part.row_base, part.row_base + part.rows_alloc
+    host_naz = torch.from_numpy(naz[lo:hi].copy()).pin_memory()
+    host_ez = torch.empty((rows[1] - rows[0], ny), dtype=torch.float32).pin_memory()
+    part.run_streamed(ns, host_naz, host_ez, blocks=4, streams=3)
+    part.synchronize()
+    assert torch.equal(host_ez, whole.tensor("ez")[rows[0]:rows[1]].cpu())
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(part.tensor(name), whole.tensor(name)[rows[0]:rows[1]]), name
+    assert float(whole.tensor("ez").abs().max()) > 1e-3
+    with pytest.raises(Exception):
+        part.run_streamed(ghost + 1, host_naz, host_ez)              # more steps than ghost rows
+
+
 # ------------------------------------------------------------------ error behaviour of the boundary
 def test_errors_are_reported_not_swallowed():
     from simulation_b200 import _lib, fd2d, surface
