@@ -293,10 +293,11 @@ __device__ __forceinline__ float2 pk_sub(const float2 a, const float2 b) { retur
 __device__ __forceinline__ float2 pk_mul(const float2 a, const float2 b, const float2 negzero) { return __ffma2_rn(a, b, negzero); }
 
 // Interior stage in packed arithmetic (float, even V): same operations in the same order as march_stage<.., FAST>.
-template <int V, bool NAZR>
+template <int V, bool NAZR, bool LOSSY>
 __device__ __forceinline__ void march_stage_pk(RowSet<float, V> &A, RowSet<float, V> &Hd, const float2 negzero,
                                                const void *naz_smem, const void *naz_held_smem) {
     static_assert(V % 2 == 0, "packed stage needs column pairs");
+    static_assert(!(NAZR && LOSSY), "the naz ring serves the plain interior kernel only");
     constexpr unsigned FULL = 0xffffffffu;
     const float2 half2 = make_float2(0.5f, 0.5f), zero2 = make_float2(0.f, 0.f);
     // ---- D of the arriving row: dz = dz + 0.5*(((hy - hy[i-1]) - hx) + hx[j-1])
@@ -324,7 +325,15 @@ __device__ __forceinline__ void march_stage_pk(RowSet<float, V> &A, RowSet<float
     } else {
 #pragma unroll
         for (int v = 0; v < V; v += 2) {
-            const float2 a = pk_mul(make_float2(A.naz[v], A.naz[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
+            float2 a;
+            if constexpr (LOSSY) {      // ez = naz*(dz - iz); iz = iz + nbz*ez
+                const float2 iz = make_float2(A.iz[v], A.iz[v + 1]);
+                a = pk_mul(make_float2(A.naz[v], A.naz[v + 1]), pk_sub(make_float2(A.dz[v], A.dz[v + 1]), iz), negzero);
+                const float2 i2 = pk_add(iz, pk_mul(make_float2(A.nbz[v], A.nbz[v + 1]), a, negzero));
+                A.iz[v] = i2.x; A.iz[v + 1] = i2.y;
+            } else {
+                a = pk_mul(make_float2(A.naz[v], A.naz[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
+            }
             A.ez[v] = a.x; A.ez[v + 1] = a.y;
             ezA[v] = a.x; ezA[v + 1] = a.y; ezH[v] = Hd.ez[v]; ezH[v + 1] = Hd.ez[v + 1];
         }
@@ -360,7 +369,7 @@ template <typename real, int V, int T, int MODE, bool FAST>
 struct MarchShape {
     static constexpr bool LOSSY = (MODE & 1) != 0, DFT = (MODE & 2) != 0;
     static constexpr bool NAZR = FAST && !LOSSY && !DFT && T >= 7;
-    static constexpr bool PACKED = FAST && !LOSSY && !DFT && sizeof(real) == 4 && V % 2 == 0;   // FADD2 / FFMA2 stage
+    static constexpr bool PACKED = FAST && !DFT && sizeof(real) == 4 && V % 2 == 0;   // FADD2 / FFMA2 stage
     static constexpr int NS = T + 1;                                   // register row sets
     static constexpr int NARR = (LOSSY ? 8 : 6) + (DFT ? 2 * NFMAX : 0) - (NAZR ? 1 : 0);   // arrays per main-ring row
     static constexpr int LB = V * (int)sizeof(real);                   // bytes per lane per array row
@@ -523,7 +532,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
             st_vec(p.out_hy + off_s, O.hy);
             st_vec(p.out_ihx + off_s, O.ihx);
             st_vec(p.out_ihy + off_s, O.ihy);
-            if (LOSSY) VecIO<real, V>::st(p.out_iz + off_s, O.iz);
+            if (LOSSY) st_vec(p.out_iz + off_s, O.iz);
             if (DFT) {
 #pragma unroll
                 for (int f = 0; f < NFMAX; ++f)
@@ -578,7 +587,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
                     const void *nzA = lane_naz + ((u >= s) ? nz_here + (u - s) * ROWB : nz_other + (NS + u - s) * ROWB);
                     const void *nzH = lane_naz + ((u >= s + 1) ? nz_here + (u - s - 1) * ROWB : nz_other + (NS + u - s - 1) * ROWB);
                     if constexpr (Shape::PACKED)
-                        march_stage_pk<V, NAZR>(S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], negzero, nzA, nzH);
+                        march_stage_pk<V, NAZR, LOSSY>(S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], negzero, nzA, nzH);
                     else
                         march_stage<real, V, MODE, FAST, NAZR>(p, c, S[(u - s + 2 * NS) % NS], S[(u - s - 1 + 2 * NS) % NS], rr - s,
                                                                 s, jb, tf_cols, src_cols, nzA, nzH);
