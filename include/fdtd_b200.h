@@ -115,6 +115,14 @@ typedef struct {
     void *bc[2];                       /* two ping-pong copies of bc[4] */
     int src_field;                     /* 0: ex, 1: dx */
     int src_index, src_hard;           /* src_index < 0: no source */
+    /* Running DFT carried through the passes (programs 2_2 / 2_3 `fourier`, fd1d/program/fd1d_2_2.py:65-71): nf <= 3
+     * frequencies (0 = off); ft.r_pt / ft.i_pt are nf x nx accumulators, ft.r_in / ft.i_in (nf each, may be NULL)
+     * accumulate ex[dft_sample] (10 in the reference); dft_cos / dft_sin are HOST float64 tables [step][nf] of
+     * cos/sin(2*pi*f*dt*t) for the steps of this call.  Every step samples Ex after the E update and before the ABC,
+     * with the float64-then-round arithmetic of fdtd1d_fourier; passes are limited to 16 (float64: 8) steps. */
+    int nf, dft_sample;
+    fdtd_ftrans ft;
+    const double *dft_cos, *dft_sin;
 } fdtd1d_problem;
 /* advance nsteps steps starting from state set `cur`; src[k] is the float64 waveform sample of the k-th of
  * these steps (HOST pointer, may be NULL without a source).  *cur_out = set holding the result.

@@ -44,7 +44,9 @@ class Problem1D(C.Structure):
     _fields_ = [("dtype", C.c_int), ("nx", C.c_int), ("flags", C.c_int),
                 ("ca", C.c_void_p), ("cb", C.c_void_p), ("md", Medium1D),
                 ("state", (C.c_void_p * 5) * 2), ("bc", C.c_void_p * 2),
-                ("src_field", C.c_int), ("src_index", C.c_int), ("src_hard", C.c_int)]
+                ("src_field", C.c_int), ("src_index", C.c_int), ("src_hard", C.c_int),
+                ("nf", C.c_int), ("dft_sample", C.c_int), ("ft", FTrans),
+                ("dft_cos", C.POINTER(C.c_double)), ("dft_sin", C.POINTER(C.c_double))]
 
 
 class Problem2D(C.Structure):

@@ -77,8 +77,9 @@ __global__ void k1_hy(int nx, const real *ex, real *hy) {
 // through memory; the ping-pong array sets make the warps order-free.
 constexpr int T1MAX = 64;     // most steps per call of the time-block argument (deeper requests are split)
 
-template <typename real> struct LineShape {
-    static constexpr int KC = sizeof(real) == 4 ? 16 : 8;     // cells per lane (registers: 9 arrays x KC x words)
+// DFT: the running-DFT variant also carries 2 x nf accumulators per cell in registers -> half the cells per lane
+template <typename real, bool DFT = false> struct LineShape {
+    static constexpr int KC = (sizeof(real) == 4 ? 16 : 8) / (DFT ? 2 : 1);   // cells per lane (registers: 9 arrays x KC x words)
     static constexpr int VEC = 16 / (int)sizeof(real);        // cells per 16-byte vector access
     static constexpr int W = 32 * KC;                         // cells staged per warp
     static constexpr int TMAX = 2 * KC;                       // deepest pass: halo <= W/8 per side
@@ -98,6 +99,18 @@ struct LineParams {
     unsigned long long negzero2;   // two float -0.0, opaque to the compiler (packed products, see fd2d_march.cu pk_mul)
 };
 
+// Running DFT carried through a pass (programs 2_2 / 2_3, fd1d/program/fd1d_2_2.py:65-71): every step samples Ex
+// between the E update and the ABC.  Phase factors of the pass by value (float64, evaluated on the host with the
+// reference's expression); accumulators are read and written in place by the lane that owns the cell.
+constexpr int DFT_NF = 3;         // frequencies the fused variant carries (more: unfused per-step path on the host side)
+constexpr int DFT_TMAX = 16;      // deepest DFT pass (= LineShape<float, true>::TMAX)
+template <typename real>
+struct LineDft {
+    real *r_pt, *i_pt, *r_in, *i_in;      // r_pt / i_pt: nf x nx; r_in / i_in: nf (may be NULL)
+    int nf, sample;                       // sample: cell whose Ex feeds r_in / i_in (10 in the reference)
+    double c[DFT_NF][DFT_TMAX], s[DFT_NF][DFT_TMAX];
+};
+
 // packed fp32 (FADD2 / FFMA2): each half rounds like the scalar instruction; a product is FFMA2(a, b, -0.0) with the
 // -0.0 pair from a kernel parameter, because ptxas contracts a packed multiply + add even under --fmad=false
 __device__ __forceinline__ float2 pk_add(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
@@ -105,7 +118,7 @@ __device__ __forceinline__ float2 pk_mul(const float2 a, const float2 b, const f
 
 template <typename real, int KC>
 __device__ __forceinline__ void ld_cells(const real *base, long long g0, bool vec_ok, int nx, real (&d)[KC], real fill) {
-    constexpr int VEC = LineShape<real>::VEC;
+    constexpr int VEC = 16 / (int)sizeof(real);
     if (vec_ok) {
 #pragma unroll
         for (int v = 0; v < KC / VEC; ++v) {
@@ -125,9 +138,11 @@ __device__ __forceinline__ void ld_cells(const real *base, long long g0, bool ve
 
 // EDGE: the staged range touches an end of the line (cells outside the line, the never-updated ex[0], ex[nx-1],
 // hy[nx-1], the ABC) or is not vector-aligned; interior warps run without any mask.
-template <typename real, bool FLUX, bool DEBYE, bool EDGE>
-__device__ __forceinline__ void line_body(const LineParams<real> &p, const int w, const int lane) {
-    constexpr int KC = LineShape<real>::KC, VEC = LineShape<real>::VEC, W = LineShape<real>::W;
+template <typename real, bool FLUX, bool DEBYE, bool EDGE, bool DFT = false>
+__device__ __forceinline__ void line_body(const LineParams<real> &p, const int w, const int lane,
+                                          const LineDft<real> *dft = nullptr) {
+    using Shape = LineShape<real, DFT>;
+    constexpr int KC = Shape::KC, VEC = Shape::VEC, W = Shape::W;
     constexpr unsigned FULL = 0xffffffffu;
     const real half = real(0.5);
     const int seg_lo = w * p.useful, seg_hi = min(seg_lo + p.useful, p.nx);
@@ -172,7 +187,31 @@ __device__ __forceinline__ void line_body(const LineParams<real> &p, const int w
     real b0 = real(0), b1 = real(0), b2 = real(0), b3 = real(0);
     if (EDGE && p.abc) { b0 = p.bc_in[0]; b1 = p.bc_in[1]; b2 = p.bc_in[2]; b3 = p.bc_in[3]; }
 
-    if constexpr (!EDGE && !FLUX && sizeof(real) == 4) {
+    // running-DFT accumulators of the cells this lane OWNS (plain loads: other warps write their own cells of the same
+    // arrays during this launch); the lane owning the sample cell also carries r_in / i_in
+    constexpr int NFR = DFT ? DFT_NF : 1, KCR = DFT ? KC : 1;
+    real acc_r[NFR][KCR], acc_i[NFR][KCR], in_r[NFR], in_i[NFR];
+    int smp_k = -1;
+    if constexpr (DFT) {
+#pragma unroll
+        for (int f = 0; f < DFT_NF; ++f) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int g = g0 + k;
+                const bool mine = f < dft->nf && g >= seg_lo && g < seg_hi;
+                acc_r[f][k] = mine ? dft->r_pt[(size_t)f * p.nx + g] : real(0);
+                acc_i[f][k] = mine ? dft->i_pt[(size_t)f * p.nx + g] : real(0);
+            }
+        }
+        if (dft->r_in && dft->sample >= max(g0, seg_lo) && dft->sample < min(g0 + KC, seg_hi)) smp_k = dft->sample - g0;
+#pragma unroll
+        for (int f = 0; f < DFT_NF; ++f) {
+            in_r[f] = (smp_k >= 0 && f < dft->nf) ? dft->r_in[f] : real(0);
+            in_i[f] = (smp_k >= 0 && f < dft->nf) ? dft->i_in[f] : real(0);
+        }
+    }
+
+    if constexpr (!EDGE && !FLUX && !DFT && sizeof(real) == 4) {
         // interior warps of the FDTD form in packed arithmetic: the same operations in the same order, two cells per
         // instruction except the two shifted-neighbour differences
         const float2 nz = make_float2(__uint_as_float((unsigned)p.negzero2), __uint_as_float((unsigned)(p.negzero2 >> 32)));
@@ -238,6 +277,26 @@ __device__ __forceinline__ void line_body(const LineParams<real> &p, const int w
                     if (k == src_k) ex[k] = inject<real>(ex[k], p.src[s], p.src_hard);
             }
         }
+        // ---- running DFT of the finished E update, BEFORE the ABC (fd1d_2_2.py:138-142: dxfield, exfield, fourier,
+        //      hyfield); float64 product and sum, one rounding into the array type per step (= k_fourier)
+        if constexpr (DFT) {
+#pragma unroll
+            for (int f = 0; f < DFT_NF; ++f) {
+                if (f < dft->nf) {
+                    const double cf = dft->c[f][s], sf = dft->s[f][s];
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) {
+                        const double e = static_cast<double>(ex[k]);
+                        acc_r[f][k] = static_cast<real>(static_cast<double>(acc_r[f][k]) + cf * e);
+                        acc_i[f][k] = static_cast<real>(static_cast<double>(acc_i[f][k]) - sf * e);
+                        if (k == smp_k) {
+                            in_r[f] = static_cast<real>(static_cast<double>(in_r[f]) + cf * e);
+                            in_i[f] = static_cast<real>(static_cast<double>(in_i[f]) - sf * e);
+                        }
+                    }
+                }
+            }
+        }
         // ---- two-step-delay ABC on the finished E half step (fd1d_1_2.py:47-48: the right-hand sides are read first)
         if (EDGE && (has_left || has_right)) {
             const real e_above = __shfl_down_sync(FULL, ex[0], 1);          // ex of the cell after my last one
@@ -290,6 +349,22 @@ __device__ __forceinline__ void line_body(const LineParams<real> &p, const int w
         st_cells(p.out[3], ix);
         if (DEBYE) st_cells(p.out[4], sx);
     }
+    if constexpr (DFT) {
+#pragma unroll
+        for (int f = 0; f < DFT_NF; ++f) {
+            if (f < dft->nf) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const int g = g0 + k;
+                    if (g >= seg_lo && g < seg_hi) {
+                        dft->r_pt[(size_t)f * p.nx + g] = acc_r[f][k];
+                        dft->i_pt[(size_t)f * p.nx + g] = acc_i[f][k];
+                    }
+                }
+                if (smp_k >= 0) { dft->r_in[f] = in_r[f]; dft->i_in[f] = in_i[f]; }
+            }
+        }
+    }
     if (EDGE && p.abc) {
         // bc[0..1] belong to the warp owning cell 0, bc[2..3] to the one owning cell nx-1
         if (seg_lo == 0 && k_first >= 0) { p.bc_out[0] = b0; p.bc_out[1] = b1; }
@@ -308,13 +383,25 @@ __global__ void __launch_bounds__(128) k1_advance(const __grid_constant__ LinePa
     else      line_body<real, FLUX, DEBYE, false>(p, w, lane);
 }
 
-template <typename real>
+// the same pass carrying the running DFT (half the cells per lane, accumulators in registers)
+template <typename real, bool FLUX, bool DEBYE>
+__global__ void __launch_bounds__(128) k1_advance_dft(const __grid_constant__ LineParams<real> p,
+                                                      const __grid_constant__ LineDft<real> d) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= p.nwarps) return;
+    const int base = w * p.useful - p.halo;
+    const bool edge = (base < 1) || (base + LineShape<real, true>::W > p.nx - 1);
+    if (edge) line_body<real, FLUX, DEBYE, true, true>(p, w, lane, &d);
+    else      line_body<real, FLUX, DEBYE, false, true>(p, w, lane, &d);
+}
+
+template <typename real, bool DFT>
 int advance1d(const fdtd1d_problem *q, int cur, int nsteps, const double *src, int tblock, cudaStream_t st,
               int *cur_out) {
-    using Shape = LineShape<real>;
+    using Shape = LineShape<real, DFT>;
     const bool flux = (q->flags & (FDTD_FLUX | FDTD_DEBYE)) != 0, debye = (q->flags & FDTD_DEBYE) != 0;
     const bool has_src = q->src_index >= 0 && src != nullptr;
-    // vector accesses need 16-byte aligned arrays and nx a multiple of the vector (every interior row start is then aligned)
+    // vector accesses need 16-byte aligned arrays; a warp's first staged cell is a whole number of vectors into the line
     int done = 0;
     while (done < nsteps) {
         const int T = min(min(tblock, Shape::TMAX), nsteps - done);
@@ -339,10 +426,29 @@ int advance1d(const fdtd1d_problem *q, int cur, int nsteps, const double *src, i
         // short lines: one warp per CTA spreads the few warps over the SMs; long lines: 4 warps per CTA
         const int wpc = lp.nwarps >= 8 * fdtd::sm_count() ? 4 : 1;
         const int grid = (lp.nwarps + wpc - 1) / wpc;
-        if (debye)     k1_advance<real, true, true><<<grid, 32 * wpc, 0, st>>>(lp);
-        else if (flux) k1_advance<real, true, false><<<grid, 32 * wpc, 0, st>>>(lp);
-        else           k1_advance<real, false, false><<<grid, 32 * wpc, 0, st>>>(lp);
-        FDTD_LAUNCH_CHECK("k1_advance");
+        if constexpr (DFT) {
+            static_assert(Shape::TMAX <= DFT_TMAX, "phase table too small for the deepest DFT pass");
+            LineDft<real> ld;
+            ld.r_pt = (real *)q->ft.r_pt; ld.i_pt = (real *)q->ft.i_pt;
+            ld.r_in = (q->ft.r_in && q->ft.i_in) ? (real *)q->ft.r_in : nullptr;
+            ld.i_in = ld.r_in ? (real *)q->ft.i_in : nullptr;
+            ld.nf = q->nf; ld.sample = q->dft_sample;
+            for (int f = 0; f < DFT_NF; ++f)
+                for (int k = 0; k < DFT_TMAX; ++k) {
+                    const bool on = f < q->nf && k < T;
+                    ld.c[f][k] = on ? q->dft_cos[(size_t)(done + k) * q->nf + f] : 0.0;
+                    ld.s[f][k] = on ? q->dft_sin[(size_t)(done + k) * q->nf + f] : 0.0;
+                }
+            if (debye)     k1_advance_dft<real, true, true><<<grid, 32 * wpc, 0, st>>>(lp, ld);
+            else if (flux) k1_advance_dft<real, true, false><<<grid, 32 * wpc, 0, st>>>(lp, ld);
+            else           k1_advance_dft<real, false, false><<<grid, 32 * wpc, 0, st>>>(lp, ld);
+            FDTD_LAUNCH_CHECK("k1_advance_dft");
+        } else {
+            if (debye)     k1_advance<real, true, true><<<grid, 32 * wpc, 0, st>>>(lp);
+            else if (flux) k1_advance<real, true, false><<<grid, 32 * wpc, 0, st>>>(lp);
+            else           k1_advance<real, false, false><<<grid, 32 * wpc, 0, st>>>(lp);
+            FDTD_LAUNCH_CHECK("k1_advance");
+        }
         cur ^= 1;
         done += T;
     }
@@ -435,8 +541,16 @@ int fdtd1d_advance(const fdtd1d_problem *q, int cur, int nsteps, const double *s
     FDTD_REQUIRE(!debye || (q->md.ncx && q->md.ndx), "fdtd1d_advance: Debye form needs ncx/ndx");
     FDTD_REQUIRE(q->src_index < q->nx, "fdtd1d_advance: source index %d outside the line", q->src_index);
     FDTD_REQUIRE(q->src_field == 0 || (q->src_field == 1 && flux), "fdtd1d_advance: src_field %d invalid for this form", q->src_field);
-    if (q->dtype == FDTD_F32) return advance1d<float>(q, cur, nsteps, src, tblock, fdtd::as_stream(stream), cur_out);
-    if (q->dtype == FDTD_F64) return advance1d<double>(q, cur, nsteps, src, tblock, fdtd::as_stream(stream), cur_out);
+    FDTD_REQUIRE(q->nf >= 0 && q->nf <= DFT_NF, "fdtd1d_advance: nf=%d outside [0, %d] (more frequencies: fdtd1d_fourier after every step)", q->nf, DFT_NF);
+    if (q->nf > 0) {
+        FDTD_REQUIRE(q->ft.r_pt && q->ft.i_pt && q->dft_cos && q->dft_sin, "fdtd1d_advance: running DFT needs ft.r_pt / ft.i_pt and the phase tables");
+        FDTD_REQUIRE(!(q->ft.r_in && q->ft.i_in) || (q->dft_sample >= 0 && q->dft_sample < q->nx),
+                     "fdtd1d_advance: DFT sample cell %d outside the line", q->dft_sample);
+        if (q->dtype == FDTD_F32) return advance1d<float, true>(q, cur, nsteps, src, tblock, fdtd::as_stream(stream), cur_out);
+        if (q->dtype == FDTD_F64) return advance1d<double, true>(q, cur, nsteps, src, tblock, fdtd::as_stream(stream), cur_out);
+    }
+    if (q->dtype == FDTD_F32) return advance1d<float, false>(q, cur, nsteps, src, tblock, fdtd::as_stream(stream), cur_out);
+    if (q->dtype == FDTD_F64) return advance1d<double, false>(q, cur, nsteps, src, tblock, fdtd::as_stream(stream), cur_out);
     fdtd::set_error("fdtd1d_advance: unknown dtype %d", q->dtype);
     return FDTD_EINVAL;
 }

@@ -84,6 +84,7 @@ class Fdtd1D:
     """One 1D line.  ``form='fdtd'`` (``ca``/``cb``; programs 1_1-1_5) or ``'flux'`` (``nax``..``ndx``; 2_1-2_3)."""
 
     FIELDS = ("ex", "hy", "dx", "ix", "sx")
+    DFT_SAMPLE = 10              # the running DFT's source sample is ex[10] (fd1d/program/fd1d_2_2.py:70-71)
 
     def __init__(self, nx: int, dtype=np.float32, *, form: str = "fdtd", abc: bool = True, source: Optional[LineSource] = None,
                  ca=None, cb=None, nax=None, nbx=None, ncx=None, ndx=None, device=None, tblock: int = 32, freqs=None,
@@ -181,10 +182,12 @@ class Fdtd1D:
             p.src_index, p.src_hard = int(self.source.index), int(self.source.hard)
         return p
 
-    def advance(self, nsteps: int, tblock: Optional[int] = None) -> None:
+    FUSED_DFT_MAX_FREQS = 3      # frequencies the fused pass carries in registers (library limit)
+
+    def advance(self, nsteps: int, tblock: Optional[int] = None, fused_dft: bool = True) -> None:
         if nsteps <= 0:
             return
-        if self.ft is not None:
+        if self.ft is not None and (not fused_dft or len(self.freqs) > self.FUSED_DFT_MAX_FREQS):
             # the DFT samples Ex between the E update and the ABC of every step (fd1d_2_2.py:138-142): unfused steps
             for _ in range(int(nsteps)):
                 self.step()
@@ -193,6 +196,15 @@ class Fdtd1D:
         if self.source is not None:
             src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)
         p = self._problem()
+        if self.ft is not None:
+            # running DFT carried through the passes: phase factors of every step of this call, evaluated with the
+            # reference's expression (numpy programs: products in the array dtype until the np.int32 step counter)
+            ph = [_phases(self.freqs, self.dt, self.t + 1 + k, True, self.np_dtype) for k in range(int(nsteps))]
+            cos_t = np.ascontiguousarray(np.stack([c for c, _ in ph]).reshape(-1), dtype=np.float64)
+            sin_t = np.ascontiguousarray(np.stack([s for _, s in ph]).reshape(-1), dtype=np.float64)
+            D = C.POINTER(C.c_double)
+            p.nf, p.dft_sample, p.ft = len(self.freqs), self.DFT_SAMPLE, self.ft.as_struct()
+            p.dft_cos, p.dft_sin = cos_t.ctypes.data_as(D), sin_t.ctypes.data_as(D)
         out = C.c_int(-1)
         with torch.cuda.device(self.device):
             check(lib().fdtd1d_advance(C.byref(p), self._cur, int(nsteps),

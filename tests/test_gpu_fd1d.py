@@ -139,6 +139,59 @@ def test_running_dft_matches_oracle(prog, dtype):
         assert sim.get(n).tobytes() == getattr(p, n).tobytes(), n
 
 
+DFT_NAMES = ("ex", "hy", "dx", "ix", "r_pt", "i_pt", "r_in", "i_in")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("tblock", [1, 3, 8, 16, 32])
+@pytest.mark.parametrize("prog,nx", [("2_2", 397), ("2_3", 4099), ("2_2", 12), ("2_3", 1000)])
+def test_running_dft_carried_through_the_passes(prog, nx, tblock, dtype):
+    """The fused pass carries the DFT accumulators (k1_advance_dft): every pass depth, ragged and multi-warp lines,
+    advance() split at odd places -- bitwise equal to the oracle AND to the per-step fdtd1d_fourier path."""
+    ns = 230
+    p, src = cases.line_program(prog, nx, ns, dtype)
+    orc.advance_1d(p, src)
+    fused = _sim_for(prog, nx, dtype, freqs=p.freqs, tblock=tblock)
+    for part in (7, 100, 1, 122):
+        fused.advance(part)
+    assert fused.t == ns
+    for n in DFT_NAMES:
+        assert fused.get(n).tobytes() == getattr(p, n).tobytes(), n
+    if tblock == 8:
+        steps = _sim_for(prog, nx, dtype, freqs=p.freqs)
+        steps.advance(ns, fused_dft=False)
+        for n in DFT_NAMES:
+            assert fused.get(n).tobytes() == steps.get(n).tobytes(), n
+
+
+@pytest.mark.parametrize("nf", [1, 2, 4])
+def test_running_dft_other_frequency_counts(nf):
+    """nf < 3 leaves accumulator slots idle; nf > 3 exceeds the fused variant and takes the per-step path."""
+    nx, ns, dtype = 700, 160, np.float32
+    freqs = np.array((100e6, 200e6, 500e6, 900e6)[:nf], dtype=dtype)
+    p, src = cases.line_program("2_2", nx, ns, dtype)
+    p.freqs = freqs
+    p.__post_init__()
+    orc.advance_1d(p, src)
+    sim = _sim_for("2_2", nx, dtype, freqs=freqs)
+    sim.advance(ns)
+    for n in DFT_NAMES:
+        assert sim.get(n).tobytes() == getattr(p, n).tobytes(), n
+
+
+def test_running_dft_survives_checkpoint_restore():
+    nx, a_steps, b_steps, dtype = 520, 90, 75, np.float32
+    p, src = cases.line_program("2_3", nx, a_steps + b_steps, dtype)
+    orc.advance_1d(p, src)
+    one = _sim_for("2_3", nx, dtype, freqs=p.freqs)
+    one.advance(a_steps)
+    two = _sim_for("2_3", nx, dtype, freqs=p.freqs)
+    two.restore(one.checkpoint())
+    two.advance(b_steps)
+    for n in DFT_NAMES + ("sx",):
+        assert two.get(n).tobytes() == getattr(p, n).tobytes(), n
+
+
 @pytest.mark.parametrize("prog", ["2_2", "2_3"])
 def test_dft_amplitude_goldens(prog):
     """amplt[2] as the reference programs plot it: fp64 main() golden and fp32 benchmark-twin golden."""
