@@ -164,6 +164,33 @@ def test_running_dft_carried_through_the_passes(prog, nx, tblock, dtype):
             assert fused.get(n).tobytes() == steps.get(n).tobytes(), n
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("tblock", [7, 32])
+@pytest.mark.parametrize("prog", ALL)
+def test_advance_from_a_random_state(prog, tblock, dtype):
+    """Uploaded non-zero state everywhere (fields, ABC delay line, DFT accumulators): every segment boundary of every
+    warp carries signal from the first step on, which the programs' own pulses reach only after hundreds of steps."""
+    nx, ns = 3001, 75
+    p, src = cases.line_program(prog, nx, ns, dtype)
+    dft = p.freqs is not None
+    sim = _sim_for(prog, nx, dtype, tblock=tblock, **({"freqs": p.freqs} if dft else {}))
+    rng = np.random.default_rng(11)
+    names = ["ex", "hy", "bc"] + (["dx", "ix"] if p.form == "flux" else []) + (["sx"] if sim.debye else [])
+    for n in names:
+        a = getattr(p, n)
+        a[...] = rng.uniform(-1, 1, a.shape).astype(dtype)
+        sim.set(n, a)
+    if dft:
+        for n in ("r_pt", "i_pt", "r_in", "i_in"):
+            a = getattr(p, n)
+            a[...] = rng.uniform(-1, 1, a.shape).astype(dtype)
+            getattr(sim.ft, n).copy_(torch.from_numpy(a))
+    sim.advance(ns)
+    orc.advance_1d(p, src)
+    for n in names + (["r_pt", "i_pt", "r_in", "i_in"] if dft else []):
+        assert sim.get(n).tobytes() == getattr(p, n).tobytes(), n
+
+
 @pytest.mark.parametrize("nf", [1, 2, 4])
 def test_running_dft_other_frequency_counts(nf):
     """nf < 3 leaves accumulator slots idle; nf > 3 exceeds the fused variant and takes the per-step path."""
