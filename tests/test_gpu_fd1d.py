@@ -175,7 +175,7 @@ def test_advance_from_a_random_state(prog, tblock, dtype):
     dft = p.freqs is not None
     sim = _sim_for(prog, nx, dtype, tblock=tblock, **({"freqs": p.freqs} if dft else {}))
     rng = np.random.default_rng(11)
-    names = ["ex", "hy", "bc"] + (["dx", "ix"] if p.form == "flux" else []) + (["sx"] if sim.debye else [])
+    names = ["ex", "hy"] + (["bc"] if p.abc else []) + (["dx", "ix"] if p.form == "flux" else []) + (["sx"] if sim.debye else [])
     for n in names:
         a = getattr(p, n)
         a[...] = rng.uniform(-1, 1, a.shape).astype(dtype)
