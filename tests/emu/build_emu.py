@@ -23,8 +23,23 @@ int sm_count() { return 148; }
 int launch_fourier(int, int, size_t, const double *, const double *, const void *, const void *, const fdtd_ftrans *, cudaStream_t) {
     set_error("launch_fourier is not part of the emulated build"); return FDTD_EUNSUPPORTED; }
 }
-extern "C" const char *fdtd_last_error(void) { return fdtd::g_err; }
-extern "C" long long emu_launches(void) { return emu::launches; }
+extern "C" {
+const char *fdtd_last_error(void) { return fdtd::g_err; }
+long long emu_launches(void) { return emu::launches; }
+// capi_misc.cu on host memory ("device pointers" are host pointers here); no peers, no IPC
+int fdtd_version(void) { return 100; }
+int fdtd_device_info(int *sm, size_t *f, size_t *t) { if (sm) *sm = 148; if (f) *f = 0; if (t) *t = 0; return FDTD_OK; }
+int fdtd_malloc(void **p, size_t n) { *p = std::aligned_alloc(256, (n + 255) / 256 * 256); return *p ? FDTD_OK : FDTD_ECUDA; }
+int fdtd_free(void *p) { std::free(p); return FDTD_OK; }
+int fdtd_memset0(void *p, size_t n, void *) { std::memset(p, 0, n); return FDTD_OK; }
+int fdtd_upload(void *d, const void *h, size_t n, void *) { std::memcpy(d, h, n); return FDTD_OK; }
+int fdtd_download(void *h, const void *d, size_t n, void *) { std::memcpy(h, d, n); return FDTD_OK; }
+int fdtd_stream_sync(void *) { return FDTD_OK; }
+int fdtd_enable_peer_access(int) { fdtd::set_error("no peers in the emulated build"); return FDTD_EUNSUPPORTED; }
+int fdtd_ipc_export(const void *, void *) { fdtd::set_error("no IPC in the emulated build"); return FDTD_EUNSUPPORTED; }
+int fdtd_ipc_open(const void *, void **) { fdtd::set_error("no IPC in the emulated build"); return FDTD_EUNSUPPORTED; }
+int fdtd_ipc_close(void *) { return FDTD_OK; }
+}
 '''
 
 
@@ -86,26 +101,74 @@ def rewrite_launches(src: str) -> str:
         pos = a1
 
 
-def build(source_name: str) -> str:
-    """-> path of the emulated shared object for simulation_b200/csrc/<source_name>"""
-    src = open(os.path.join(CSRC, source_name)).read()
-    hdr = open(os.path.join(HERE, "cuda_runtime.h")).read() + open(os.path.join(CSRC, "common.cuh")).read()
-    tag = hashlib.sha256((src + hdr + STUBS).encode()).hexdigest()[:16]
+ASM = [  # the kernels' inline PTX, statement by statement -> its emulation (tests/emu/cuda_runtime.h, namespace emu)
+    (r'asm volatile\("cp\.async\.c[ag]\.shared\.global \[%0\], \[%1\], (\d+), %2;" ::"r"\((\w+)\), "l"\((\w+)\), "r"\((\w+)\) : "memory"\);',
+     r'emu::cp_async(\2, \3, \1, \4);'),
+    (r'asm volatile\("cp\.async\.commit_group;" ::: "memory"\);', ';'),
+    (r'asm volatile\("cp\.async\.wait_group %0;" ::"n"\(\w+\) : "memory"\);', ';'),
+    (r'asm volatile\("ld\.acquire\.sys\.global\.u64 %0, \[%1\];" : "=l"\((\w+)\) : "l"\((\w+)\) : "memory"\);', r'\1 = emu::ld_acquire(\2);'),
+    (r'asm volatile\("st\.release\.sys\.global\.u64 \[%0\], %1;" ::"l"\((\w+)\), "l"\((\w+)\) : "memory"\);', r'emu::st_release(\1, \2);'),
+]
+
+
+def rewrite_device_code(src: str) -> str:
+    import re
+    for pat, rep in ASM:
+        src = re.sub(pat, rep, src)
+    if re.search(r"\basm\b", src):
+        raise RuntimeError("inline PTX without an emulation: " + re.search(r"\basm\b.*", src).group(0)[:120])
+    # extern __shared__ T name[];  ->  the CTA's dynamic shared memory
+    src = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];",
+                 r"\1 *const \2 = reinterpret_cast<\1 *>(emu::blk->smem);", src)
+    return src
+
+
+def build(*source_names: str) -> str:
+    """-> path of the emulated shared object made of simulation_b200/csrc/<source_names>"""
+    srcs = {n: open(os.path.join(CSRC, n)).read() for n in source_names}
+    hdr = open(os.path.join(HERE, "cuda_runtime.h")).read() + open(os.path.join(CSRC, "common.cuh")).read() \
+        + open(os.path.join(ROOT, "include", "fdtd_b200.h")).read() + open(__file__).read()
+    tag = hashlib.sha256(("".join(srcs.values()) + hdr).encode()).hexdigest()[:16]
     bdir = os.path.join(HERE, "_build")
     os.makedirs(bdir, exist_ok=True)
-    so = os.path.join(bdir, f"emu_{os.path.splitext(source_name)[0]}_{tag}.so")
+    stem = "_".join(os.path.splitext(n)[0] for n in source_names)
+    so = os.path.join(bdir, f"emu_{stem}_{tag}.so")
     if os.path.exists(so):
         return so
-    cpp = os.path.join(bdir, f"emu_{os.path.splitext(source_name)[0]}.cpp")
-    with open(cpp, "w") as f:
-        f.write(f'#line 1 "{source_name}"\n' + rewrite_launches(src) + STUBS)
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-shared", "-pthread", "-w",
-           "-I", HERE, "-I", CSRC, "-x", "c++", cpp, "-o", so + ".tmp"]
-    subprocess.run(cmd, check=True)
+    stubs = STUBS if "fd2d_steps.cu" not in srcs else STUBS.replace(STUBS[STUBS.index("int launch_fourier"):STUBS.index("}\nextern")], "")
+    assert "capi_misc.cu" not in srcs, "capi_misc.cu is replaced by the stubs"
+    units = {"stubs": '#include "common.cuh"\n' + stubs}
+    for n, src in srcs.items():
+        units[os.path.splitext(n)[0]] = f'#line 1 "{n}"\n' + rewrite_launches(rewrite_device_code(src))
+    def compile_unit(item):
+        name, text = item
+        cpp = os.path.join(bdir, f"emu_{name}_{tag}.cpp")
+        with open(cpp, "w") as f:
+            f.write(text)
+        obj = os.path.join(bdir, f"emu_{name}_{tag}.o")
+        subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-pthread", "-w",
+                        "-I", HERE, "-I", CSRC, "-x", "c++", "-c", cpp, "-o", obj], check=True)
+        os.remove(cpp)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(len(units)) as pool:
+        objs = list(pool.map(compile_unit, units.items()))
+    subprocess.run(["g++", "-shared", "-pthread", *objs, "-o", so + ".tmp"], check=True)
     os.replace(so + ".tmp", so)
+    for o in objs:
+        os.remove(o)
     return so
+
+
+ALL_SOURCES = ("fd1d.cu", "fd2d_steps.cu", "fd2d_march.cu")
+
+
+def build_library() -> str:
+    """the whole library (every kernel source; capi_misc.cu replaced by host stubs) as one emulated shared object"""
+    return build(*ALL_SOURCES)
 
 
 if __name__ == "__main__":
     import sys
-    print(build(sys.argv[1] if len(sys.argv) > 1 else "fd1d.cu"))
+    print(build(*(sys.argv[1:] or ["fd1d.cu"])))

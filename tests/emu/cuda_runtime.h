@@ -1,15 +1,19 @@
 // TEST INFRASTRUCTURE ONLY -- never part of the product.  A stand-in for <cuda_runtime.h> that lets g++ compile the
-// kernels' CUDA C++ SOURCE for the host, so their index / mask / ownership logic can be checked on a machine without
-// a GPU (tests/test_emu_*.py).  A launch runs every CTA's threads as real host threads; the 32 lanes of a warp meet at
-// a barrier inside every warp shuffle, which is all the lockstep those kernels rely on.  Arithmetic is IEEE with
-// contraction off (-ffp-contract=off) and fmaf for the explicit fused forms, i.e. the rounding sequence of the GPU build.
+// kernels' CUDA C++ SOURCE for the host, so their index / mask / ownership / ordering logic can be checked on a machine
+// without a GPU (tests/test_emu_*.py).  Execution model: every thread of a CTA is a fiber (ucontext) on one host
+// thread; fibers run until they reach a barrier -- every warp shuffle, __syncwarp and __syncthreads is one -- which is
+// all the lockstep these kernels rely on.  CTAs are spread over a few host threads.  Arithmetic is IEEE with
+// contraction off (-ffp-contract=off) and fmaf for the explicit fused forms: the rounding sequence of the GPU build.
 #pragma once
+#include <ucontext.h>
+
 #include <algorithm>
-#include <barrier>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -22,10 +26,11 @@
 #define __grid_constant__
 #define __launch_bounds__(...)
 #define __restrict__
+#define __align__(n) alignas(n)
 
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
-struct double2 { double x, y; };
+struct alignas(16) double2 { double x, y; };
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
     unsigned x, y, z;
@@ -33,72 +38,203 @@ struct dim3 {
 };
 inline float2 make_float2(float a, float b) { return float2{a, b}; }
 inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+inline double2 make_double2(double a, double b) { return double2{a, b}; }
 
-typedef void *cudaStream_t;
+// ---- the slice of the runtime API the host side of the library touches (single device, everything in order)
+typedef struct EmuStream_ *cudaStream_t;
+typedef struct EmuEvent_ *cudaEvent_t;
 typedef int cudaError_t;
 constexpr cudaError_t cudaSuccess = 0;
+constexpr unsigned cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2;
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+struct cudaFuncAttributes { int numRegs; };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+template <typename F> cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename F> cudaError_t cudaFuncGetAttributes(cudaFuncAttributes *a, F) { a->numRegs = 0; return cudaSuccess; }
+template <typename T> cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)std::malloc(n); return cudaSuccess; }
+inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemset(void *p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
 
 using std::max;
 using std::min;
+using std::signbit;
 
 namespace emu {
-struct Warp {
-    std::barrier<> bar{32};
-    uint64_t slot[32];
+
+struct Barrier {
+    int expected = 0, arrived = 0;
+    unsigned gen = 0;
 };
-inline thread_local Warp *warp = nullptr;
-inline thread_local int lane = 0;
-inline long long launches = 0;     // kernels launched since load (the tests read it through emu_launches())
+struct Fiber {
+    ucontext_t ctx;
+    char *stack = nullptr;
+    bool done = false;
+    uint3 tid;
+    int lane = 0;
+    Barrier *warp = nullptr;
+    uint64_t (*slots)[2] = nullptr;   // the warp's 32 shuffle mailboxes (up to 16 bytes each)
+};
+struct Block {
+    ucontext_t sched;
+    std::vector<Fiber> fibers;
+    std::vector<Barrier> warps;
+    std::vector<uint64_t> mail;       // 32 x 2 words per warp
+    Barrier all;
+    void (*body)(void *) = nullptr;
+    void *arg = nullptr;
+    unsigned long long events = 0;    // barrier releases + fiber exits: the deadlock detector watches it move
+    alignas(128) unsigned char smem[232448];   // dynamic shared memory of the CTA (227 KB)
+    ~Block() { for (auto &f : fibers) std::free(f.stack); }
+};
+inline thread_local Block *blk = nullptr;
+inline thread_local Fiber *cur = nullptr;
+inline std::atomic<long long> launches{0};   // kernels launched since load (the tests read it through emu_launches())
+constexpr size_t STACK = 1u << 20;
+
+inline void yield() { swapcontext(&cur->ctx, &blk->sched); }
+inline void release(Barrier &b) { b.arrived = 0; ++b.gen; ++blk->events; }
+inline void wait(Barrier &b) {
+    const unsigned g = b.gen;
+    if (++b.arrived == b.expected) release(b);
+    else while (b.gen == g) yield();
+}
+inline void drop(Barrier &b) {           // a thread that exits no longer takes part
+    --b.expected;
+    if (b.expected > 0 && b.arrived == b.expected) release(b);
+}
+inline void trampoline() {
+    blk->body(blk->arg);
+    cur->done = true;
+    ++blk->events;
+    drop(*cur->warp);
+    drop(blk->all);
+}                                        // returning resumes uc_link = the scheduler
 
 template <typename T>
 T shuffle(T v, int src_lane) {
-    static_assert(sizeof(T) <= 8, "shuffle payload");
-    std::memcpy(&warp->slot[lane], &v, sizeof(T));
-    warp->bar.arrive_and_wait();
+    static_assert(sizeof(T) <= 16, "shuffle payload");
+    std::memcpy(cur->slots[cur->lane], &v, sizeof(T));
+    wait(*cur->warp);
     T r = v;
-    if (src_lane >= 0 && src_lane < 32) std::memcpy(&r, &warp->slot[src_lane], sizeof(T));
-    warp->bar.arrive_and_wait();
+    if (src_lane >= 0 && src_lane < 32) std::memcpy(&r, cur->slots[src_lane], sizeof(T));
+    wait(*cur->warp);
     return r;
 }
-}  // namespace emu
 
-inline thread_local uint3 threadIdx, blockIdx;
-inline thread_local dim3 blockDim, gridDim;
+inline thread_local uint3 block_idx;
+inline thread_local dim3 block_dim, grid_dim;
 
-template <typename T> T __shfl_up_sync(unsigned, T v, int d) { return emu::shuffle(v, emu::lane - d); }
-template <typename T> T __shfl_down_sync(unsigned, T v, int d) { return emu::shuffle(v, emu::lane + d); }
-template <typename T> T __ldg(const T *p) { return *p; }
-inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
-inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
-inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
+inline void run_block(Block &b, dim3 block, void (*body)(void *), void *arg) {
+    const unsigned nthreads = block.x * block.y * block.z, nwarps = (nthreads + 31) / 32;
+    blk = &b;
+    b.body = body;
+    b.arg = arg;
+    if (b.fibers.size() < nthreads) {
+        const size_t old = b.fibers.size();
+        b.fibers.resize(nthreads);
+        for (size_t t = old; t < nthreads; ++t) b.fibers[t].stack = (char *)std::malloc(STACK);
+    }
+    b.warps.assign(nwarps, Barrier{});
+    b.mail.assign((size_t)nwarps * 64, 0);
+    b.all = Barrier{};
+    b.all.expected = (int)nthreads;
+    for (unsigned t = 0; t < nthreads; ++t) {
+        Fiber &f = b.fibers[t];
+        f.done = false;
+        f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+        f.lane = (int)(t % 32);
+        f.warp = &b.warps[t / 32];
+        f.warp->expected++;
+        f.slots = reinterpret_cast<uint64_t(*)[2]>(b.mail.data() + (size_t)(t / 32) * 64);
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = STACK;
+        f.ctx.uc_link = &b.sched;
+        makecontext(&f.ctx, trampoline, 0);
+    }
+    unsigned live = nthreads;
+    while (live) {
+        const unsigned long long before = b.events;
+        live = 0;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            Fiber &f = b.fibers[t];
+            if (f.done) continue;
+            cur = &f;
+            swapcontext(&b.sched, &f.ctx);
+            if (!f.done) ++live;
+        }
+        if (live && b.events == before) {
+            std::fprintf(stderr, "emu: deadlock -- %u threads of a CTA wait at barriers the others never reach\n", live);
+            std::abort();
+        }
+    }
+    cur = nullptr;
+}
 
-namespace emu {
 // kernel<<<grid, block, smem, stream>>>(args) is rewritten (tests/emu/build_emu.py) into launch(grid, block, [&]{ kernel(args); })
 template <typename F>
 void launch(dim3 grid, dim3 block, F body) {
     ++launches;
-    const unsigned nthreads = block.x * block.y * block.z;
-    const unsigned nwarps = (nthreads + 31) / 32;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                std::vector<std::unique_ptr<Warp>> warps;
-                for (unsigned w = 0; w < nwarps; ++w) warps.emplace_back(new Warp);
-                std::vector<std::thread> threads;
-                threads.reserve(nthreads);
-                for (unsigned t = 0; t < nthreads; ++t)
-                    threads.emplace_back([&, t] {
-                        threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-                        blockIdx = uint3{bx, by, bz};
-                        blockDim = block;
-                        gridDim = grid;
-                        warp = warps[t / 32].get();
-                        lane = (int)(t % 32);
-                        body();
-                    });
-                for (auto &th : threads) th.join();
-            }
+    const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+    if (nblocks == 0 || block.x * block.y * block.z == 0) return;
+    std::atomic<unsigned long long> next{0};
+    auto worker = [&] {
+        std::unique_ptr<Block> b(new Block);           // fiber stacks are reused by all the CTAs this host thread runs
+        for (;;) {
+            const unsigned long long id = next.fetch_add(1);
+            if (id >= nblocks) break;
+            block_idx = uint3{(unsigned)(id % grid.x), (unsigned)((id / grid.x) % grid.y), (unsigned)(id / ((unsigned long long)grid.x * grid.y))};
+            block_dim = block;
+            grid_dim = grid;
+            run_block(*b, block, [](void *p) { (*static_cast<F *>(p))(); }, &body);
+        }
+    };
+    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const unsigned nthr = (unsigned)std::min<unsigned long long>(hw, nblocks);
+    if (nthr <= 1) { worker(); return; }
+    std::vector<std::thread> pool;
+    for (unsigned k = 0; k < nthr; ++k) pool.emplace_back(worker);
+    for (auto &t : pool) t.join();
 }
+}  // namespace emu
+
+#define threadIdx (emu::cur->tid)
+#define blockIdx (emu::block_idx)
+#define blockDim (emu::block_dim)
+#define gridDim (emu::grid_dim)
+
+template <typename T> T __shfl_up_sync(unsigned, T v, int d) { return emu::shuffle(v, emu::cur->lane - d); }
+template <typename T> T __shfl_down_sync(unsigned, T v, int d) { return emu::shuffle(v, emu::cur->lane + d); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::wait(*emu::cur->warp); }
+inline void __syncthreads() { emu::wait(emu::blk->all); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+template <typename T> T __ldg(const T *p) { return *p; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicExch(unsigned long long *p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+// shared-window address of a pointer into the CTA's dynamic shared memory (what cp.async takes as its destination)
+inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)((const unsigned char *)p - emu::blk->smem); }
+
+namespace emu {
+// what the inline PTX of the kernels does, statement by statement (tests/emu/build_emu.py maps each asm to one of these)
+inline void cp_async(unsigned dst, const void *src, int bytes, int src_bytes) {
+    unsigned char *d = blk->smem + dst;
+    std::memset(d, 0, bytes);
+    if (src_bytes > 0) std::memcpy(d, src, std::min(bytes, src_bytes));
+}
+inline unsigned long long ld_acquire(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 }  // namespace emu

@@ -1,0 +1,178 @@
+"""CPU check of the fused 2D kernels' OWN SOURCE and of the product's HOST code together: the whole library
+(simulation_b200/csrc/fd1d.cu, fd2d_steps.cu, fd2d_march.cu) compiled for the host against the fiber-based CTA
+emulator of tests/emu/, and simulation_b200.fd2d.Fdtd2D pointed at it with CPU tensors as device memory
+(tests/emu/device.py).  Bit-for-bit against the numpy oracle: strips / chunks / halos of the march kernel, the
+interior-vs-careful split and the special-strip lists, PML / TFSF / source cells, the incident-line history, the
+running DFT carried with the rows, row slabs with ghost rows, lazy Ez, checkpoint / restore.
+
+Test infrastructure only -- the product path is the sm_100a build and has no CPU fallback; tests/test_gpu_fd2d.py
+runs these and many more cases on the device.  What the emulator cannot see: timing, memory-ordering races between
+warps (every cp.async completes at once, CTAs of one launch interleave only at barriers)."""
+import numpy as np
+import pytest
+
+from oracle import fdtd_oracle as orc
+from tests import cases
+from tests.emu import device
+from tests.test_gpu_fd2d import _assert_same, _sim_for
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    return device.install(monkeypatch)
+
+
+def _run(emu, prog, nx, ny, npml, ns, dtype, tblock=None, radius=0.12, tune=(0, 0, 0, 0, 0), parts=None):
+    before = emu.emu_launches()
+    emu.fdtd2d_tune(*tune)
+    try:
+        sim = _sim_for(prog, nx, ny, dtype, npml=npml, radius=radius, device="cpu")
+        for part in (parts or (ns,)):
+            sim.advance(part, tblock=tblock)
+    finally:
+        emu.fdtd2d_tune(0, 0, 0, 0, 0)
+    assert sim.t == ns and emu.emu_launches() > before
+    g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=radius, dft=False)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, prog)
+    return sim
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("tblock", [1, 3, 4, 6, 8])
+@pytest.mark.parametrize("prog,nx,ny,npml,ns", [("3_2", 56, 72, 8, 41), ("3_3", 64, 48, 7, 45), ("3_4", 60, 72, 8, 37),
+                                                ("3_1", 40, 56, 0, 30)])
+def test_emulated_advance_matches_oracle(emu, prog, nx, ny, npml, ns, tblock, dtype):
+    _run(emu, prog, nx, ny, npml, ns, dtype, tblock)
+
+
+@pytest.mark.parametrize("force_v,chunk_rows,tblock", [(4, 0, 6), (2, 16, 6), (1, 5, 4), (4, 40, 8), (2, 0, 3)])
+@pytest.mark.parametrize("prog,nx,ny,npml", [("3_2", 420, 1100, 8), ("3_3", 400, 1000, 12), ("3_4", 380, 1040, 10)])
+def test_emulated_interior_and_careful_kernels(emu, prog, nx, ny, npml, force_v, chunk_rows, tblock):
+    """Grids with a true interior: the mask-free identity-coefficient kernel (packed arithmetic at fp32) and the
+    careful kernel share every pass; every vector width, several row partitions, ragged last strips and chunks."""
+    _run(emu, prog, nx, ny, npml, 2 * tblock + 1, np.float32, tblock, radius=0.3, tune=(force_v, chunk_rows, 0, 0, 0))
+
+
+def test_emulated_interior_kernel_equals_careful_kernel(emu):
+    nx, ny, npml, ns = 330, 900, 10, 19
+    a = _run(emu, "3_3", nx, ny, npml, ns, np.float32)
+    b = _run(emu, "3_3", nx, ny, npml, ns, np.float32, tune=(0, 0, 0, 0, 1))      # every warp through the careful kernel
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert a.get(name).tobytes() == b.get(name).tobytes(), name
+
+
+@pytest.mark.parametrize("ny", [61, 62, 63, 130])
+def test_emulated_odd_widths(emu, ny):
+    _run(emu, "3_3", 50, ny, 6, 29, np.float32)
+
+
+def test_emulated_split_calls_mixed_with_reference_named_steps(emu):
+    nx, ny, npml = 70, 90, 8
+    sim = _sim_for("3_3", nx, ny, np.float64, npml=npml, device="cpu")
+    sim.advance(23)
+    sim.step()                       # ezinct, dfield, inctdz, efield, hxinct, hfield, incthx, incthy: one kernel each
+    sim.advance(30, tblock=3)
+    g, src = cases.grid_program("3_3", nx, ny, 54, np.float64, npml=npml)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, "3_3")
+
+
+def test_emulated_random_state_and_medium(emu):
+    rng = np.random.default_rng(7)
+    nx, ny, npml, ns = 66, 140, 8, 21
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    sim = _sim_for("3_2", nx, ny, np.float32, npml=npml, naz=naz, device="cpu")
+    g, src = cases.grid_program("3_2", nx, ny, ns, np.float32, npml=npml, naz=naz.copy())
+    for name in ("dz", "hx", "hy", "ihx", "ihy"):
+        a = rng.standard_normal((nx, ny)).astype(np.float32)
+        sim.set(name, a)
+        getattr(g, name)[...] = a
+    sim.advance(ns)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, "3_2")
+
+
+@pytest.mark.parametrize("prog", ["3_1", "3_2", "3_3"])
+def test_emulated_advance_matches_reference_goldens(emu, prog):
+    ref = cases.golden(f"drive_{prog}_f32")
+    nx, ny, ns = int(ref["nx"]), int(ref["ny"]), int(ref["ns"])
+    sim = _sim_for(prog, nx, ny, np.float32, npml=int(ref["npml"]) if "npml" in ref else 0, device="cpu")
+    sim.advance(ns)
+    for name in ("dz", "ez", "hx", "hy"):
+        if prog == "3_1":
+            assert np.array_equal(sim.get(name), ref[name]), name
+        else:
+            assert sim.get(name).tobytes() == ref[name].tobytes(), name
+
+
+@pytest.mark.parametrize("tblock", [1, 4, None])
+@pytest.mark.parametrize("nx,ny,npml", [(60, 72, 8), (300, 420, 10)])
+def test_emulated_running_dft_carried_with_the_rows(emu, nx, ny, npml, tblock):
+    from simulation_b200 import fd2d, surface
+    ns = 27
+    g, src = cases.grid_program("3_4", nx, ny, ns, np.float32, npml=npml, radius=0.2, dft=True)
+    sim = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)),
+                      naz=g.naz.copy(), nbz=g.nbz.copy(), freqs=g.freqs, device="cpu")
+    sim.advance(10, tblock=tblock)
+    sim.advance(ns - 10, tblock=tblock)
+    orc.advance_2d(g, src)
+    for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy", "r_pt", "i_pt", "r_in", "i_in"):
+        got, want = sim.get(name), getattr(g, name)
+        assert got.tobytes() == want.tobytes(), (name, np.argwhere(got != want)[:4].tolist())
+
+
+@pytest.mark.parametrize("prog,nslab", [("3_3", 3), ("3_2", 2)])
+def test_emulated_row_slabs_with_ghost_rows(emu, prog, nslab):
+    """One Fdtd2D per row slab, T ghost rows per side, ghost rows refreshed from the neighbours between blocks (what
+    slab.py does over NVLink): owned rows bit-identical to the monolithic oracle."""
+    nx, ny, npml, T, nblocks, dtype = 96, 80, 8, 4, 5, np.float32
+    cuts = np.linspace(0, nx, nslab + 1).astype(int)
+    slabs = [_sim_for(prog, nx, ny, dtype, npml=npml, rows=(int(lo), int(hi)), ghost=T, tblock=T, device="cpu")
+             for lo, hi in zip(cuts[:-1], cuts[1:])]
+    names = ("dz", "hx", "hy", "ihx", "ihy")
+    for _ in range(nblocks):
+        for s in slabs:
+            s.advance(T, lazy_ez=True)
+        whole = {n: np.concatenate([s.get(n) for s in slabs]) for n in names}
+        for s in slabs:
+            for n in names:
+                s.set(n, whole[n])                   # whole-grid array: fills owned AND ghost rows
+    for s in slabs:
+        s.advance(1)                                 # a last non-lazy step stores Ez
+    ns = nblocks * T + 1
+    g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml)
+    orc.advance_2d(g, src)
+    for n in names + ("ez",):
+        got = np.concatenate([s.get(n) for s in slabs])
+        assert got.tobytes() == getattr(g, n).tobytes(), n
+
+
+def test_emulated_checkpoint_restore(emu):
+    nx, ny, npml = 72, 100, 8
+    one = _sim_for("3_4", nx, ny, np.float32, npml=npml, device="cpu")
+    one.advance(17)
+    two = _sim_for("3_4", nx, ny, np.float32, npml=npml, device="cpu")
+    two.restore(one.checkpoint())
+    two.advance(20)
+    g, src = cases.grid_program("3_4", nx, ny, 37, np.float32, npml=npml, dft=False)
+    orc.advance_2d(g, src)
+    _assert_same(two, g, "3_4")
+
+
+def test_emulated_identity_promise_is_checked(emu):
+    sim = _sim_for("3_2", 128, 160, np.float32, npml=8, device="cpu")
+    assert sim.check_identity() == 0
+    sim.pml.gy2[40] = 0.5
+    assert sim.check_identity() == 1
+
+
+def test_emulated_device_cylinder_rasteriser(emu):
+    """fdtd2d_dielectric_cylinder (k_cylinder) against the host evaluation of the reference's Python statements."""
+    from simulation_b200 import fd2d, surface
+    nx, ny, npml, rgrid = 90, 120, 8, 17
+    md = fd2d.dielectric(nx, ny, npml, rgrid, surface.DT, 30.0, 0.30, np.float32, device="cpu")
+    naz, nbz = surface.dielectric_cylinder(nx, ny, npml, rgrid, surface.DT, 30.0, 0.30, np.float32)
+    assert md.naz.numpy().tobytes() == naz.tobytes() and md.nbz.numpy().tobytes() == nbz.tobytes()
