@@ -242,7 +242,7 @@ def run_ours(args, emit=print):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        nn, ss = 4096, 10
+        nn, ss = 4096, 40                                   # ~13 s of single-core numpy: a bounded sample of the workload
         v, dt = cpu_numpy_port(nn, ss)
         cpu = {"value": v, "unit": "Mcell-updates/s", "cores": 1, "kind": "port",
                "sample": f"{nn}x{nn} fp32 npml={NPML}, {ss} steps after 1 warm-up ({dt:.1f} s); numpy oracle == "

@@ -798,10 +798,13 @@ int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStre
     int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : (items >= 32 * fdtd::sm_count() ? 8 : (items >= 8 * fdtd::sm_count() ? 4 : 2));
     while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) --warps;
     const size_t smem = (size_t)warps * per_warp;
-    static size_t configured = 0;                       // per instantiation: largest dynamic smem opted in so far
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[64] = {0};                 // per instantiation and device: largest dynamic smem opted in so far
+    int dev = 0;
+    FDTD_CUDA(cudaGetDevice(&dev));
+    size_t &opted = configured[dev >= 0 && dev < 64 ? dev : 0];
+    if (smem > 48 * 1024 && (smem > opted || dev >= 64)) {
         FDTD_CUDA(cudaFuncSetAttribute(k_march<real, V, T, MODE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        opted = smem;
     }
     const int grid = (items + warps - 1) / warps;
     k_march<real, V, T, MODE, FAST><<<grid, warps * 32, smem, st>>>(mp, all_careful);

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import check, lib
-from .fd2d import _NP_DT, _TORCH_DT, _code, _phases, _ptr, _require_cuda, _stream, ftrans
+from .fd2d import _NP_DT, _TORCH_DT, _code, _phase_tables, _phases, _ptr, _require_cuda, _stream, ftrans
 
 
 class medium(NamedTuple):
@@ -199,9 +199,7 @@ class Fdtd1D:
         if self.ft is not None:
             # running DFT carried through the passes: phase factors of every step of this call, evaluated with the
             # reference's expression (numpy programs: products in the array dtype until the np.int32 step counter)
-            ph = [_phases(self.freqs, self.dt, self.t + 1 + k, True, self.np_dtype) for k in range(int(nsteps))]
-            cos_t = np.ascontiguousarray(np.stack([c for c, _ in ph]).reshape(-1), dtype=np.float64)
-            sin_t = np.ascontiguousarray(np.stack([s for _, s in ph]).reshape(-1), dtype=np.float64)
+            cos_t, sin_t = _phase_tables(self.freqs, self.dt, self.t + 1, nsteps, True, self.np_dtype)
             D = C.POINTER(C.c_double)
             p.nf, p.dft_sample, p.ft = len(self.freqs), self.DFT_SAMPLE, self.ft.as_struct()
             p.dft_cos, p.dft_sin = cos_t.ctypes.data_as(D), sin_t.ctypes.data_as(D)

@@ -99,6 +99,29 @@ def _phases(freq, dt, t, numpy_style, np_dtype):
     return np.cos(arg), np.sin(arg)
 
 
+def _phase_tables(freq, dt, t_first, n, numpy_style, np_dtype):
+    """``_phases`` of steps ``t_first .. t_first+n-1`` as two contiguous float64 tables [step][frequency].  Evaluated
+    in one vectorised expression and probed against the per-step evaluation (numpy's array and scalar cos / sin are
+    not guaranteed to round alike); any difference falls back to the per-step loop."""
+    n = int(n)
+    t = np.arange(t_first, t_first + n).astype(np.int32).reshape(n, 1)
+    if numpy_style:
+        arg = 2 * np.pi * np.asarray(freq, dtype=np_dtype).reshape(1, -1) * dt * t
+        cos_t, sin_t = np.cos(arg).astype(np.float64), np.sin(arg).astype(np.float64)
+    else:
+        arg = 2 * np.pi * np.asarray(freq, dtype=np_dtype).astype(np.float64).reshape(1, -1) * dt * t
+        cos_t, sin_t = np.cos(arg), np.sin(arg)
+    probe = sorted(set(range(min(n, 8))) | set(range(max(n - 8, 0), n)) | set(range(0, n, max(1, n // 16))))
+    for k in probe:
+        c, s = _phases(freq, dt, t_first + k, numpy_style, np_dtype)
+        if c.tobytes() != cos_t[k].tobytes() or s.tobytes() != sin_t[k].tobytes():
+            ph = [_phases(freq, dt, t_first + j, numpy_style, np_dtype) for j in range(n)]
+            cos_t, sin_t = np.stack([c for c, _ in ph]), np.stack([s for _, s in ph])
+            break
+    return (np.ascontiguousarray(cos_t.reshape(-1), dtype=np.float64),
+            np.ascontiguousarray(sin_t.reshape(-1), dtype=np.float64))
+
+
 def fourier(t: int, nf: int, nx: int, ny: int, dt: float, freq, ezi, ez, ft: ftrans) -> None:
     """Running DFT of Ez and of the source sample ``ezi[6]`` (reference argument order)."""
     _require_cuda(ez, ezi, *ft)
@@ -413,9 +436,7 @@ class Fdtd2D:
         if self.ft is not None:
             # running DFT fused into the passes: per-step phase factors, evaluated as the reference evaluates them
             nf = len(self.freqs)
-            ph = [_phases(self.freqs, self.dt, self.t + 1 + k, False, self.np_dtype) for k in range(int(nsteps))]
-            cos_t = np.ascontiguousarray(np.stack([c for c, _ in ph]).reshape(-1), dtype=np.float64)
-            sin_t = np.ascontiguousarray(np.stack([s for _, s in ph]).reshape(-1), dtype=np.float64)
+            cos_t, sin_t = _phase_tables(self.freqs, self.dt, self.t + 1, nsteps, False, self.np_dtype)
             D = C.POINTER(C.c_double)
             p.nf, p.ft = nf, self.ft.as_struct()
             if not self.tfsf:

@@ -10,6 +10,6 @@ for p in ref_cuda_test_3_2 ref_cuda_test_3_3 ref_cuda_test_3_2_8192; do
   [ -x $exe ] || { echo "$p: not built"; continue; }
   echo "== $p"
   t0=$(date +%s%N)
-  timeout 120 $exe 2>&1 | awk 'NR<=4 || /rror/ {print} NR==5 {print "..."}'
+  timeout 45 $exe 2>&1 | awk 'NR<=4 || /rror/ {print} NR==5 {print "..."}'
   echo "exit status: ${PIPESTATUS[0]}, wall $(( ($(date +%s%N) - t0) / 1000000 )) ms"
 done
