@@ -499,7 +499,16 @@ class Fdtd2D:
         lo_all, hi_all = self.row_base, self.row_base + self.rows_alloc           # global rows stored here
         if blocks is None and block_rows is None:
             block_rows = 1024 if self.rows_alloc >= 8192 else max(4 * max(depths), -(-self.rows_alloc // 8))
-        if block_rows:                                   # explicit block height (the last block takes the remainder)
+        if isinstance(block_rows, (list, tuple)):        # explicit block heights, top to bottom (the last one is stretched
+            edges, least = [lo_all], 4 * max(depths)     # or cut to end at the last stored row)
+            for h in block_rows:
+                if hi_all - edges[-1] < 2 * least:
+                    break
+                edges.append(min(edges[-1] + max(int(h), least), hi_all - least))
+            edges[-1] = hi_all
+            if len(edges) == 1:
+                edges.append(hi_all)
+        elif block_rows:                                 # one block height (the last block takes the remainder)
             edges = list(range(lo_all, hi_all, max(int(block_rows), 4 * max(depths)))) + [hi_all]
         else:
             B = max(1, min(int(blocks), self.rows_alloc // max(4 * max(depths), 1)))

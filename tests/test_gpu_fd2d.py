@@ -392,6 +392,27 @@ def test_streamed_run_equals_plain_run(blocks, streams):
     assert b.t == ns and float(host_ez.abs().max()) > 1e-3
 
 
+@pytest.mark.parametrize("plan", [[64, 128, 256, 512, 256, 128, 64], [100, 1000], [700], [24, 30, 24] * 30])
+def test_streamed_run_with_ragged_block_plans(plan):
+    """run_streamed with explicit block heights (short blocks first and last, tall ones in between; plans shorter or
+    longer than the grid; heights below the halo limit are raised) == plain advance, bit for bit."""
+    from simulation_b200 import fd2d, surface
+    rng = np.random.default_rng(6)
+    nx, ny, npml, ns = 1500, 640, 16, 40
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    src = fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6))
+    a = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, naz=naz)
+    a.advance(ns)
+    b = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src)
+    host_naz = torch.from_numpy(naz).pin_memory()
+    host_ez = torch.empty((nx, ny), dtype=torch.float32).pin_memory()
+    b.run_streamed(ns, host_naz, host_ez, block_rows=plan, streams=5)
+    b.synchronize()
+    assert torch.equal(host_ez, a.tensor("ez").cpu())
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+
+
 @pytest.mark.parametrize("rows,ghost,ns", [((300, 700), 48, 48), ((0, 500), 30, 24), ((900, 1500), 36, 36)])
 def test_streamed_run_on_a_slab_consumes_its_ghost_band(rows, ghost, ns):
     """Communication-avoiding streamed run: a slab with g ghost rows takes <= g steps with no exchange (rows beyond

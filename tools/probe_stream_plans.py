@@ -1,0 +1,58 @@
+"""Sweep of row-block plans for Fdtd2D.run_streamed on the BASELINE config-5 grid (32768^2 fp32, K steps): uniform block
+heights against ramped plans (small blocks first so stepping starts early, tall blocks in the middle for efficient
+launches, small blocks last so the download tail is short).   python tools/probe_stream_plans.py [K]"""
+import os
+import sys
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from simulation_b200 import fd2d, surface  # noqa: E402
+
+n = 32768
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+src = fd2d.PointSource(n // 2 - 5, n // 2 - 5, surface.Sinusoid(1500e6), hard=True)
+sim = fd2d.Fdtd2D(n, n, 80, np.float32, source=src, tblock=6)
+host_naz = torch.ones((n, n), dtype=torch.float32).pin_memory()
+host_ez = torch.empty((n, n), dtype=torch.float32).pin_memory()
+
+
+def ramp(head, body, tail):
+    left = n - sum(head) - sum(tail)
+    nb = max(1, round(left / body))
+    return list(head) + [left // nb] * nb + list(tail)
+
+
+plans = {
+    "uniform 1024": 1024,
+    "uniform 2048": 2048,
+    "ramp 512,1024,2048 | 4096 | 2048,1024,512": ramp((512, 1024, 2048), 4096, (2048, 1024, 512)),
+    "ramp 512,1024 | 2048 | 1024,512": ramp((512, 1024), 2048, (1024, 512)),
+    "ramp 512,1024,2048 | 3072 | 2048,1024,512": ramp((512, 1024, 2048), 3072, (2048, 1024, 512)),
+    "ramp 256,512,1024,2048 | 4096 | 2048,1024,512,256": ramp((256, 512, 1024, 2048), 4096, (2048, 1024, 512, 256)),
+    "ramp 1024,2048 | 4096 | 2048,1024": ramp((1024, 2048), 4096, (2048, 1024)),
+    "ramp 512,1024,2048 | 6144 | 2048,1024,512": ramp((512, 1024, 2048), 6144, (2048, 1024, 512)),
+    "ramp 512,1024,2048 | 4096 | 1024": ramp((512, 1024, 2048), 4096, (1024,)),
+}
+ref = None
+for name, plan in plans.items():
+    best = None
+    for rep in range(3):
+        for f in ("dz", "hx", "hy", "ihx", "ihy", "ez"):
+            sim.tensor(f, stored=True).zero_()
+        sim.t = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        sim.run_streamed(K, host_naz, host_ez, block_rows=plan)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None or (rep > 0 and ms < best) else best
+    if ref is None:
+        ref = host_ez.clone()
+    same = torch.equal(ref, host_ez)
+    nblk = len(plan) if isinstance(plan, list) else -(-n // plan)
+    print(f"{name:52s} blocks {nblk:3d}: {best:7.1f} ms  {n * n * K / best / 1e6:6.1f} Gcell/s  ez == uniform-1024 ez: {same}", flush=True)
