@@ -464,29 +464,35 @@ class Fdtd2D:
         return out
 
     def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, blocks: Optional[int] = None,
-                     tblock=None, streams: int = 16, trace: Optional[list] = None, block_rows: Optional[int] = None) -> None:
+                     tblock=None, streams: int = 16, trace: Optional[list] = None, block_rows=None,
+                     schedule: str = "skewed") -> None:
         """The whole job a reference ``main()`` does -- medium from the host, ``nsteps`` steps from zero fields,
         Ez back on the host -- with the PCIe transfers hidden behind the kernels.
 
-        The grid is cut into row blocks (``block_rows`` rows each, default 1024 on big grids: a whole number of
-        interior waves per launch, and enough skew between the first and the last block to cover both transfers; or
-        ``blocks`` equal blocks) and the passes are issued as a wavefront: while block b of the medium is still
-        uploading, pass 1 runs on block b-1, pass 2 on block b-2, ...  Pass p on block b needs pass p-1 on blocks
-        b-1, b, b+1 (it reads their rows and overwrites the set they read).  Each pass level runs its blocks in order
-        on its own stream (``p % streams``) and waits for the event of (b+1, p-1), which -- same stream, later block --
-        implies the other two: the pass levels form a systolic pipeline whose launches overlap, so the ramp and tail
-        of every small launch (0.1 ms of a 0.35 ms launch when one stream drains between them) is filled by its
-        neighbours (measured at 32768^2 x 96 steps: 195 -> 176 ms).  The last pass of each block is
-        followed by the download of that block's Ez.  Same kernels, same arithmetic, same result as
-        ``set naz; advance(nsteps); get ez``.  ``naz_host``: pinned CPU tensor over the stored rows, ``ez_host`` over the
-        owned rows (both (nx, ny) on a single device).  Point source or no source only (the TFSF incident line is
-        advanced once per whole-grid pass).
+        The grid is cut into row blocks (``block_rows``: one height or a list of heights top to bottom; or ``blocks``
+        equal blocks) that are uploaded in order; every pass (``depth`` time steps) is issued block by block, each pass
+        level on its own stream, so the levels form a systolic pipeline whose small launches overlap.
+
+        ``schedule="skewed"`` (default): pass level p works on the block boundaries shifted UP by (p+1)*depth rows
+        (parallelogram tiling in space-time).  Level p of block b then reads level p-1 only over rows that level p-1
+        produced for blocks b and b-1 -- never for b+1 -- so a block runs through ALL its passes as soon as it has
+        arrived, whatever its height; the last block grows by the shift and the first shrinks.  The ping-pong sets stay
+        safe: what level p of block b overwrites was read by level p-1 of blocks <= b only (its dependencies).
+        ``schedule="wavefront"``: unshifted blocks; level p of block b must wait for level p-1 of block b+1, i.e. for
+        the upload of block b+p+1 -- tall blocks starve the early passes (kept for comparison and for runs whose total
+        shift would not fit the first block).
+
+        Same kernels, same arithmetic, same result as ``set naz; advance(nsteps); get ez``.  ``naz_host``: pinned CPU
+        tensor over the stored rows, ``ez_host`` over the owned rows (both (nx, ny) on a single device).  Point source
+        or no source only (the TFSF incident line is advanced once per whole-grid pass).
 
         On a slab (``rows=``, ``ghost=g``) the run is communication-avoiding: at most g steps, during which the
         ghost band is consumed one row per step instead of being exchanged (``FDTD_GHOST_DECAY``) -- the owned rows come
         out exact, the ghost rows must be refreshed before stepping on (``SlabFdtd2D.run_streamed`` does)."""
         if self.tfsf or self.ft is not None:
             raise _lib.FdtdError("run_streamed: point source (or none) and no running DFT")
+        if schedule not in ("skewed", "wavefront"):
+            raise ValueError(schedule)
         slab = self.rows_alloc != self.nx
         rows_own = self.row_hi - self.row_lo
         if slab and int(nsteps) > self.ghost:
@@ -496,11 +502,16 @@ class Fdtd2D:
         depths = self._depths(nsteps, tblock)
         P = len(depths)
         S = max(1, min(int(streams), P))
+        dmax = max(depths)
+        least = 4 * dmax                                                           # shortest block a pass may be given
         lo_all, hi_all = self.row_base, self.row_base + self.rows_alloc           # global rows stored here
+        skew = P * dmax if schedule == "skewed" else 0                             # shift of the last pass level
+        if skew and skew + least > self.rows_alloc // 2:
+            schedule, skew = "wavefront", 0                                        # a long run on a short grid
         if blocks is None and block_rows is None:
-            block_rows = 1024 if self.rows_alloc >= 8192 else max(4 * max(depths), -(-self.rows_alloc // 8))
+            block_rows = self._default_block_rows(schedule, least)
         if isinstance(block_rows, (list, tuple)):        # explicit block heights, top to bottom (the last one is stretched
-            edges, least = [lo_all], 4 * max(depths)     # or cut to end at the last stored row)
+            edges = [lo_all]                             # or cut to end at the last stored row)
             for h in block_rows:
                 if hi_all - edges[-1] < 2 * least:
                     break
@@ -509,16 +520,32 @@ class Fdtd2D:
             if len(edges) == 1:
                 edges.append(hi_all)
         elif block_rows:                                 # one block height (the last block takes the remainder)
-            edges = list(range(lo_all, hi_all, max(int(block_rows), 4 * max(depths)))) + [hi_all]
+            edges = list(range(lo_all, hi_all, max(int(block_rows), least))) + [hi_all]
         else:
-            B = max(1, min(int(blocks), self.rows_alloc // max(4 * max(depths), 1)))
+            B = max(1, min(int(blocks), self.rows_alloc // max(least, 1)))
             edges = [lo_all + self.rows_alloc * k // B for k in range(B + 1)]
+        if skew:
+            # the first block must keep `least` rows after the deepest shift: merge leading blocks until it does
+            while len(edges) > 2 and edges[1] - lo_all < skew + least:
+                del edges[1]
+            if edges[1] - lo_all < skew + least:
+                schedule, skew = "wavefront", 0
         B = len(edges) - 1
+
+        def rows_of(b, p):
+            """global rows pass level p produces for block b"""
+            sh = (p + 1) * dmax if skew else 0
+            return (lo_all if b == 0 else edges[b] - sh), (hi_all if b == B - 1 else edges[b + 1] - sh)
+
         src = None
         if self.source is not None:
             src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)
         first_step = np.concatenate(([0], np.cumsum(depths)))          # step offset of every pass
         D = C.POINTER(C.c_double)
+        if skew:                                          # block by block, every level of a block in a row
+            order = [(b, p_idx) for b in range(B) for p_idx in range(P)]
+        else:                                             # by wave, increasing p inside
+            order = [(w - p_idx, p_idx) for w in range(B + P - 1) for p_idx in range(P) if 0 <= w - p_idx < B]
         with torch.cuda.device(self.device):
             caller = torch.cuda.current_stream()
             if getattr(self, "_lanes", None) is None or len(self._lanes) < S + 2:
@@ -536,47 +563,53 @@ class Fdtd2D:
                     uploaded.append(ev)
             cur0 = self._cur
             done = {}                                                      # (b, p) -> event
-            for w in range(B + P - 1):
-                for p_idx in range(P):                                     # issue order: by wave, increasing p inside
-                    b = w - p_idx
-                    if not (0 <= b < B):
-                        continue
-                    lane = lanes[p_idx % S]
-                    if p_idx == 0:
-                        lane.wait_event(uploaded[min(b + 1, B - 1)])       # the pass reads naz up to depth rows below
-                    else:
-                        lane.wait_event(done[(min(b + 1, B - 1), p_idx - 1)])
-                    prob = self._problem()
-                    prob.row_lo, prob.row_hi = edges[b], edges[b + 1]
-                    if p_idx < P - 1:
-                        prob.flags |= _lib.LAZY_EZ
-                    if slab:
-                        prob.flags |= _lib.GHOST_DECAY          # the ghost band is consumed instead of exchanged
-                    out = C.c_int(-1)
-                    k0 = int(first_step[p_idx])
-                    if trace is not None:                                  # timeline probe (tools/probe_streamed.py)
-                        t0 = torch.cuda.Event(enable_timing=True)
-                        t0.record(lane)
-                    check(lib().fdtd2d_advance(C.byref(prob), (cur0 + p_idx) % 2, depths[p_idx],
-                                               None if src is None else src[k0:].ctypes.data_as(D),
-                                               depths[p_idx], C.c_void_p(lane.cuda_stream), C.byref(out)),
-                          "fdtd2d_advance (streamed)")
-                    ev = torch.cuda.Event(enable_timing=trace is not None)
-                    ev.record(lane)
-                    done[(b, p_idx)] = ev
-                    if trace is not None:
-                        trace.append((b, p_idx, t0, ev))
-                    if p_idx == P - 1:
-                        down.wait_event(ev)
-                        a, z = max(edges[b], self.row_lo), min(edges[b + 1], self.row_hi)     # owned rows of this block
-                        if z > a:
-                            with torch.cuda.stream(down):
-                                ez_dev = self._sets[(cur0 + P) % 2]["ez"]
-                                ez_host[a - self.row_lo:z - self.row_lo].copy_(ez_dev[a - lo_all:z - lo_all], non_blocking=True)
+            for b, p_idx in order:
+                lane = lanes[p_idx % S]
+                if skew:
+                    # needs level p-1 of blocks b and b-1: the event of (b, p-1) implies (b-1, p-1), same stream, earlier
+                    # block.  Level 0 reads naz up to the end of block b, and nothing of block b+1.
+                    lane.wait_event(uploaded[b] if p_idx == 0 else done[(b, p_idx - 1)])
+                elif p_idx == 0:
+                    lane.wait_event(uploaded[min(b + 1, B - 1)])           # the pass reads naz up to depth rows below
+                else:
+                    lane.wait_event(done[(min(b + 1, B - 1), p_idx - 1)])  # (b+1, p-1) implies (b, p-1) and (b-1, p-1)
+                prob = self._problem()
+                prob.row_lo, prob.row_hi = rows_of(b, p_idx)
+                if p_idx < P - 1:
+                    prob.flags |= _lib.LAZY_EZ
+                if slab:
+                    prob.flags |= _lib.GHOST_DECAY          # the ghost band is consumed instead of exchanged
+                out = C.c_int(-1)
+                k0 = int(first_step[p_idx])
+                if trace is not None:                                  # timeline probe (tools/probe_streamed.py)
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t0.record(lane)
+                check(lib().fdtd2d_advance(C.byref(prob), (cur0 + p_idx) % 2, depths[p_idx],
+                                           None if src is None else src[k0:].ctypes.data_as(D),
+                                           depths[p_idx], C.c_void_p(lane.cuda_stream), C.byref(out)),
+                      "fdtd2d_advance (streamed)")
+                ev = torch.cuda.Event(enable_timing=trace is not None)
+                ev.record(lane)
+                done[(b, p_idx)] = ev
+                if trace is not None:
+                    trace.append((b, p_idx, t0, ev))
+                if p_idx == P - 1:
+                    down.wait_event(ev)
+                    r0, r1 = rows_of(b, p_idx)
+                    a, z = max(r0, self.row_lo), min(r1, self.row_hi)      # owned rows this block's last pass produced
+                    if z > a:
+                        with torch.cuda.stream(down):
+                            ez_dev = self._sets[(cur0 + P) % 2]["ez"]
+                            ez_host[a - self.row_lo:z - self.row_lo].copy_(ez_dev[a - lo_all:z - lo_all], non_blocking=True)
             for st in lanes + [up, down]:
                 caller.wait_stream(st)
         self._cur = (cur0 + P) % 2
         self.t += int(nsteps)
+
+    def _default_block_rows(self, schedule: str, least: int):
+        if schedule == "wavefront":
+            return 1024 if self.rows_alloc >= 8192 else max(least, -(-self.rows_alloc // 8))
+        return 1024 if self.rows_alloc >= 8192 else max(least, -(-self.rows_alloc // 8))
 
     # ---- checkpoint / restore, snapshots --------------------------------------------------
     def checkpoint(self) -> dict:

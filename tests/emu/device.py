@@ -25,6 +25,26 @@ def handle():
     return _handle
 
 
+class _Stream:
+    """stand-in for torch.cuda.Stream / Event: the emulated library runs every launch at once, in issue order"""
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+
 def install(monkeypatch):
     """-> the emulated library handle; Fdtd1D / Fdtd2D built with device="cpu" now run on it"""
     import torch
@@ -35,6 +55,10 @@ def install(monkeypatch):
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
     monkeypatch.setattr(torch.cuda, "device", contextlib.nullcontext)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Stream", _Stream)
+    monkeypatch.setattr(torch.cuda, "Event", _Stream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.cuda, "stream", contextlib.nullcontext)
     no_stream = lambda: C.c_void_p(None)
     accept = lambda *tensors: None
     for mod in (fd1d, fd2d):

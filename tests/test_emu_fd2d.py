@@ -150,6 +150,47 @@ def test_emulated_row_slabs_with_ghost_rows(emu, prog, nslab):
         assert got.tobytes() == getattr(g, n).tobytes(), n
 
 
+@pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
+@pytest.mark.parametrize("plan,ns", [(5, 52), ([64, 128, 256, 512], 40), ([24, 30, 24] * 30, 33), (2, 7)])
+def test_emulated_streamed_run(emu, plan, ns, schedule):
+    """run_streamed in ISSUE order (the emulated library runs every launch at once): the row ranges of the skewed
+    (parallelogram) and of the wavefront schedule, the upload / download slices and the ping-pong bookkeeping give the
+    plain run's bits.  (What concurrent streams may reorder is the GPU tests' business.)"""
+    from simulation_b200 import fd2d, surface
+    rng = np.random.default_rng(5)
+    nx, ny, npml = 700, 260, 12
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    src = fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6))
+    a = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, naz=naz, device="cpu")
+    a.advance(ns)
+    b = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, device="cpu")
+    host_ez = torch.empty((nx, ny), dtype=torch.float32)
+    kw = {"block_rows": plan} if isinstance(plan, list) else {"blocks": plan}
+    b.run_streamed(ns, torch.from_numpy(naz), host_ez, streams=5, schedule=schedule, **kw)
+    assert torch.equal(host_ez, a.tensor("ez"))
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+    assert b.t == ns and float(host_ez.abs().max()) > 1e-3
+
+
+@pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
+def test_emulated_streamed_run_on_a_slab(emu, schedule):
+    from simulation_b200 import fd2d, surface
+    rng = np.random.default_rng(9)
+    nx, ny, npml, rows, ghost, ns = 700, 200, 12, (200, 460), 36, 36
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    src = fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6))
+    whole = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, naz=naz, device="cpu")
+    whole.advance(ns)
+    part = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, rows=rows, ghost=ghost, device="cpu")
+    lo, hi = part.row_base, part.row_base + part.rows_alloc
+    host_ez = torch.empty((rows[1] - rows[0], ny), dtype=torch.float32)
+    part.run_streamed(ns, torch.from_numpy(naz[lo:hi].copy()), host_ez, blocks=3, streams=3, schedule=schedule)
+    assert torch.equal(host_ez, whole.tensor("ez")[rows[0]:rows[1]])
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(part.tensor(name), whole.tensor(name)[rows[0]:rows[1]]), name
+
+
 def test_emulated_checkpoint_restore(emu):
     nx, ny, npml = 72, 100, 8
     one = _sim_for("3_4", nx, ny, np.float32, npml=npml, device="cpu")

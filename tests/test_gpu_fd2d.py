@@ -370,8 +370,9 @@ def test_device_dielectric_equals_host_setup(dtype):
     assert sim.naz.shape == (100, 100)
 
 
+@pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
 @pytest.mark.parametrize("blocks,streams", [(5, 1), (5, 4), (9, 3), (2, 2)])
-def test_streamed_run_equals_plain_run(blocks, streams):
+def test_streamed_run_equals_plain_run(blocks, streams, schedule):
     """run_streamed (block wavefront over several streams, transfers overlapped) == set naz; advance; get ez -- bit
     for bit, and the whole state with it."""
     from simulation_b200 import fd2d, surface
@@ -384,7 +385,7 @@ def test_streamed_run_equals_plain_run(blocks, streams):
     b = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src)
     host_naz = torch.from_numpy(naz).pin_memory()
     host_ez = torch.empty((nx, ny), dtype=torch.float32).pin_memory()
-    b.run_streamed(ns, host_naz, host_ez, blocks=blocks, streams=streams)
+    b.run_streamed(ns, host_naz, host_ez, blocks=blocks, streams=streams, schedule=schedule)
     b.synchronize()
     assert torch.equal(host_ez, a.tensor("ez").cpu())
     for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
@@ -392,8 +393,9 @@ def test_streamed_run_equals_plain_run(blocks, streams):
     assert b.t == ns and float(host_ez.abs().max()) > 1e-3
 
 
+@pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
 @pytest.mark.parametrize("plan", [[64, 128, 256, 512, 256, 128, 64], [100, 1000], [700], [24, 30, 24] * 30])
-def test_streamed_run_with_ragged_block_plans(plan):
+def test_streamed_run_with_ragged_block_plans(plan, schedule):
     """run_streamed with explicit block heights (short blocks first and last, tall ones in between; plans shorter or
     longer than the grid; heights below the halo limit are raised) == plain advance, bit for bit."""
     from simulation_b200 import fd2d, surface
@@ -406,15 +408,16 @@ def test_streamed_run_with_ragged_block_plans(plan):
     b = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src)
     host_naz = torch.from_numpy(naz).pin_memory()
     host_ez = torch.empty((nx, ny), dtype=torch.float32).pin_memory()
-    b.run_streamed(ns, host_naz, host_ez, block_rows=plan, streams=5)
+    b.run_streamed(ns, host_naz, host_ez, block_rows=plan, streams=5, schedule=schedule)
     b.synchronize()
     assert torch.equal(host_ez, a.tensor("ez").cpu())
     for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
         assert torch.equal(a.tensor(name), b.tensor(name)), name
 
 
+@pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
 @pytest.mark.parametrize("rows,ghost,ns", [((300, 700), 48, 48), ((0, 500), 30, 24), ((900, 1500), 36, 36)])
-def test_streamed_run_on_a_slab_consumes_its_ghost_band(rows, ghost, ns):
+def test_streamed_run_on_a_slab_consumes_its_ghost_band(rows, ghost, ns, schedule):
     """Communication-avoiding streamed run: a slab with g ghost rows takes <= g steps with no exchange (rows beyond
     the stored ones read as zero, FDTD_GHOST_DECAY) and its OWNED rows equal the same rows of the whole-grid run."""
     from simulation_b200 import fd2d, surface
@@ -428,7 +431,7 @@ def test_streamed_run_on_a_slab_consumes_its_ghost_band(rows, ghost, ns):
     lo, hi = part.row_base, part.row_base + part.rows_alloc
     host_naz = torch.from_numpy(naz[lo:hi].copy()).pin_memory()
     host_ez = torch.empty((rows[1] - rows[0], ny), dtype=torch.float32).pin_memory()
-    part.run_streamed(ns, host_naz, host_ez, blocks=4, streams=3)
+    part.run_streamed(ns, host_naz, host_ez, blocks=4, streams=3, schedule=schedule)
     part.synchronize()
     assert torch.equal(host_ez, whole.tensor("ez")[rows[0]:rows[1]].cpu())
     for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):

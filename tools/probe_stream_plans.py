@@ -27,7 +27,9 @@ def ramp(head, body, tail):
 
 plans = {
     "uniform 1024": 1024,
+    "uniform 512": 512,
     "uniform 2048": 2048,
+    "uniform 4096": 4096,
     "ramp 512,1024,2048 | 4096 | 2048,1024,512": ramp((512, 1024, 2048), 4096, (2048, 1024, 512)),
     "ramp 512,1024 | 2048 | 1024,512": ramp((512, 1024), 2048, (1024, 512)),
     "ramp 512,1024,2048 | 3072 | 2048,1024,512": ramp((512, 1024, 2048), 3072, (2048, 1024, 512)),
@@ -37,7 +39,7 @@ plans = {
     "ramp 512,1024,2048 | 4096 | 1024": ramp((512, 1024, 2048), 4096, (1024,)),
 }
 ref = None
-for name, plan in plans.items():
+for schedule, name, plan in [("wavefront", "uniform 1024", 1024)] + [("skewed", k, v) for k, v in plans.items()]:
     best = None
     for rep in range(3):
         for f in ("dz", "hx", "hy", "ihx", "ihy", "ez"):
@@ -46,7 +48,7 @@ for name, plan in plans.items():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        sim.run_streamed(K, host_naz, host_ez, block_rows=plan)
+        sim.run_streamed(K, host_naz, host_ez, block_rows=plan, schedule=schedule)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -55,4 +57,4 @@ for name, plan in plans.items():
         ref = host_ez.clone()
     same = torch.equal(ref, host_ez)
     nblk = len(plan) if isinstance(plan, list) else -(-n // plan)
-    print(f"{name:52s} blocks {nblk:3d}: {best:7.1f} ms  {n * n * K / best / 1e6:6.1f} Gcell/s  ez == uniform-1024 ez: {same}", flush=True)
+    print(f"{schedule:9s} {name:52s} blocks {nblk:3d}: {best:7.1f} ms  {n * n * K / best / 1e6:6.1f} Gcell/s  ez == wavefront ez: {same}", flush=True)
