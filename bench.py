@@ -315,8 +315,9 @@ def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync):
     return {"value": float(nx_global) * n * K / dt / 1e6, "unit": "Mcell-updates/s",
             "h2d_bytes_per_step": stored * n * 4 / K, "d2h_bytes_per_step": rows * n * 4 / K,
             "what": f"pinned naz H2D ({stored * n * 4 / 2**30:.1f} GiB/GPU) + {K} steps + pinned Ez D2H, CUDA events on the launch "
-                    f"stream, max over ranks; run_streamed: 1024-row blocks, one stream per pass level, transfers overlapped "
-                    f"with the passes (after an untimed {2 * T}-step warm-up of the same call)"
+                    f"stream, max over ranks; run_streamed: row blocks uploaded in order (512..3072 rows), every block stepped through "
+                    f"all its passes as soon as it has arrived (skewed space-time tiling), one stream per pass level, Ez of "
+                    f"finished blocks downloaded behind the stepping (after an untimed {2 * T}-step warm-up of the same call)"
                     + ("" if world == 1 else f"; per rank a {K}-row ghost band consumed instead of exchanged (no communication in {K} steps)")}
 
 

@@ -607,9 +607,19 @@ class Fdtd2D:
         self.t += int(nsteps)
 
     def _default_block_rows(self, schedule: str, least: int):
-        if schedule == "wavefront":
-            return 1024 if self.rows_alloc >= 8192 else max(least, -(-self.rows_alloc // 8))
-        return 1024 if self.rows_alloc >= 8192 else max(least, -(-self.rows_alloc // 8))
+        """Block plan of run_streamed (profiles/r1_streamed_schedules_k96.txt, 32768^2 x 96 steps).  Wavefront: 1024-row
+        blocks (tall blocks starve the early pass levels).  Skewed: short blocks first, so stepping starts after ~1 ms
+        of upload, ~3072-row blocks in the middle (launches of several waves), short blocks last, so little is left to
+        download once the last pass ends."""
+        rows = self.rows_alloc
+        if rows < 8192:
+            return max(least, -(-rows // 8))
+        if schedule == "wavefront" or rows < 16384:
+            return 1024
+        head, tail = [512, 1024, 2048], [2048, 1024, 512]
+        left = rows - sum(head) - sum(tail)
+        nb = max(1, round(left / 3072))
+        return head + [left // nb] * nb + tail
 
     # ---- checkpoint / restore, snapshots (SURVEY.md 8f-3) --------------------------------------------------
     def checkpoint(self) -> dict:

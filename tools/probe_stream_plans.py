@@ -26,6 +26,7 @@ def ramp(head, body, tail):
 
 
 plans = {
+    "default": None,
     "uniform 1024": 1024,
     "uniform 512": 512,
     "uniform 2048": 2048,
@@ -56,5 +57,41 @@ for schedule, name, plan in [("wavefront", "uniform 1024", 1024)] + [("skewed", 
     if ref is None:
         ref = host_ez.clone()
     same = torch.equal(ref, host_ez)
-    nblk = len(plan) if isinstance(plan, list) else -(-n // plan)
+    nblk = len(plan) if isinstance(plan, list) else (-(-n // plan) if plan else 0)
     print(f"{schedule:9s} {name:52s} blocks {nblk:3d}: {best:7.1f} ms  {n * n * K / best / 1e6:6.1f} Gcell/s  ez == wavefront ez: {same}", flush=True)
+
+for S in (1, 2, 4, 8, 16):
+    best = None
+    for rep in range(3):
+        for f in ("dz", "hx", "hy", "ihx", "ihy", "ez"):
+            sim.tensor(f, stored=True).zero_()
+        sim.t = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        sim.run_streamed(K, host_naz, host_ez, streams=S)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None or (rep > 0 and ms < best) else best
+    print(f"skewed default plan, {S:2d} pass-level streams: {best:7.1f} ms  {n * n * K / best / 1e6:6.1f} Gcell/s", flush=True)
+
+# timeline of the default plan: where the time between the kernels' sum and the wall goes
+for f in ("dz", "hx", "hy", "ihx", "ihy", "ez"):
+    sim.tensor(f, stored=True).zero_()
+sim.t = 0
+trace = []
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+e0.record()
+sim.run_streamed(K, host_naz, host_ez, trace=trace)
+e1.record()
+torch.cuda.synchronize()
+rows = [(b, p, e0.elapsed_time(a), e0.elapsed_time(z)) for b, p, a, z in trace]
+print(f"default plan traced: {e0.elapsed_time(e1):.1f} ms; items {len(rows)}, sum of item durations {sum(z - a for _, _, a, z in rows):.1f} ms, "
+      f"first start {min(r[2] for r in rows):.2f}, last end {max(r[3] for r in rows):.2f}")
+nb = max(r[0] for r in rows) + 1
+for b in sorted({0, 1, 3, nb // 2, nb - 2, nb - 1}):
+    it = [r for r in rows if r[0] == b]
+    print(f"  block {b:2d}: level 0 starts {it[0][2]:7.2f}, last level ends {it[-1][3]:7.2f}; item durations "
+          + " ".join(f"{z - a:.2f}" for _, _, a, z in it))
