@@ -465,7 +465,7 @@ class Fdtd2D:
 
     def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, blocks: Optional[int] = None,
                      tblock=None, streams: int = 16, trace: Optional[list] = None, block_rows=None,
-                     schedule: str = "skewed") -> None:
+                     schedule: str = "skewed", window: Optional[int] = None, priorities: bool = False) -> None:
         """The whole job a reference ``main()`` does -- medium from the host, ``nsteps`` steps from zero fields,
         Ez back on the host -- with the PCIe transfers hidden behind the kernels.
 
@@ -548,8 +548,17 @@ class Fdtd2D:
             order = [(w - p_idx, p_idx) for w in range(B + P - 1) for p_idx in range(P) if 0 <= w - p_idx < B]
         with torch.cuda.device(self.device):
             caller = torch.cuda.current_stream()
-            if getattr(self, "_lanes", None) is None or len(self._lanes) < S + 2:
-                self._lanes = [torch.cuda.Stream() for _ in range(S + 2)]
+            if getattr(self, "_lanes", None) is None or len(self._lanes) < S + 2 or getattr(self, "_lanes_prio", False) != bool(priorities):
+                if priorities:
+                    # later pass levels first: work close to completion overtakes fresh blocks, so blocks finish in
+                    # order and their Ez leaves while the rest still steps
+                    least_p, greatest_p = torch.cuda.Stream.priority_range()
+                    span = max(1, least_p - greatest_p)
+                    self._lanes = [torch.cuda.Stream(priority=least_p - min(span, (k * (span + 1)) // S)) for k in range(S)] \
+                        + [torch.cuda.Stream(), torch.cuda.Stream()]
+                else:
+                    self._lanes = [torch.cuda.Stream() for _ in range(S + 2)]
+                self._lanes_prio = bool(priorities)
             lanes, up, down = self._lanes[:S], self._lanes[S], self._lanes[S + 1]
             for st in lanes + [up, down]:
                 st.wait_stream(caller)
@@ -569,6 +578,8 @@ class Fdtd2D:
                     # needs level p-1 of blocks b and b-1: the event of (b, p-1) implies (b-1, p-1), same stream, earlier
                     # block.  Level 0 reads naz up to the end of block b, and nothing of block b+1.
                     lane.wait_event(uploaded[b] if p_idx == 0 else done[(b, p_idx - 1)])
+                    if p_idx == 0 and window and b - int(window) >= 0:
+                        lane.wait_event(done[(b - int(window), P - 1)])     # at most `window` blocks in flight
                 elif p_idx == 0:
                     lane.wait_event(uploaded[min(b + 1, B - 1)])           # the pass reads naz up to depth rows below
                 else:

@@ -39,29 +39,10 @@ plans = {
     "ramp 512,1024,2048 | 6144 | 2048,1024,512": ramp((512, 1024, 2048), 6144, (2048, 1024, 512)),
     "ramp 512,1024,2048 | 4096 | 1024": ramp((512, 1024, 2048), 4096, (1024,)),
 }
-ref = None
-for schedule, name, plan in [("wavefront", "uniform 1024", 1024)] + [("skewed", k, v) for k, v in plans.items()]:
-    best = None
-    for rep in range(3):
-        for f in ("dz", "hx", "hy", "ihx", "ihy", "ez"):
-            sim.tensor(f, stored=True).zero_()
-        sim.t = 0
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        sim.run_streamed(K, host_naz, host_ez, block_rows=plan, schedule=schedule)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        best = ms if best is None or (rep > 0 and ms < best) else best
-    if ref is None:
-        ref = host_ez.clone()
-    same = torch.equal(ref, host_ez)
-    nblk = len(plan) if isinstance(plan, list) else (-(-n // plan) if plan else 0)
-    print(f"{schedule:9s} {name:52s} blocks {nblk:3d}: {best:7.1f} ms  {n * n * K / best / 1e6:6.1f} Gcell/s  ez == wavefront ez: {same}", flush=True)
 
-for S in (1, 2, 4, 8, 16):
+def timed(**kw):
     best = None
+    sim._lanes = None                                  # fresh streams for this configuration
     for rep in range(3):
         for f in ("dz", "hx", "hy", "ihx", "ihy", "ez"):
             sim.tensor(f, stored=True).zero_()
@@ -69,12 +50,28 @@ for S in (1, 2, 4, 8, 16):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        sim.run_streamed(K, host_naz, host_ez, streams=S)
+        sim.run_streamed(K, host_naz, host_ez, **kw)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         best = ms if best is None or (rep > 0 and ms < best) else best
-    print(f"skewed default plan, {S:2d} pass-level streams: {best:7.1f} ms  {n * n * K / best / 1e6:6.1f} Gcell/s", flush=True)
+    return best
+
+
+print("stream priority range", torch.cuda.Stream.priority_range())
+if os.environ.get("PLANS"):
+    ref = None
+    for schedule, name, plan in [("wavefront", "uniform 1024", 1024)] + [("skewed", k, v) for k, v in plans.items()]:
+        best = timed(block_rows=plan, schedule=schedule)
+        if ref is None:
+            ref = host_ez.clone()
+        nblk = len(plan) if isinstance(plan, list) else (-(-n // plan) if plan else 0)
+        print(f"{schedule:9s} {name:52s} blocks {nblk:3d}: {best:7.1f} ms  {n * n * K / best / 1e6:6.1f} Gcell/s  ez == wavefront ez: {torch.equal(ref, host_ez)}", flush=True)
+for prio in (False, True):
+    for S in (4, 8, 16):
+        for window in (None, 2, 3, 4, 6):
+            best = timed(streams=S, window=window, priorities=prio)
+            print(f"skewed default plan, {S:2d} streams, window {window}, priorities {prio}: {best:7.1f} ms  {n * n * K / best / 1e6:6.1f} Gcell/s", flush=True)
 
 # timeline of the default plan: where the time between the kernels' sum and the wall goes
 for f in ("dz", "hx", "hy", "ihx", "ihy", "ez"):
