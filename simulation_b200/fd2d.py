@@ -465,7 +465,7 @@ class Fdtd2D:
 
     def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, blocks: Optional[int] = None,
                      tblock=None, streams: int = 16, trace: Optional[list] = None, block_rows=None,
-                     schedule: str = "skewed", window: Optional[int] = None, priorities: bool = False) -> None:
+                     schedule: str = "skewed", window: Optional[int] = 2, priorities: bool = False) -> None:
         """The whole job a reference ``main()`` does -- medium from the host, ``nsteps`` steps from zero fields,
         Ez back on the host -- with the PCIe transfers hidden behind the kernels.
 
@@ -478,6 +478,11 @@ class Fdtd2D:
         produced for blocks b and b-1 -- never for b+1 -- so a block runs through ALL its passes as soon as it has
         arrived, whatever its height; the last block grows by the shift and the first shrinks.  The ping-pong sets stay
         safe: what level p of block b overwrites was read by level p-1 of blocks <= b only (its dependencies).
+        ``window`` blocks are in flight at most (block b+window starts once block b has finished its last pass): blocks
+        then finish in order and evenly spaced, so their Ez leaves over PCIe while later blocks still step -- without
+        it all 16 pass-level streams share the GPU, every block finishes near the end and the downloads trail the
+        stepping (32768^2 x 96 steps: 157 ms without a window, 142 ms with 2; profiles/r1_streamed_schedules_k96.txt).
+        ``priorities=True`` gives later pass levels higher stream priority instead (145 ms).
         ``schedule="wavefront"``: unshifted blocks; level p of block b must wait for level p-1 of block b+1, i.e. for
         the upload of block b+p+1 -- tall blocks starve the early passes (kept for comparison and for runs whose total
         shift would not fit the first block).
