@@ -5,11 +5,11 @@
 # status and the printed values (all zeros / nan = the kernels faulted) are shown too.
 set -u
 cd "$(dirname "$0")/.."
-for p in ref_cuda_test_3_2 ref_cuda_test_3_3 ref_cuda_test_3_2_8192; do
+for p in ref_cuda_test_3_2 ref_cuda_test_3_2_pmlfix ref_cuda_test_3_3_pmlfix ref_cuda_test_3_2_8192_pmlfix; do
   exe=oracle/_ref/$p
   [ -x $exe ] || { echo "$p: not built"; continue; }
   echo "== $p"
   t0=$(date +%s%N)
-  timeout 45 $exe 2>&1 | awk 'NR<=4 || /rror/ {print} NR==5 {print "..."}'
+  timeout 60 $exe 2>&1 | awk 'NR<=4 || /rror/ {print} NR==5 {print "..."}'
   echo "exit status: ${PIPESTATUS[0]}, wall $(( ($(date +%s%N) - t0) / 1000000 )) ms"
 done
