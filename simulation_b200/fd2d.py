@@ -496,61 +496,22 @@ class Fdtd2D:
         out exact, the ghost rows must be refreshed before stepping on (``SlabFdtd2D.run_streamed`` does)."""
         if self.tfsf or self.ft is not None:
             raise _lib.FdtdError("run_streamed: point source (or none) and no running DFT")
-        if schedule not in ("skewed", "wavefront"):
-            raise ValueError(schedule)
         slab = self.rows_alloc != self.nx
         rows_own = self.row_hi - self.row_lo
         if slab and int(nsteps) > self.ghost:
             raise _lib.FdtdError(f"run_streamed on a slab: {nsteps} steps without an exchange need {nsteps} ghost rows, have {self.ghost}")
         if tuple(naz_host.shape) != (self.rows_alloc, self.ny) or tuple(ez_host.shape) != (rows_own, self.ny):
             raise _lib.FdtdError("run_streamed: naz_host must cover the stored rows (rows_alloc, ny), ez_host the owned rows")
-        depths = self._depths(nsteps, tblock)
-        P = len(depths)
-        S = max(1, min(int(streams), P))
-        dmax = max(depths)
-        least = 4 * dmax                                                           # shortest block a pass may be given
-        lo_all, hi_all = self.row_base, self.row_base + self.rows_alloc           # global rows stored here
-        skew = P * dmax if schedule == "skewed" else 0                             # shift of the last pass level
-        if skew and skew + least > self.rows_alloc // 2:
-            schedule, skew = "wavefront", 0                                        # a long run on a short grid
-        if blocks is None and block_rows is None:
-            block_rows = self._default_block_rows(schedule, least)
-        if isinstance(block_rows, (list, tuple)):        # explicit block heights, top to bottom (the last one is stretched
-            edges = [lo_all]                             # or cut to end at the last stored row)
-            for h in block_rows:
-                if hi_all - edges[-1] < 2 * least:
-                    break
-                edges.append(min(edges[-1] + max(int(h), least), hi_all - least))
-            edges[-1] = hi_all
-            if len(edges) == 1:
-                edges.append(hi_all)
-        elif block_rows:                                 # one block height (the last block takes the remainder)
-            edges = list(range(lo_all, hi_all, max(int(block_rows), least))) + [hi_all]
-        else:
-            B = max(1, min(int(blocks), self.rows_alloc // max(least, 1)))
-            edges = [lo_all + self.rows_alloc * k // B for k in range(B + 1)]
-        if skew:
-            # the first block must keep `least` rows after the deepest shift: merge leading blocks until it does
-            while len(edges) > 2 and edges[1] - lo_all < skew + least:
-                del edges[1]
-            if edges[1] - lo_all < skew + least:
-                schedule, skew = "wavefront", 0
+        plan = self.streamed_plan(nsteps, tblock=tblock, streams=streams, blocks=blocks, block_rows=block_rows,
+                                  schedule=schedule, window=window)
+        depths, edges, P, S = plan["depths"], plan["edges"], plan["levels"], plan["streams"]
         B = len(edges) - 1
-
-        def rows_of(b, p):
-            """global rows pass level p produces for block b"""
-            sh = (p + 1) * dmax if skew else 0
-            return (lo_all if b == 0 else edges[b] - sh), (hi_all if b == B - 1 else edges[b + 1] - sh)
-
+        lo_all = self.row_base
         src = None
         if self.source is not None:
             src = np.ascontiguousarray(self.source.waveform.table(self.t + 1, nsteps), dtype=np.float64)
         first_step = np.concatenate(([0], np.cumsum(depths)))          # step offset of every pass
         D = C.POINTER(C.c_double)
-        if skew:                                          # block by block, every level of a block in a row
-            order = [(b, p_idx) for b in range(B) for p_idx in range(P)]
-        else:                                             # by wave, increasing p inside
-            order = [(w - p_idx, p_idx) for w in range(B + P - 1) for p_idx in range(P) if 0 <= w - p_idx < B]
         with torch.cuda.device(self.device):
             caller = torch.cuda.current_stream()
             if getattr(self, "_lanes", None) is None or len(self._lanes) < S + 2 or getattr(self, "_lanes_prio", False) != bool(priorities):
@@ -577,20 +538,13 @@ class Fdtd2D:
                     uploaded.append(ev)
             cur0 = self._cur
             done = {}                                                      # (b, p) -> event
-            for b, p_idx in order:
-                lane = lanes[p_idx % S]
-                if skew:
-                    # needs level p-1 of blocks b and b-1: the event of (b, p-1) implies (b-1, p-1), same stream, earlier
-                    # block.  Level 0 reads naz up to the end of block b, and nothing of block b+1.
-                    lane.wait_event(uploaded[b] if p_idx == 0 else done[(b, p_idx - 1)])
-                    if p_idx == 0 and window and b - int(window) >= 0:
-                        lane.wait_event(done[(b - int(window), P - 1)])     # at most `window` blocks in flight
-                elif p_idx == 0:
-                    lane.wait_event(uploaded[min(b + 1, B - 1)])           # the pass reads naz up to depth rows below
-                else:
-                    lane.wait_event(done[(min(b + 1, B - 1), p_idx - 1)])  # (b+1, p-1) implies (b, p-1) and (b-1, p-1)
+            for item in plan["items"]:
+                b, p_idx = item["block"], item["level"]
+                lane = lanes[item["lane"]]
+                for kind, key in item["waits"]:
+                    lane.wait_event(uploaded[key] if kind == "upload" else done[key])
                 prob = self._problem()
-                prob.row_lo, prob.row_hi = rows_of(b, p_idx)
+                prob.row_lo, prob.row_hi = item["rows"]
                 if p_idx < P - 1:
                     prob.flags |= _lib.LAZY_EZ
                 if slab:
@@ -611,8 +565,7 @@ class Fdtd2D:
                     trace.append((b, p_idx, t0, ev))
                 if p_idx == P - 1:
                     down.wait_event(ev)
-                    r0, r1 = rows_of(b, p_idx)
-                    a, z = max(r0, self.row_lo), min(r1, self.row_hi)      # owned rows this block's last pass produced
+                    a, z = max(item["rows"][0], self.row_lo), min(item["rows"][1], self.row_hi)   # owned rows of this block's last pass
                     if z > a:
                         with torch.cuda.stream(down):
                             ez_dev = self._sets[(cur0 + P) % 2]["ez"]
@@ -621,6 +574,75 @@ class Fdtd2D:
                 caller.wait_stream(st)
         self._cur = (cur0 + P) % 2
         self.t += int(nsteps)
+
+    def streamed_plan(self, nsteps: int, tblock=None, streams: int = 16, blocks: Optional[int] = None, block_rows=None,
+                      schedule: str = "skewed", window: Optional[int] = 2) -> dict:
+        """The launch plan of :meth:`run_streamed` as plain data (no device work): pass depths, block edges (global rows)
+        and, in issue order, one item per (block, pass level) with the rows it produces, its stream and the events it
+        waits for -- ``("upload", k)``: block k of the medium has arrived, ``("item", (b, p))``: that item has finished.
+        Items of one stream run in issue order.  tests/test_streamed_plan.py proves on this data that any two items not
+        ordered by these rules touch disjoint rows of every array set."""
+        if schedule not in ("skewed", "wavefront"):
+            raise ValueError(schedule)
+        depths = self._depths(nsteps, tblock)
+        P = len(depths)
+        S = max(1, min(int(streams), P))
+        dmax = max(depths)
+        least = 4 * dmax                                                           # shortest block a pass may be given
+        lo_all, hi_all = self.row_base, self.row_base + self.rows_alloc           # global rows stored here
+        skew = P * dmax if schedule == "skewed" else 0                             # shift of the last pass level
+        if skew and skew + least > self.rows_alloc // 2:
+            schedule, skew = "wavefront", 0                                        # a long run on a short grid
+        if blocks is None and block_rows is None:
+            block_rows = self._default_block_rows(schedule, least)
+        if isinstance(block_rows, (list, tuple)):        # explicit block heights, top to bottom (the last one is stretched
+            edges = [lo_all]                             # or cut to end at the last stored row)
+            for h in block_rows:
+                if hi_all - edges[-1] < 2 * least:
+                    break
+                edges.append(min(edges[-1] + max(int(h), least), hi_all - least))
+            edges[-1] = hi_all
+            if len(edges) == 1:
+                edges.append(hi_all)
+        elif block_rows:                                 # one block height (the last block takes the remainder)
+            edges = list(range(lo_all, hi_all, max(int(block_rows), least))) + [hi_all]
+            if len(edges) > 2 and edges[-1] - edges[-2] < least:
+                del edges[-2]                            # a remainder too short for a pass joins the block above
+        else:
+            B = max(1, min(int(blocks), self.rows_alloc // max(least, 1)))
+            edges = [lo_all + self.rows_alloc * k // B for k in range(B + 1)]
+        if skew:
+            # the first block must keep `least` rows after the deepest shift: merge leading blocks until it does
+            while len(edges) > 2 and edges[1] - lo_all < skew + least:
+                del edges[1]
+            if edges[1] - lo_all < skew + least:
+                schedule, skew = "wavefront", 0
+        B = len(edges) - 1
+
+        def rows_of(b, p):
+            """global rows pass level p produces for block b"""
+            sh = (p + 1) * dmax if skew else 0
+            return (lo_all if b == 0 else edges[b] - sh), (hi_all if b == B - 1 else edges[b + 1] - sh)
+
+        if skew:                                          # block by block, every level of a block in a row
+            order = [(b, p) for b in range(B) for p in range(P)]
+        else:                                             # by wave, increasing p inside
+            order = [(w - p, p) for w in range(B + P - 1) for p in range(P) if 0 <= w - p < B]
+        items = []
+        for b, p in order:
+            if skew:
+                # needs level p-1 of blocks b and b-1: (b, p-1) implies (b-1, p-1) -- same stream, earlier block.
+                # Level 0 reads naz up to the end of block b, and nothing of block b+1.
+                waits = [("upload", b)] if p == 0 else [("item", (b, p - 1))]
+                if p == 0 and window and b - int(window) >= 0:
+                    waits.append(("item", (b - int(window), P - 1)))       # at most `window` blocks in flight
+            elif p == 0:
+                waits = [("upload", min(b + 1, B - 1))]                    # the pass reads naz up to depth rows below
+            else:
+                waits = [("item", (min(b + 1, B - 1), p - 1))]             # (b+1, p-1) implies (b, p-1) and (b-1, p-1)
+            items.append({"block": b, "level": p, "rows": rows_of(b, p), "lane": p % S, "waits": waits})
+        return {"schedule": schedule, "depths": depths, "levels": P, "streams": S, "edges": edges, "items": items,
+                "stored_rows": (lo_all, hi_all)}
 
     def _default_block_rows(self, schedule: str, least: int):
         """Block plan of run_streamed (profiles/r1_streamed_schedules_k96.txt, 32768^2 x 96 steps).  Wavefront: 1024-row
