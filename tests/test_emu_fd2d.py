@@ -191,6 +191,56 @@ def test_emulated_streamed_run_on_a_slab(emu, schedule):
         assert torch.equal(part.tensor(name), whole.tensor(name)[rows[0]:rows[1]]), name
 
 
+class _SyncWords:
+    """stands in for the library-allocated sync words of slab.py: {flag from up, flag from down, counter 0, counter 1}"""
+
+    def __init__(self):
+        self.words = np.zeros(4, dtype=np.int64)
+        self.ptr = self.words.ctypes.data
+
+
+@pytest.mark.parametrize("prog,nslab,order", [("3_2", 2, "down"), ("3_3", 3, "up"), ("3_2", 4, "random"), ("3_4", 3, "random")])
+def test_emulated_fused_halo_exchange(emu, prog, nslab, order):
+    """The halo exchange fused into the pass (multi-GPU, slab.py's p2p mode) with every "GPU" a slab in this process:
+    the careful warps store their edge rows straight into the neighbours' ghost rows (here: the neighbours' host
+    arrays) and publish an epoch flag; each pass first checks its neighbours' flags.  Ranks run one after the other
+    within an epoch, in varying order -- any order is legal once the previous epoch is complete everywhere.  Owned
+    rows come out bit-identical to the monolithic oracle; no NCCL-style exchange happens anywhere."""
+    from simulation_b200 import fd2d
+    nx, ny, npml, T, nblocks, dtype = 200, 300, 8, 6, 5, np.float32
+    cuts = np.linspace(0, nx, nslab + 1).astype(int)
+    slabs = [_sim_for(prog, nx, ny, dtype, npml=npml, radius=0.3, rows=(int(lo), int(hi)), ghost=T, tblock=T, device="cpu")
+             for lo, hi in zip(cuts[:-1], cuts[1:])]
+    names = [n for n in fd2d.FIELD_NAMES if n != "ez" and (n != "iz" or prog == "3_4")]
+    for s in slabs:
+        s._sync_words = _SyncWords()
+    for r, s in enumerate(slabs):
+        def peer(q):
+            if q is None:
+                return None
+            o = slabs[q]
+            return {"row_base": o.row_base, "sync": o._sync_words.ptr,
+                    "sets": [{n: o._sets[k][n].data_ptr() for n in names} for k in range(2)]}
+        s.p2p = {"halo": T, "sync": s._sync_words, "up": peer(r - 1 if r > 0 else None), "dn": peer(r + 1 if r < nslab - 1 else None)}
+    rng = np.random.default_rng(3)
+    for epoch in range(1, nblocks + 1):
+        ranks = list(range(nslab))
+        if order == "up":
+            ranks.reverse()
+        elif order == "random":
+            rng.shuffle(ranks)
+        for r in ranks:
+            slabs[r].advance(T, tblock=T, lazy_ez=epoch < nblocks, epoch=epoch)
+    for r, s in enumerate(slabs):                      # every rank announced every epoch to each neighbour it has
+        assert s._sync_words.words[0] == (nblocks if r > 0 else 0) and s._sync_words.words[1] == (nblocks if r < nslab - 1 else 0)
+    ns = nblocks * T
+    g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=0.3, dft=False)
+    orc.advance_2d(g, src)
+    for n in names + ["ez"]:
+        got = np.concatenate([s.get(n) for s in slabs])
+        assert got.tobytes() == getattr(g, n).tobytes(), (n, np.argwhere(got != getattr(g, n))[:4].tolist())
+
+
 def test_emulated_checkpoint_restore(emu):
     nx, ny, npml = 72, 100, 8
     one = _sim_for("3_4", nx, ny, np.float32, npml=npml, device="cpu")
