@@ -58,13 +58,25 @@ class NumpyStandIn:
 def main():
     nx, ny, npml, ns, ghost, dtype = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]),
                                       int(sys.argv[5]), np.dtype(sys.argv[6]).type)
+    engine = sys.argv[7] if len(sys.argv) > 7 else "numpy"
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     table = orc.source_table("sine", ns, freq=1500e6)
     rng = np.random.default_rng(3)
     naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(dtype)
     src = {"i": nx // 2 - 5, "j": ny // 2 - 5, "table": table}
-    s = slab.SlabFdtd2D(nx, ny, npml, dtype, ghost=ghost, engine_factory=NumpyStandIn, source=src, naz=naz)
+    if engine == "emu":
+        # the PRODUCT's per-rank stepper (fd2d.Fdtd2D host code + the kernels' own source on the CTA emulator of
+        # tests/emu) under slab.py's grouped send/recv exchange, CPU tensors as device memory
+        import pytest
+        from tests.emu import device
+        device.install(pytest.MonkeyPatch())
+        from simulation_b200 import fd2d, surface
+        s = slab.SlabFdtd2D(nx, ny, npml, dtype, ghost=ghost, tblock=min(ghost, 6), halo="nccl", device="cpu", naz=naz,
+                            source=fd2d.PointSource(src["i"], src["j"], surface.Sinusoid(1500e6)))
+        assert s.halo_mode == "nccl" and type(s.engine) is fd2d.Fdtd2D
+    else:
+        s = slab.SlabFdtd2D(nx, ny, npml, dtype, ghost=ghost, engine_factory=NumpyStandIn, source=src, naz=naz)
     lo, hi = slab.partition(nx, world, rank)
     assert (s.row_lo, s.row_hi) == (lo, hi)
     # uneven advance calls: 7 steps, then the rest

@@ -31,6 +31,24 @@ def test_slab_equals_monolithic(world, nx, ny, npml, ns, ghost, dtype):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("world,nx,ny,npml,ns,ghost,dtype", [
+    (2, 96, 80, 8, 37, 6, "float32"),
+    (3, 130, 72, 6, 29, 4, "float64"),      # a middle rank; uneven split
+    (2, 64, 48, 6, 11, 1, "float32"),       # exchange every step
+])
+def test_slab_of_emulated_engines_equals_monolithic(world, nx, ny, npml, ns, ghost, dtype):
+    """The same protocol with the PRODUCT's stepper on every rank: fd2d.Fdtd2D (host code) driving the kernels' own
+    source on the CPU CTA emulator (tests/emu), ghost rows exchanged by slab.py over gloo."""
+    from tests.emu import build_emu
+    build_emu.build_library()               # once, before the ranks race for the build directory
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "slab_gloo_worker.py"), str(nx), str(ny), str(npml), str(ns), str(ghost), dtype, "emu"]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_partition_covers_all_rows():
     from simulation_b200 import slab
     for nx, world in ((32768 * 8, 8), (51, 2), (100, 3), (7, 7)):
