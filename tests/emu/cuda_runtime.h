@@ -180,6 +180,24 @@ inline void run_block(Block &b, dim3 block, void (*body)(void *), void *arg) {
     cur = nullptr;
 }
 
+// CTA contexts (shared memory + fiber stacks) are expensive to set up: keep them in a free list across launches
+struct BlockLease {
+    static std::vector<Block *> &pool() { static std::vector<Block *> p; return p; }
+    static std::atomic_flag &lock() { static std::atomic_flag f = ATOMIC_FLAG_INIT; return f; }
+    Block *b = nullptr;
+    BlockLease() {
+        while (lock().test_and_set(std::memory_order_acquire)) { }
+        if (!pool().empty()) { b = pool().back(); pool().pop_back(); }
+        lock().clear(std::memory_order_release);
+        if (b == nullptr) b = new Block;
+    }
+    ~BlockLease() {
+        while (lock().test_and_set(std::memory_order_acquire)) { }
+        pool().push_back(b);
+        lock().clear(std::memory_order_release);
+    }
+};
+
 // kernel<<<grid, block, smem, stream>>>(args) is rewritten (tests/emu/build_emu.py) into launch(grid, block, [&]{ kernel(args); })
 template <typename F>
 void launch(dim3 grid, dim3 block, F body) {
@@ -188,7 +206,8 @@ void launch(dim3 grid, dim3 block, F body) {
     if (nblocks == 0 || block.x * block.y * block.z == 0) return;
     std::atomic<unsigned long long> next{0};
     auto worker = [&] {
-        std::unique_ptr<Block> b(new Block);           // fiber stacks are reused by all the CTAs this host thread runs
+        BlockLease lease;                              // fiber stacks are reused by all the CTAs this host thread runs,
+        Block *b = lease.b;                            // and by later launches
         for (;;) {
             const unsigned long long id = next.fetch_add(1);
             if (id >= nblocks) break;

@@ -49,11 +49,16 @@ def test_emulated_advance_matches_oracle(emu, prog, nx, ny, npml, ns, tblock, dt
 
 
 @pytest.mark.parametrize("force_v,chunk_rows,tblock", [(4, 0, 6), (2, 16, 6), (1, 5, 4), (4, 40, 8), (2, 0, 3)])
-@pytest.mark.parametrize("prog,nx,ny,npml", [("3_2", 420, 1100, 8), ("3_3", 400, 1000, 12), ("3_4", 380, 1040, 10)])
+@pytest.mark.parametrize("prog,nx,ny,npml", [("3_2", 300, 1100, 8), ("3_3", 280, 1000, 12), ("3_4", 260, 1040, 10)])
 def test_emulated_interior_and_careful_kernels(emu, prog, nx, ny, npml, force_v, chunk_rows, tblock):
     """Grids with a true interior: the mask-free identity-coefficient kernel (packed arithmetic at fp32) and the
     careful kernel share every pass; every vector width, several row partitions, ragged last strips and chunks."""
+    before = emu.emu_launches()
     _run(emu, prog, nx, ny, npml, 2 * tblock + 1, np.float32, tblock, radius=0.3, tune=(force_v, chunk_rows, 0, 0, 0))
+    # 3 passes, each = careful kernel + interior kernel (+ the incident-line kernel with a TFSF source); the oracle-side
+    # setup launches nothing, the device-side identity check two kernels
+    per_pass = 3 if prog in ("3_3", "3_4") else 2
+    assert emu.emu_launches() - before == 3 * per_pass + 2, "the interior kernel did not run in every pass"
 
 
 def test_emulated_interior_kernel_equals_careful_kernel(emu):
@@ -151,14 +156,14 @@ def test_emulated_row_slabs_with_ghost_rows(emu, prog, nslab):
 
 
 @pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
-@pytest.mark.parametrize("plan,ns", [(5, 52), ([64, 128, 256, 512], 40), ([24, 30, 24] * 30, 33), (2, 7)])
+@pytest.mark.parametrize("plan,ns", [(4, 40), ([48, 96, 192], 26), ([24, 30, 24] * 30, 19), (2, 7)])
 def test_emulated_streamed_run(emu, plan, ns, schedule):
     """run_streamed in ISSUE order (the emulated library runs every launch at once): the row ranges of the skewed
     (parallelogram) and of the wavefront schedule, the upload / download slices and the ping-pong bookkeeping give the
     plain run's bits.  (What concurrent streams may reorder is the GPU tests' business.)"""
     from simulation_b200 import fd2d, surface
     rng = np.random.default_rng(5)
-    nx, ny, npml = 700, 260, 12
+    nx, ny, npml = 420, 132, 12
     naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
     src = fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6))
     a = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, naz=naz, device="cpu")
@@ -177,7 +182,7 @@ def test_emulated_streamed_run(emu, plan, ns, schedule):
 def test_emulated_streamed_run_on_a_slab(emu, schedule):
     from simulation_b200 import fd2d, surface
     rng = np.random.default_rng(9)
-    nx, ny, npml, rows, ghost, ns = 700, 200, 12, (200, 460), 36, 36
+    nx, ny, npml, rows, ghost, ns = 500, 132, 12, (150, 330), 24, 24
     naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
     src = fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6))
     whole = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, naz=naz, device="cpu")
