@@ -207,6 +207,12 @@ typedef struct {
     int peer_up_base, peer_dn_base;
     void *sync_local, *sync_up, *sync_dn;
     unsigned long long epoch;
+    /* FDTD_LOSSY problems whose loss is local (the reference's dielectric cylinder in free space, fd2d/python/
+     * fd2d_3_4.py:173-194): a promise that OUTSIDE global rows [lossy_row_lo, lossy_row_hi) x columns [lossy_col_lo,
+     * lossy_col_hi) nbz is 0 and iz is +0 in both state sets.  There `ez = naz*(dz-iz); iz += nbz*ez` has the bits of
+     * `ez = naz*dz` and leaves iz alone, so interior warps that stay outside the box run the lossless kernel (no iz /
+     * nbz traffic).  All four zero (or an empty box): no promise.  fdtd2d_check_lossless_outside() verifies it. */
+    int lossy_row_lo, lossy_row_hi, lossy_col_lo, lossy_col_hi;
 } fdtd2d_problem;
 
 /* Advance nsteps full time steps (reference order: ezinct, dfield+source, inctdz, efield, hxinct, hfield,
@@ -219,11 +225,19 @@ int fdtd2d_advance(const fdtd2d_problem *p, int cur, int nsteps, const double *s
                    void *stream, int *cur_out);
 /* number of coefficient entries that violate the ident_* promise of `p` (0 = promise holds); synchronises */
 int fdtd2d_check_identity(const fdtd2d_problem *p, long long *violations);
+/* *violations = stored cells outside the lossless-outside box of `p` with nbz != 0 or iz != +0 (either set) */
+int fdtd2d_check_lossless_outside(const fdtd2d_problem *p, long long *violations);
 /* resolve (module-load) every kernel instantiation a problem of this dtype / width can launch, so that no
  * time step pays CUDA's lazy loading.  lossy: bit 0 = FDTD_LOSSY kernels, bit 1 = also the fused-DFT kernels */
 int fdtd2d_preload(int dtype, int ny, int lossy);
 /* largest supported tblock for a dtype / ny (0 if unsupported) */
 int fdtd2d_max_tblock(int dtype, int ny);
+/* Test / tuning hook, process-wide, all zero = defaults: force_v (1, 2, 4) and chunk_rows override the launch plan,
+ * warps_per_cta (1..8), ring_depth == 1 runs the edge and interior kernels in stream order instead of forking the
+ * edge kernel onto a side stream, force_careful bit 0 sends every warp through the careful (edge) kernel, bit 1
+ * ignores the lossless-outside promise.  Results are bit-identical under every setting (that is what the tests use
+ * it for). */
+int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, int force_careful);
 
 #ifdef __cplusplus
 }

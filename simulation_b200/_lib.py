@@ -63,7 +63,8 @@ class Problem2D(C.Structure):
                 ("halo", C.c_int), ("peer_up", (C.c_void_p * NFIELDS) * 2), ("peer_dn", (C.c_void_p * NFIELDS) * 2),
                 ("peer_up_base", C.c_int), ("peer_dn_base", C.c_int),
                 ("sync_local", C.c_void_p), ("sync_up", C.c_void_p), ("sync_dn", C.c_void_p),
-                ("epoch", C.c_ulonglong)]
+                ("epoch", C.c_ulonglong),
+                ("lossy_row_lo", C.c_int), ("lossy_row_hi", C.c_int), ("lossy_col_lo", C.c_int), ("lossy_col_hi", C.c_int)]
 
 
 # every symbol include/fdtd_b200.h declares: name -> (restype, argtypes)
@@ -100,6 +101,7 @@ SYMBOLS = {
     "fdtd2d_dielectric_cylinder": (_I, [_I, _I, _I, _I, _I, _D, _D, _D, _I, _I, _P, _P, _P]),
     "fdtd2d_advance": (_I, [C.POINTER(Problem2D), _I, _I, C.POINTER(_D), _I, _P, C.POINTER(_I)]),
     "fdtd2d_check_identity": (_I, [C.POINTER(Problem2D), C.POINTER(C.c_longlong)]),
+    "fdtd2d_check_lossless_outside": (_I, [C.POINTER(Problem2D), C.POINTER(C.c_longlong)]),
     "fdtd2d_preload": (_I, [_I, _I, _I]),
     "fdtd2d_max_tblock": (_I, [_I, _I]),
     "fdtd2d_tune": (_I, [_I, _I, _I, _I, _I]),

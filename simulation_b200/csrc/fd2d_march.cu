@@ -58,6 +58,13 @@ struct MarchParams {
     unsigned long long epoch;                  // sequence number of this advance call (1, 2, ...)
     unsigned total_warps;                      // warps of the careful kernel of the pass (the only ones that touch ghosts)
     int write_ez;                              // 0: this pass leaves ez untouched (it is never read by a pass)
+    // Lossy problems whose loss is local (a dielectric object in free space): outside rows [lz_row_lo, lz_row_hi) x
+    // cols [lz_col_lo, lz_col_hi) nbz is 0 and iz is +0 in both state sets, where ez = naz*(dz-iz), iz += nbz*ez gives
+    // the bits of ez = naz*dz and leaves iz alone.  Interior warps that stay outside the box then run the lossless
+    // kernel (no iz / nbz traffic); the two interior kernels of a pass share one index space and each warp keeps or
+    // drops itself by this box.
+    int split_lossless;
+    int lz_row_lo, lz_row_hi, lz_col_lo, lz_col_hi;
     int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
     int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
     int n_spairs;                              // single (strip, chunk) cells of otherwise ordinary strips and chunks that the
@@ -655,6 +662,15 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
         chunk = kth_not_in(w / nsf, p.schunks, p.n_schunks);
         for (int q = 0; q < p.n_spairs; ++q)
             if (strip == p.spairs[q][0] && chunk == p.spairs[q][1]) return;     // the careful kernel has this one
+        if (p.split_lossless) {
+            // rows and columns this warp touches (warm-up, drain and fetch run-ahead included), as the host classifies them
+            constexpr int W = 32 * V, HALO = ((T + V - 1) / V) * V, USE = W - 2 * HALO;
+            const int c0 = strip * USE - HALO, c1 = c0 + W;
+            const int r0 = p.out_lo + chunk * crows, r1 = min(r0 + crows, p.out_hi);
+            const int lo = r0 - T - 1, hi = r1 + 2 * T + RING + 2;
+            const bool in_box = c0 < p.lz_col_hi && c1 > p.lz_col_lo && lo < p.lz_row_hi && hi > p.lz_row_lo;
+            if (in_box != ((MODE & 1) != 0)) return;     // lossy kernel: warps meeting the box; lossless kernel: the others
+        }
     } else if (all_careful) {
         if (w >= p.nstrips * p.nchunks) return;
         strip = w % p.nstrips;
@@ -757,11 +773,28 @@ __global__ void k_check_identity(const real *f1, const real *f2, const real *f3,
     if (!ok) atomicAdd(bad, 1ull);
 }
 
+// counts stored cells OUTSIDE the promised box whose nbz is not 0 or whose iz (either state set) is not +0
+template <typename real>
+__global__ void k_check_lossless_outside(const real *nbz, const real *iz0, const real *iz1, int ny, int row_base, int rows,
+                                         int rlo, int rhi, int clo, int chi, unsigned long long *bad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ny) return;
+    const real zero = real(0);
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+        const int i = row_base + r;
+        if (i >= rlo && i < rhi && j >= clo && j < chi) continue;
+        const size_t n = (size_t)r * ny + j;
+        const bool ok = nbz[n] == zero && iz0[n] == zero && !signbit(iz0[n]) && iz1[n] == zero && !signbit(iz1[n]);
+        if (!ok) atomicAdd(bad, 1ull);
+    }
+}
+
 int g_force_v = 0;          // test / tuning hooks (fdtd2d_tune)
 int g_chunk_rows = 0;
 int g_warps = 0;
 int g_careful = 0;
 
+int g_split = 1;             // 0 = ignore the lossless-outside promise (tests: the lossy kernel everywhere)
 int g_serial = 2;            // 2 = fork the edge kernel onto a side stream (measured +2 %); 1 = edge then interior in order
 
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
@@ -879,17 +912,28 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     // The careful kernel is small (edges only) and would run alone at a fraction of a wave: fork it onto a side
     // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
     SideStream *side = (n_careful > 0 && n_fast > 0 && g_serial == 2) ? side_stream(st) : nullptr;
+    // interior warps: one launch, or -- lossy problem with a lossless-outside promise -- two over the same index space
+    // (the lossy kernel keeps the warps that meet the box, the lossless kernel the others)
+    auto launch_interior = [&]() -> int {
+        if constexpr (MODE == 1) {
+            if (mp.split_lossless) {
+                int rc2 = launch_one<real, V, T, 0, true>(mp, n_fast, 0, st);
+                if (rc2 != FDTD_OK) return rc2;
+            }
+        }
+        return launch_one<real, V, T, MODE, true>(mp, n_fast, 0, st);
+    };
     if (side == nullptr) {
         int rc = launch_one<real, V, T, MODE, false>(mp, n_careful, 0, st);
         if (rc != FDTD_OK) return rc;
-        return launch_one<real, V, T, MODE, true>(mp, n_fast, 0, st);
+        return launch_interior();
     }
     FDTD_CUDA(cudaEventRecord(side->fork, st));
     FDTD_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
     int rc = launch_one<real, V, T, MODE, false>(mp, n_careful, 0, side->stream);
     if (rc != FDTD_OK) return rc;
     FDTD_CUDA(cudaEventRecord(side->join, side->stream));
-    rc = launch_one<real, V, T, MODE, true>(mp, n_fast, 0, st);
+    rc = launch_interior();
     if (rc != FDTD_OK) return rc;
     FDTD_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     return FDTD_OK;
@@ -938,6 +982,7 @@ void touch_T(bool lossy) {
     if (lossy) {
         cudaFuncGetAttributes(&a, k_march<real, V, T, 1, true>);
         cudaFuncGetAttributes(&a, k_march<real, V, T, 1, false>);
+        cudaFuncGetAttributes(&a, k_march<real, V, T, 0, true>);     // lossless-outside split
     } else {
         cudaFuncGetAttributes(&a, k_march<real, V, T, 0, true>);
         cudaFuncGetAttributes(&a, k_march<real, V, T, 0, false>);
@@ -1063,6 +1108,9 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
             mp.epoch = q->epoch;
             mp.total_warps = 0;
         }
+        mp.lz_row_lo = q->lossy_row_lo; mp.lz_row_hi = q->lossy_row_hi;
+        mp.lz_col_lo = q->lossy_col_lo; mp.lz_col_hi = q->lossy_col_hi;
+        mp.split_lossless = lossy && q->nf == 0 && g_split != 0 && q->lossy_row_hi > q->lossy_row_lo && q->lossy_col_hi > q->lossy_col_lo;
         mp.nf = q->nf;
         mp.r_pt = (real *)q->ft.r_pt; mp.i_pt = (real *)q->ft.i_pt;
         mp.dft_plane = (long long)q->rows_alloc * q->ny;
@@ -1145,6 +1193,29 @@ int fdtd2d_check_identity(const fdtd2d_problem *q, long long *violations) {
     return FDTD_OK;
 }
 
+int fdtd2d_check_lossless_outside(const fdtd2d_problem *q, long long *violations) {
+    FDTD_REQUIRE(q && violations, "fdtd2d_check_lossless_outside: null argument");
+    FDTD_REQUIRE(q->dtype == FDTD_F32 || q->dtype == FDTD_F64, "fdtd2d_check_lossless_outside: unknown dtype %d", q->dtype);
+    FDTD_REQUIRE((q->flags & FDTD_LOSSY) && q->md.nbz && q->state[0][FDTD2D_IZ] && q->state[1][FDTD2D_IZ],
+                 "fdtd2d_check_lossless_outside: a lossy problem with nbz and both iz arrays");
+    FDTD_REQUIRE(q->rows_alloc >= 1 && q->ny >= 1, "fdtd2d_check_lossless_outside: bad sizes");
+    unsigned long long *bad = nullptr, host = 0;
+    FDTD_CUDA(cudaMalloc(&bad, sizeof(*bad)));
+    FDTD_CUDA(cudaMemset(bad, 0, sizeof(*bad)));
+    const dim3 grid((q->ny + 255) / 256, min(q->rows_alloc, 65535));
+    if (q->dtype == FDTD_F32)
+        k_check_lossless_outside<float><<<grid, 256>>>((const float *)q->md.nbz, (const float *)q->state[0][FDTD2D_IZ], (const float *)q->state[1][FDTD2D_IZ],
+                                                       q->ny, q->row_base, q->rows_alloc, q->lossy_row_lo, q->lossy_row_hi, q->lossy_col_lo, q->lossy_col_hi, bad);
+    else
+        k_check_lossless_outside<double><<<grid, 256>>>((const double *)q->md.nbz, (const double *)q->state[0][FDTD2D_IZ], (const double *)q->state[1][FDTD2D_IZ],
+                                                        q->ny, q->row_base, q->rows_alloc, q->lossy_row_lo, q->lossy_row_hi, q->lossy_col_lo, q->lossy_col_hi, bad);
+    FDTD_LAUNCH_CHECK("k_check_lossless_outside");
+    FDTD_CUDA(cudaMemcpy(&host, bad, sizeof(host), cudaMemcpyDeviceToHost));
+    FDTD_CUDA(cudaFree(bad));
+    *violations = (long long)host;
+    return FDTD_OK;
+}
+
 int fdtd2d_preload(int dtype, int ny, int lossy) {
     (void)ny;
 #ifdef FDTD_DEV_ONLY
@@ -1189,7 +1260,8 @@ int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, 
     g_chunk_rows = chunk_rows;
     g_warps = warps_per_cta;
     g_serial = (ring_depth == 1) ? 1 : 2;     // (slot reused) 1 = serialise the edge and interior kernels
-    g_careful = force_careful;
+    g_careful = force_careful & 1;            // bit 0: every warp through the careful kernel
+    g_split = (force_careful & 2) ? 0 : 1;    // bit 1: ignore the lossless-outside promise
     return FDTD_OK;
 }
 

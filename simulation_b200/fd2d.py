@@ -257,6 +257,8 @@ class Fdtd2D:
         self.row_base = max(self.row_lo - self.ghost, 0)
         self.rows_alloc = min(self.row_hi + self.ghost, self.nx) - self.row_base
         self.t = 0                                        # steps taken so far (next step is t+1)
+        self._lossy_box_cache = None
+        self._int_dtype = torch.int32 if self.np_dtype == np.float32 else torch.int64    # bit view: -0.0 is not +0
         code = _lib.dtype_code(self.np_dtype)
         self.max_tblock = lib().fdtd2d_max_tblock(code, self.ny)
         self.tblock = int(tblock) if tblock else 0       # 0: the library picks depth / vector width / chunking by grid size
@@ -291,6 +293,8 @@ class Fdtd2D:
             check(lib().fdtd2d_preload(code, self.ny, int(self.lossy) | (2 if freqs is not None else 0)), "fdtd2d_preload")
             if self.check_identity() != 0:
                 raise _lib.FdtdError("PML vectors violate the identity-coefficient promise outside the layer")
+            if self.lossy and self.check_lossless_outside() != 0:
+                raise _lib.FdtdError("nbz / iz violate the lossless-outside promise computed from them")
             # running DFT (program 3_4): accumulators over the stored rows, updated after every step
             self.freqs, self.dt = (None if freqs is None else np.asarray(freqs, dtype=self.np_dtype)), float(dt)
             if self.freqs is not None:
@@ -344,6 +348,8 @@ class Fdtd2D:
         if name in ("ezi", "hxi", "bc"):
             getattr(self, name).copy_(torch.as_tensor(np.asarray(host, dtype=self.np_dtype)))
             return
+        if name == "iz":
+            self._lossy_box_cache = None
         a = np.asarray(host, dtype=self.np_dtype)
         if a.shape == (self.nx, self.ny) and (self.rows_alloc != self.nx):
             self.tensor(name, stored=True).copy_(torch.from_numpy(
@@ -375,7 +381,37 @@ class Fdtd2D:
         # pmlparam leaves every coefficient at its identity value on [npml, N-1-npml): promise it to the kernel
         p.ident_row_lo, p.ident_row_hi = self._ident(self.nx)
         p.ident_col_lo, p.ident_col_hi = self._ident(self.ny)
+        if self.lossy:
+            p.lossy_row_lo, p.lossy_row_hi, p.lossy_col_lo, p.lossy_col_hi = self._lossy_box()
         return p
+
+    def _lossy_box(self):
+        """Global rows / columns ``(r0, r1, c0, c1)`` outside which ``nbz == 0`` and ``iz == +0`` in both state sets (the
+        lossless-outside promise of fdtd2d_problem), found on the device from the arrays themselves; recomputed after
+        ``iz`` or ``nbz`` was written from outside (``set``, ``restore``, :meth:`invalidate_lossy_box`)."""
+        if self._lossy_box_cache is None:
+            with torch.cuda.device(self.device):
+                live = (self.nbz != 0) | (self._sets[0]["iz"].view(self._int_dtype) != 0) | (self._sets[1]["iz"].view(self._int_dtype) != 0)
+                rows = torch.nonzero(live.any(dim=1)).flatten()
+                cols = torch.nonzero(live.any(dim=0)).flatten()
+                if rows.numel() == 0:
+                    box = (self.row_base, self.row_base + 1, 0, 1)          # nothing lossy here: a one-cell box at a corner
+                else:
+                    box = (self.row_base + int(rows[0]), self.row_base + int(rows[-1]) + 1, int(cols[0]), int(cols[-1]) + 1)
+            self._lossy_box_cache = box
+        return self._lossy_box_cache
+
+    def invalidate_lossy_box(self) -> None:
+        """Call after writing ``nbz`` or ``iz`` tensors directly (``tensor('iz')[...] = ...``)."""
+        self._lossy_box_cache = None
+
+    def check_lossless_outside(self) -> int:
+        """Device-side verification of the lossless-outside promise (0 = holds)."""
+        bad = C.c_longlong(-1)
+        p = self._problem()
+        with torch.cuda.device(self.device):
+            check(lib().fdtd2d_check_lossless_outside(C.byref(p), C.byref(bad)), "fdtd2d_check_lossless_outside")
+        return int(bad.value)
 
     def _ident(self, n):
         lo, hi = self.npml, n - 1 - self.npml

@@ -57,8 +57,10 @@ def test_emulated_interior_and_careful_kernels(emu, prog, nx, ny, npml, force_v,
     _run(emu, prog, nx, ny, npml, 2 * tblock + 1, np.float32, tblock, radius=0.3, tune=(force_v, chunk_rows, 0, 0, 0))
     # 3 passes, each = careful kernel + interior kernel (+ the incident-line kernel with a TFSF source); the oracle-side
     # setup launches nothing, the device-side identity check two kernels
-    per_pass = 3 if prog in ("3_3", "3_4") else 2
-    assert emu.emu_launches() - before == 3 * per_pass + 2, "the interior kernel did not run in every pass"
+    # 3_4 (lossy cylinder in free space): two interior kernels per pass -- lossy for the warps that meet the cylinder's
+    # box, lossless for the others -- and one more setup check (the lossless-outside promise)
+    per_pass = {"3_2": 2, "3_3": 3, "3_4": 4}[prog]
+    assert emu.emu_launches() - before == 3 * per_pass + (3 if prog == "3_4" else 2), "an interior kernel did not run in every pass"
 
 
 def test_emulated_interior_kernel_equals_careful_kernel(emu):
@@ -244,6 +246,36 @@ def test_emulated_fused_halo_exchange(emu, prog, nslab, order):
     for n in names + ["ez"]:
         got = np.concatenate([s.get(n) for s in slabs])
         assert got.tobytes() == getattr(g, n).tobytes(), (n, np.argwhere(got != getattr(g, n))[:4].tolist())
+
+
+def test_emulated_lossless_outside_split(emu):
+    """A lossy object in free space: interior warps outside the object's box run the lossless kernel.  Same bits as the
+    lossy kernel everywhere (split disabled), as the oracle, and the promise is re-derived when iz is uploaded."""
+    nx, ny, npml, ns = 300, 900, 10, 20
+    a = _run(emu, "3_4", nx, ny, npml, ns, np.float32, 6, radius=0.25)
+    r0, r1, c0, c1 = a._lossy_box()
+    assert 0 < r1 - r0 < 60 and 0 < c1 - c0 < 60 and a.check_lossless_outside() == 0        # rgrid = 24 cells
+    b = _run(emu, "3_4", nx, ny, npml, ns, np.float32, 6, radius=0.25, tune=(0, 0, 0, 0, 2))   # lossy kernel everywhere
+    for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy"):
+        assert a.get(name).tobytes() == b.get(name).tobytes(), name
+    # iz uploaded from outside, non-zero far from the cylinder: the box must grow to hold it, results stay exact
+    rng = np.random.default_rng(2)
+    g, src = cases.grid_program("3_4", nx, ny, ns, np.float32, npml=npml, radius=0.25, dft=False)
+    c = _sim_for("3_4", nx, ny, np.float32, npml=npml, radius=0.25, device="cpu")
+    iz = np.zeros((nx, ny), dtype=np.float32)
+    iz[40:44, 700:720] = rng.standard_normal((4, 20)).astype(np.float32)
+    iz[250, 100] = -0.0                                     # a negative zero is not +0 either
+    c.set("iz", iz)
+    g.iz[...] = iz
+    box = c._lossy_box()
+    assert box[0] <= 40 and box[1] >= 251 and box[2] <= 100 and box[3] >= 720 and c.check_lossless_outside() == 0
+    c.advance(ns)
+    orc.advance_2d(g, src)
+    _assert_same(c, g, "3_4")
+    # a stale promise is caught by the device-side check
+    c._lossy_box_cache = (r0, r1, c0, c1)
+    c.tensor("iz")[5, 5] = 1.0
+    assert c.check_lossless_outside() >= 1
 
 
 def test_emulated_checkpoint_restore(emu):

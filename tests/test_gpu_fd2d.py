@@ -261,6 +261,45 @@ def test_interior_kernel_equals_edge_kernel_everywhere():
     assert float(a.tensor("ez").abs().max()) > 0.5
 
 
+def test_lossless_outside_split_equals_lossy_kernel_everywhere():
+    """A lossy cylinder in free space: interior warps outside the cylinder's box run the lossless kernel (no iz / nbz
+    traffic).  Bitwise equal to the lossy kernel on every warp (split disabled), iz included; and the oracle on a
+    smaller grid with iz uploaded far from the object."""
+    from simulation_b200 import _lib
+    nx, ny, npml, ns = 1400, 1800, 20, 66
+    a = _sim_for("3_4", nx, ny, np.float32, npml=npml, radius=1.5)
+    r0, r1, c0, c1 = a._lossy_box()
+    assert 0 < r1 - r0 < 320 and 0 < c1 - c0 < 320 and a.check_lossless_outside() == 0
+    a.advance(ns)
+    _lib.lib().fdtd2d_tune(0, 0, 0, 0, 2)
+    try:
+        b = _sim_for("3_4", nx, ny, np.float32, npml=npml, radius=1.5)
+        b.advance(ns)
+        b.synchronize()
+    finally:
+        _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
+    for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy"):
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+    assert float(a.tensor("iz").abs().max()) > 0 and float(a.tensor("ez").abs().max()) > 0.5
+    # uploaded iz (negative zero included) outside the object: the promise is re-derived, the oracle's bits come out
+    nx, ny, npml, ns = 300, 900, 10, 40
+    rng = np.random.default_rng(2)
+    g, src = cases.grid_program("3_4", nx, ny, ns, np.float32, npml=npml, radius=0.25, dft=False)
+    c = _sim_for("3_4", nx, ny, np.float32, npml=npml, radius=0.25)
+    iz = np.zeros((nx, ny), dtype=np.float32)
+    iz[40:44, 700:720] = rng.standard_normal((4, 20)).astype(np.float32)
+    iz[250, 100] = -0.0
+    c.set("iz", iz)
+    g.iz[...] = iz
+    box = c._lossy_box()
+    assert box[0] <= 40 and box[1] >= 251 and box[2] <= 100 and box[3] >= 720 and c.check_lossless_outside() == 0
+    c.advance(ns)
+    orc.advance_2d(g, src)
+    _assert_same(c, g, "3_4")
+    c._lossy_box_cache = (140, 160, 440, 460)
+    assert c.check_lossless_outside() >= 1                  # a stale promise is caught on the device
+
+
 def test_identity_promise_is_checked():
     from simulation_b200 import _lib
     sim = _sim_for("3_2", 128, 160, np.float32, npml=8)
