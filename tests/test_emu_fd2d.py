@@ -258,6 +258,9 @@ def test_emulated_lossless_outside_split(emu):
     b = _run(emu, "3_4", nx, ny, npml, ns, np.float32, 6, radius=0.25, tune=(0, 0, 0, 0, 2))   # lossy kernel everywhere
     for name in ("dz", "ez", "iz", "hx", "hy", "ihx", "ihy"):
         assert a.get(name).tobytes() == b.get(name).tobytes(), name
+    # the wave must have reached the object for iz to mean anything: a narrow grid, enough steps
+    d = _run(emu, "3_4", 300, 200, npml, 110, np.float32, 6, radius=0.25)
+    assert float(np.abs(d.get("iz")).max()) > 0 and 0 < d._lossy_box()[1] - d._lossy_box()[0] < 60
     # iz uploaded from outside, non-zero far from the cylinder: the box must grow to hold it, results stay exact
     rng = np.random.default_rng(2)
     g, src = cases.grid_program("3_4", nx, ny, ns, np.float32, npml=npml, radius=0.25, dft=False)
