@@ -103,6 +103,28 @@ class ClockSampler:
         return out
 
 
+def pin_to_gpu_numa_node(index):
+    """Run this process on the CPUs next to its GPU (NVML's ideal affinity), so that the pinned host buffers of the e2e
+    leg are allocated on the GPU's NUMA node: on a two-socket box a buffer on the far socket halves the PCIe rate.
+    FDTD_NO_AFFINITY=1 leaves the affinity alone."""
+    if os.environ.get("FDTD_NO_AFFINITY"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------ CPU legs
 def cpu_numpy_port(n, steps):
     """The numpy oracle (bit-identical restatement of fd2d/program/fd2d_3_2.py) on one core."""
@@ -185,6 +207,7 @@ def run_ours(args, emit=print):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    pin_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
