@@ -32,6 +32,7 @@ N_FULL = 32768
 NPML = 80
 BYTES_PER_CELL_UPDATE = 48          # dz,hx,hy,ihx,ihy R+W; naz R; ez W (fp32) -- SURVEY.md 8(d)
 METRIC = "Mcell-updates/s, 2D TM+PML fp32"
+E2E_REPEATS = 3                     # the end-to-end job is a single ~0.15 s shot whose overlap depends on launch timing: median of 3
 
 
 def peaks():
@@ -323,24 +324,30 @@ def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync):
             sim.tensor(name, stored=True).zero_()
         sim.t = 0
     sim.run_streamed(2 * T, host_naz, host_ez)                     # untimed warm-up of this path (streams, events, pages)
-    fresh()                                                        # fresh problem: fields start at zero
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    e0.record()
-    sim.run_streamed(K, host_naz, host_ez)                         # transfers overlapped with the passes
-    e1.record()
-    sync()
-    dt = e0.elapsed_time(e1) * 1e-3
-    if world > 1:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    runs = []
+    for _ in range(E2E_REPEATS):                                   # the whole job, E2E_REPEATS times; the median is reported
+        fresh()                                                    # fresh problem: fields start at zero
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        e0.record()
+        sim.run_streamed(K, host_naz, host_ez)                     # transfers overlapped with the passes
+        e1.record()
+        sync()
+        dt = e0.elapsed_time(e1) * 1e-3
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        runs.append(dt)
+    dt = float(np.median(runs))
     return {"value": float(nx_global) * n * K / dt / 1e6, "unit": "Mcell-updates/s",
             "h2d_bytes_per_step": stored * n * 4 / K, "d2h_bytes_per_step": rows * n * 4 / K,
+            "runs_ms": [round(x * 1e3, 2) for x in runs],
             "what": f"pinned naz H2D ({stored * n * 4 / 2**30:.1f} GiB/GPU) + {K} steps + pinned Ez D2H, CUDA events on the launch "
                     f"stream, max over ranks; run_streamed: row blocks uploaded in order (512..3072 rows), every block stepped through "
                     f"all its passes as soon as it has arrived (skewed space-time tiling), one stream per pass level, Ez of "
-                    f"finished blocks downloaded behind the stepping (after an untimed {2 * T}-step warm-up of the same call)"
+                    f"finished blocks downloaded behind the stepping (after an untimed {2 * T}-step warm-up of the same call); "
+                    f"median of {E2E_REPEATS} whole jobs (runs_ms)"
                     + ("" if world == 1 else f"; per rank a {K}-row ghost band consumed instead of exchanged (no communication in {K} steps)")}
 
 
