@@ -104,8 +104,8 @@ def rewrite_launches(src: str) -> str:
 ASM = [  # the kernels' inline PTX, statement by statement -> its emulation (tests/emu/cuda_runtime.h, namespace emu)
     (r'asm volatile\("cp\.async\.c[ag]\.shared\.global \[%0\], \[%1\], (\d+), %2;" ::"r"\((\w+)\), "l"\((\w+)\), "r"\((\w+)\) : "memory"\);',
      r'emu::cp_async(\2, \3, \1, \4);'),
-    (r'asm volatile\("cp\.async\.commit_group;" ::: "memory"\);', ';'),
-    (r'asm volatile\("cp\.async\.wait_group %0;" ::"n"\(\w+\) : "memory"\);', ';'),
+    (r'asm volatile\("cp\.async\.commit_group;" ::: "memory"\);', 'emu::cp_async_commit();'),
+    (r'asm volatile\("cp\.async\.wait_group %0;" ::"n"\((\w+)\) : "memory"\);', r'emu::cp_async_wait(\1);'),
     (r'asm volatile\("ld\.acquire\.sys\.global\.u64 %0, \[%1\];" : "=l"\((\w+)\) : "l"\((\w+)\) : "memory"\);', r'\1 = emu::ld_acquire(\2);'),
     (r'asm volatile\("st\.release\.sys\.global\.u64 \[%0\], %1;" ::"l"\((\w+)\), "l"\((\w+)\) : "memory"\);', r'emu::st_release(\1, \2);'),
 ]

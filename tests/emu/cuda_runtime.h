@@ -2,7 +2,8 @@
 // kernels' CUDA C++ SOURCE for the host, so their index / mask / ownership / ordering logic can be checked on a machine
 // without a GPU (tests/test_emu_*.py).  Execution model: every thread of a CTA is a fiber (ucontext) on one host
 // thread; fibers run until they reach a barrier -- every warp shuffle, __syncwarp and __syncthreads is one -- which is
-// all the lockstep these kernels rely on.  CTAs are spread over a few host threads.  Arithmetic is IEEE with
+// all the lockstep these kernels rely on.  CTAs are spread over a few host threads.  cp.async copies land as late as
+// PTX allows (at the wait_group that covers them), so a missing wait shows up as wrong data.  Arithmetic is IEEE with
 // contraction off (-ffp-contract=off) and fmaf for the explicit fused forms: the rounding sequence of the GPU build.
 #pragma once
 #include <ucontext.h>
@@ -111,8 +112,10 @@ inline void drop(Barrier &b) {           // a thread that exits no longer takes 
     --b.expected;
     if (b.expected > 0 && b.arrived == b.expected) release(b);
 }
+inline void cp_async_thread_exit();
 inline void trampoline() {
     blk->body(blk->arg);
+    cp_async_thread_exit();
     cur->done = true;
     ++blk->events;
     drop(*cur->warp);
@@ -249,10 +252,44 @@ inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)((const u
 
 namespace emu {
 // what the inline PTX of the kernels does, statement by statement (tests/emu/build_emu.py maps each asm to one of these)
+// cp.async is emulated as LATE as the PTX model allows: a copy lands only when a cp.async.wait_group covering its group
+// executes (until then the destination keeps its old bytes), so a kernel that reads a ring slot before waiting for it
+// fails the parity tests here too.  Groups are per thread, as in hardware.
+struct PendingCopy { unsigned dst; const void *src; int bytes, src_bytes; };
+struct AsyncState {
+    std::vector<std::vector<PendingCopy>> groups;     // committed groups, oldest first
+    std::vector<PendingCopy> open;                    // copies issued since the last commit
+};
+inline AsyncState &async_state() {
+    static thread_local std::vector<AsyncState> per_fiber;            // indexed by the fiber's slot in its CTA
+    const size_t id = (size_t)(cur - blk->fibers.data());
+    if (per_fiber.size() <= id) per_fiber.resize(id + 1);
+    return per_fiber[id];
+}
+inline void land(const PendingCopy &c) {
+    unsigned char *d = blk->smem + c.dst;
+    std::memset(d, 0, c.bytes);
+    if (c.src_bytes > 0) std::memcpy(d, c.src, std::min(c.bytes, c.src_bytes));
+}
 inline void cp_async(unsigned dst, const void *src, int bytes, int src_bytes) {
-    unsigned char *d = blk->smem + dst;
-    std::memset(d, 0, bytes);
-    if (src_bytes > 0) std::memcpy(d, src, std::min(bytes, src_bytes));
+    async_state().open.push_back(PendingCopy{dst, src, bytes, src_bytes});
+}
+inline void cp_async_commit() {
+    AsyncState &a = async_state();
+    a.groups.push_back(std::move(a.open));
+    a.open.clear();
+}
+inline void cp_async_wait(int newest_allowed_pending) {
+    AsyncState &a = async_state();
+    while ((int)a.groups.size() > newest_allowed_pending) {
+        for (const PendingCopy &c : a.groups.front()) land(c);
+        a.groups.erase(a.groups.begin());
+    }
+}
+inline void cp_async_thread_exit() {                  // a thread that ends leaves nothing behind for the fiber slot's next user
+    AsyncState &a = async_state();
+    a.groups.clear();
+    a.open.clear();
 }
 inline unsigned long long ld_acquire(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void st_release(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }

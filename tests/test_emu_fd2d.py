@@ -6,8 +6,9 @@ interior-vs-careful split and the special-strip lists, PML / TFSF / source cells
 running DFT carried with the rows, row slabs with ghost rows, lazy Ez, checkpoint / restore.
 
 Test infrastructure only -- the product path is the sm_100a build and has no CPU fallback; tests/test_gpu_fd2d.py
-runs these and many more cases on the device.  What the emulator cannot see: timing, memory-ordering races between
-warps (every cp.async completes at once, CTAs of one launch interleave only at barriers)."""
+runs these and many more cases on the device.  The emulator completes a cp.async only when a wait_group covering it executes, so the
+ring discipline is checked too; what it cannot see is timing and memory-ordering races between warps (CTAs of one launch
+interleave only at barriers)."""
 import numpy as np
 import pytest
 
