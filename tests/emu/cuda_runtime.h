@@ -257,7 +257,9 @@ namespace emu {
 // fails the parity tests here too.  Groups are per thread, as in hardware.
 struct PendingCopy { unsigned dst; const void *src; int bytes, src_bytes; };
 struct AsyncState {
-    std::vector<std::vector<PendingCopy>> groups;     // committed groups, oldest first
+    static constexpr int CAP = 32;                    // committed groups a thread may have in flight
+    std::vector<PendingCopy> ring[CAP];               // committed groups (circular, oldest at head); capacity is kept
+    int head = 0, count = 0;
     std::vector<PendingCopy> open;                    // copies issued since the last commit
 };
 inline AsyncState &async_state() {
@@ -274,21 +276,26 @@ inline void land(const PendingCopy &c) {
 inline void cp_async(unsigned dst, const void *src, int bytes, int src_bytes) {
     async_state().open.push_back(PendingCopy{dst, src, bytes, src_bytes});
 }
-inline void cp_async_commit() {
-    AsyncState &a = async_state();
-    a.groups.push_back(std::move(a.open));
-    a.open.clear();
-}
 inline void cp_async_wait(int newest_allowed_pending) {
     AsyncState &a = async_state();
-    while ((int)a.groups.size() > newest_allowed_pending) {
-        for (const PendingCopy &c : a.groups.front()) land(c);
-        a.groups.erase(a.groups.begin());
+    while (a.count > newest_allowed_pending) {
+        for (const PendingCopy &c : a.ring[a.head]) land(c);
+        a.ring[a.head].clear();
+        a.head = (a.head + 1) % AsyncState::CAP;
+        --a.count;
     }
+}
+inline void cp_async_commit() {
+    AsyncState &a = async_state();
+    if (a.count == AsyncState::CAP) cp_async_wait(AsyncState::CAP - 1);     // (hardware has its own limit; never reached here)
+    a.ring[(a.head + a.count) % AsyncState::CAP].swap(a.open);
+    ++a.count;
+    a.open.clear();
 }
 inline void cp_async_thread_exit() {                  // a thread that ends leaves nothing behind for the fiber slot's next user
     AsyncState &a = async_state();
-    a.groups.clear();
+    for (auto &g : a.ring) g.clear();
+    a.head = a.count = 0;
     a.open.clear();
 }
 inline unsigned long long ld_acquire(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
