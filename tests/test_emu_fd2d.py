@@ -308,3 +308,22 @@ def test_emulated_device_cylinder_rasteriser(emu):
     md = fd2d.dielectric(nx, ny, npml, rgrid, surface.DT, 30.0, 0.30, np.float32, device="cpu")
     naz, nbz = surface.dielectric_cylinder(nx, ny, npml, rgrid, surface.DT, 30.0, 0.30, np.float32)
     assert md.naz.numpy().tobytes() == naz.tobytes() and md.nbz.numpy().tobytes() == nbz.tobytes()
+
+
+def test_plain_c_host_runs_against_the_emulated_library(tmp_path):
+    """examples/c_host_3_3.c -- a C main() shaped like the reference's fd2d/cuda/test_3_3.cu, calling nothing but the C
+    ABI of include/fdtd_b200.h -- linked against the emulated build: the reference-named step functions in a loop and
+    one fused fdtd2d_advance give identical bytes (the program's own check), without a GPU."""
+    import os
+    import subprocess
+    from tests.emu import build_emu
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = build_emu.build_library()
+    exe = tmp_path / "c_host_3_3_emu"
+    subprocess.run(["gcc", "-Wall", "-O1", os.path.join(root, "examples", "c_host_3_3.c"), "-I", os.path.join(root, "include"),
+                    so, "-lm", "-lstdc++", "-pthread", "-o", str(exe)], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(so) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([str(exe), "120", "200", "40", "8"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "identical bytes" in r.stdout
+
