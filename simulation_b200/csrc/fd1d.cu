@@ -404,7 +404,15 @@ int advance1d(const fdtd1d_problem *q, int cur, int nsteps, const double *src, i
     // vector accesses need 16-byte aligned arrays; a warp's first staged cell is a whole number of vectors into the line
     int done = 0;
     while (done < nsteps) {
-        const int T = min(min(tblock, Shape::TMAX), nsteps - done);
+        int T = min(min(tblock, Shape::TMAX), nsteps - done);
+        {
+            // The right-hand ABC reads ex[nx-2] after every sub-step.  When the segments leave the last warp exactly one
+            // cell (nx-1 a multiple of the segment length), ex[nx-2] is that warp's innermost halo cell, valid for
+            // halo-1 sub-steps only -- one fewer than the pass takes if T is a whole number of vectors.  Take one step
+            // less in this pass (the halo and the segment length stay as they are).
+            const int halo_T = ((T + Shape::VEC - 1) / Shape::VEC) * Shape::VEC, use_T = Shape::W - 2 * halo_T;
+            if ((q->flags & FDTD_ABC) && T > 1 && halo_T == T && q->nx > use_T && (q->nx - 1) % use_T == 0) --T;
+        }
         LineParams<real> lp;
         for (int f = 0; f < 5; ++f) {
             lp.in[f] = (const real *)q->state[cur][f];

@@ -74,6 +74,18 @@ def test_emulated_per_step_path_with_the_fourier_kernel(emu):
     _run(emu, "2_3", 300, 25, np.float32, 8, dft=True, fused_dft=False)
 
 
+@pytest.mark.parametrize("dtype,tblock", [(np.float32, 32), (np.float64, 16), (np.float32, 4), (np.float64, 10)])
+def test_emulated_last_warp_owning_one_cell(emu, dtype, tblock):
+    """Found by tools/fuzz_emulated_1d.py: when nx-1 is a multiple of the segment length the last warp owns cell nx-1
+    alone and the right-hand ABC's ex[nx-2] is its innermost halo cell -- one sub-step short of a pass whose depth is a
+    whole number of vectors.  (nx below: 3 / 6 / 2 / 5 whole segments + 1.)"""
+    vec, w = (4, 512) if dtype == np.float32 else (2, 256)
+    halo = -(-tblock // vec) * vec
+    nx = (w - 2 * halo) * {32: 3, 16: 6, 4: 2, 10: 5}[tblock] + 1
+    for prog in ("1_2", "1_5", "2_3"):
+        _run(emu, prog, nx, 2 * tblock + 7, dtype, tblock, dft=False)
+
+
 def test_emulated_tiny_lines(emu):
     for nx in (3, 4, 17):
         _run(emu, "1_2", nx, 40, np.float64, 5, dft=False)

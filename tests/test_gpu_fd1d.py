@@ -118,6 +118,30 @@ def test_baseline_config_2_long_lossy_line():
         assert b.get(n).tobytes() == getattr(p, n).tobytes(), n
 
 
+@pytest.mark.parametrize("dtype,tblock", [(np.float32, 32), (np.float64, 16), (np.float32, 4), (np.float64, 10)])
+def test_last_warp_owning_one_cell(dtype, tblock):
+    """nx-1 a multiple of the segment length: the last warp owns cell nx-1 alone and the right-hand ABC's ex[nx-2] is its
+    innermost halo cell (found by tools/fuzz_emulated_1d.py on the CPU emulator; non-zero state up to the line's end)."""
+    vec, w = (4, 512) if dtype == np.float32 else (2, 256)
+    halo = -(-tblock // vec) * vec
+    nx = (w - 2 * halo) * {32: 3, 16: 6, 4: 2, 10: 5}[tblock] + 1
+    ns = 2 * tblock + 7
+    for prog in ("1_2", "1_5", "2_3"):
+        p, src = cases.line_program(prog, nx, ns, dtype)
+        p.freqs = None
+        sim = _sim_for(prog, nx, dtype, tblock=tblock)
+        rng = np.random.default_rng(4)
+        names = ["ex", "hy", "bc"] + (["dx", "ix"] if p.form == "flux" else []) + (["sx"] if sim.debye else [])
+        for n in names:
+            a = getattr(p, n)
+            a[...] = rng.uniform(-1, 1, a.shape).astype(dtype)
+            sim.set(n, a)
+        sim.advance(ns)
+        orc.advance_1d(p, src)
+        for n in names:
+            assert sim.get(n).tobytes() == getattr(p, n).tobytes(), (prog, n)
+
+
 def test_tiny_lines():
     for nx in (3, 4, 17):
         sim = _sim_for("1_2", nx, np.float64)
