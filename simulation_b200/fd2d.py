@@ -322,7 +322,8 @@ class Fdtd2D:
             a = a[self.row_base:self.row_base + self.rows_alloc]
         if a.shape != (self.rows_alloc, self.ny):
             raise _lib.FdtdError(f"coefficient array has shape {a.shape}, expected {(self.rows_alloc, self.ny)}")
-        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        return t if t.data_ptr() % 16 == 0 else t.clone()      # (a row slice of a host array shared without a copy)
 
     def _owned(self, t: torch.Tensor) -> torch.Tensor:
         o = self.row_lo - self.row_base
@@ -637,9 +638,9 @@ class Fdtd2D:
                 if hi_all - edges[-1] < 2 * least:
                     break
                 edges.append(min(edges[-1] + max(int(h), least), hi_all - least))
-            edges[-1] = hi_all
             if len(edges) == 1:
-                edges.append(hi_all)
+                edges.append(hi_all)                     # a grid too short to cut: one block
+            edges[-1] = hi_all
         elif block_rows:                                 # one block height (the last block takes the remainder)
             edges = list(range(lo_all, hi_all, max(int(block_rows), least))) + [hi_all]
             if len(edges) > 2 and edges[-1] - edges[-2] < least:

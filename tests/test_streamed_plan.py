@@ -113,6 +113,8 @@ CONFIGS = [
     (1030, 0, 12, {"block_rows": 1024}),                                    # remainder shorter than a pass allows
     (496, 252, 48, {"blocks": 4, "streams": 3}),                            # slab test geometry
     (700, 0, 7, {"blocks": 2, "tblock": 4}),
+    (47, 0, 10, {"block_rows": [26, 19, 12, 102]}),                         # too short to cut (found by tools/fuzz_emulated_2d_modes.py)
+    (45, 0, 13, {"block_rows": [60, 111], "schedule": "wavefront"}),
     (4096, 0, 600, {}),                                                     # long run on a short grid: falls back to the wavefront
     (9000, 0, 61, {"tblock": 1, "streams": 16, "block_rows": 700}),
 ]
