@@ -24,7 +24,7 @@ emu = device.install(mp)
 t_end, n, bad = time.time() + budget, 0, 0
 STATE = ("dz", "hx", "hy", "ihx", "ihy")
 while time.time() < t_end:
-    mode = str(rng.choice(["dft", "slab", "random_state", "p2p", "streamed"]))
+    mode = str(rng.choice(sys.argv[3].split(",") if len(sys.argv) > 3 else ["dft", "slab", "random_state", "p2p", "streamed"]))
     dtype = np.float32 if rng.random() < 0.7 else np.float64
     nx, ny = int(rng.integers(40, 260)), int(rng.integers(40, 420))
     npml = int(rng.integers(2, min(nx, ny) // 2 - 8))
@@ -38,6 +38,18 @@ while time.time() < t_end:
             g, src = cases.grid_program("3_4", nx, ny, ns, dtype, npml=npml, radius=radius, dft=True)
             sim = fd2d.Fdtd2D(nx, ny, npml, dtype, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)),
                               naz=g.naz.copy(), nbz=g.nbz.copy(), freqs=g.freqs, device="cpu")
+            if rng.random() < 0.7:                       # signal at every strip / chunk boundary from the first step on
+                import torch
+                for name in STATE + ("iz",):
+                    a = rng.standard_normal((nx, ny)).astype(dtype)
+                    if name == "iz":
+                        a = np.where(g.nbz != 0, a, 0).astype(dtype)      # iz lives where the medium is lossy
+                    sim.set(name, a)
+                    getattr(g, name)[...] = a
+                for name in ("r_pt", "i_pt", "r_in", "i_in"):
+                    a = getattr(g, name)
+                    a[...] = rng.standard_normal(a.shape).astype(dtype)
+                    getattr(sim.ft, name).copy_(torch.from_numpy(a.reshape(tuple(getattr(sim.ft, name).shape))))
             cut = int(rng.integers(0, ns + 1))
             sim.advance(cut, tblock=tb or None)
             sim.advance(ns - cut, tblock=tb or None)
@@ -57,6 +69,14 @@ while time.time() < t_end:
             slabs = [_sim_for(prog, nx, ny, dtype, npml=npml, radius=0.15, rows=(int(lo), int(hi)), ghost=T, tblock=T, device="cpu")
                      for lo, hi in zip(cuts[:-1], cuts[1:])]
             names = STATE + (("iz",) if prog == "3_4" else ())
+            init = {}
+            if rng.random() < 0.7:                       # non-zero state everywhere: the slab boundaries carry signal at once
+                g0, _ = cases.grid_program(prog, nx, ny, 1, dtype, npml=npml, radius=0.15, dft=False)
+                for k in names:
+                    a = rng.standard_normal((nx, ny)).astype(dtype)
+                    init[k] = np.where(g0.nbz != 0, a, 0).astype(dtype) if k == "iz" else a
+                    for s in slabs:
+                        s.set(k, init[k])                # whole-grid array: owned and ghost rows
             for _ in range(nblocks):
                 for s in slabs:
                     s.advance(T, lazy_ez=True)
@@ -68,6 +88,8 @@ while time.time() < t_end:
                 s.advance(1)
             ns = nblocks * T + 1
             g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=0.15, dft=False)
+            for k, a in init.items():
+                getattr(g, k)[...] = a
             orc.advance_2d(g, src)
             for k in names + ("ez",):
                 assert np.concatenate([s.get(k) for s in slabs]).tobytes() == getattr(g, k).tobytes(), k
@@ -90,11 +112,21 @@ while time.time() < t_end:
                                                          "sets": [{k: slabs[q]._sets[i][k].data_ptr() for k in names} for i in range(2)]}
                 s.p2p = {"halo": T, "sync": type("W", (), {"ptr": words[r].ctypes.data})(),
                          "up": peer(r - 1 if r > 0 else None), "dn": peer(r + 1 if r < nslab - 1 else None)}
+            init = {}
+            if rng.random() < 0.7:
+                g0, _ = cases.grid_program(prog, nx, ny, 1, dtype, npml=npml, radius=0.15, dft=False)
+                for k in names:
+                    a = rng.standard_normal((nx, ny)).astype(dtype)
+                    init[k] = np.where(g0.nbz != 0, a, 0).astype(dtype) if k == "iz" else a
+                    for s in slabs:
+                        s.set(k, init[k])
             for epoch in range(1, nblocks + 1):
                 for r in rng.permutation(nslab):
                     slabs[int(r)].advance(T, tblock=T, lazy_ez=epoch < nblocks, epoch=epoch)
             ns = nblocks * T
             g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=0.15, dft=False)
+            for k, a in init.items():
+                getattr(g, k)[...] = a
             orc.advance_2d(g, src)
             for k in names + ["ez"]:
                 assert np.concatenate([s.get(k) for s in slabs]).tobytes() == getattr(g, k).tobytes(), k
