@@ -130,7 +130,14 @@ def build(*source_names: str) -> str:
         + open(os.path.join(ROOT, "include", "fdtd_b200.h")).read() + open(__file__).read()
     tag = hashlib.sha256(("".join(srcs.values()) + hdr).encode()).hexdigest()[:16]
     bdir = os.path.join(HERE, "_build")
-    os.makedirs(bdir, exist_ok=True)
+    try:
+        os.makedirs(bdir, exist_ok=True)
+        if not os.access(bdir, os.W_OK):
+            raise OSError("not writable")
+    except OSError:                                      # a read-only checkout: build beside the system's temp files
+        import tempfile
+        bdir = os.path.join(tempfile.gettempdir(), "fdtd_b200_emu_build")
+        os.makedirs(bdir, exist_ok=True)
     stem = "_".join(os.path.splitext(n)[0] for n in source_names)
     so = os.path.join(bdir, f"emu_{stem}_{tag}.so")
     if os.path.exists(so):
