@@ -1,25 +1,32 @@
 #!/usr/bin/env python
 """Benchmark of the 2D TM+PML time-stepping hot path (BASELINE.json metric: Mcell-updates/s and HBM GB/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one full FDTD time step (D, E, Hx, Hy and both PML integrals of every cell).  Workload at
-N GPUs: BASELINE config 5 weak-scaled -- every GPU owns a 32768 x 32768 fp32 row slab of an
-(N*32768) x 32768 grid with npml=80 and the point sinusoid of program 3_2, ghost rows exchanged over
-NVLink every time block.  One JSON line on stdout (rank 0).
+N GPUs: BASELINE config 5 -- a 32768-column fp32 grid with npml=80 and the point sinusoid of program 3_2, cut into
+row slabs, ghost rows exchanged over NVLink every time block.  Default (--scaling weak): every GPU owns 32768 rows of
+an (N*32768) x 32768 grid; --scaling strong: ONE 32768 x 32768 grid over the N GPUs (BASELINE.json configs[4] as
+worded).  At N > 1 the weak run also measures the strong split and reports it under "configs".  One JSON line on
+stdout (rank 0).
+
+At N > 1 the line carries "parity_check": before the timed region the N ranks run a small slab problem with the
+kernels and launch plan of the bench (4-wide vectors, 128-row chunks, fused peer-store halo exchange) and every rank
+compares its rows of all six arrays, byte for byte, with a single-device run of the same problem; a mismatch exits
+non-zero.
 
 --impl reference times the REFERENCE's own C/OpenMP step functions (oracle/_ref, compiled from
-/root/reference/fd2d/clang/test_3_2.c; falls back to the numpy oracle port when absent) on all host cores,
-on a bounded sample of the same workload.  The oracle is used only there and in the cpu_baseline leg --
-never on the measured GPU path.
+/root/reference/fd2d/clang/test_3_2.c; falls back to the numpy oracle port when absent) on all host cores, on the
+full 32768 x 32768 grid when the host has the memory for it (28 GiB), else on an 8192 x 8192 sample.  The oracle is
+used only there and in the cpu_baseline leg -- never on the measured GPU path.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import time
 
@@ -31,8 +38,10 @@ sys.path.insert(0, ROOT)
 N_FULL = 32768
 NPML = 80
 BYTES_PER_CELL_UPDATE = 48          # dz,hx,hy,ihx,ihy R+W; naz R; ez W (fp32) -- SURVEY.md 8(d)
+BYTES_LOSSY = 60                    # + iz R+W, nbz R (program 3_4, DFT off)
+BYTES_1D_LOSSY = 24                 # ex,hy R+W; ca,cb R
 METRIC = "Mcell-updates/s, 2D TM+PML fp32"
-E2E_REPEATS = 3                     # the end-to-end job is a single ~0.15 s shot whose overlap depends on launch timing: median of 3
+E2E_REPEATS = 3                     # the end-to-end job is a single ~0.1 s shot whose overlap depends on launch timing: median of 3
 
 
 def peaks():
@@ -43,7 +52,7 @@ def peaks():
 
 
 def measured_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    """DRAM bytes per pass of the dominant kernel from the committed ncu --set full captures, by pass depth."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
@@ -53,9 +62,21 @@ def measured_traffic():
     return None
 
 
+def traffic_for(depth):
+    """-> (bytes per pass of 32768^2 cells at this depth or None, provenance string)"""
+    t = measured_traffic()
+    if not t:
+        return None, "no committed ncu capture"
+    per = t.get("by_depth", {}).get(str(depth))
+    if per is None and depth == 6 and "dram_bytes_per_launch" in t:
+        per = {"dram_bytes_per_pass": t["dram_bytes_per_launch"], "source": t.get("source", "profiles/roofline_traffic.json")}
+    if per is None:
+        return None, f"no ncu capture for pass depth {depth} in profiles/roofline_traffic.json"
+    return float(per["dram_bytes_per_pass"]), "from profile " + per.get("source", "?") + ", commit " + str(per.get("commit", t.get("commit", "?")))
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (5 ms period),
-    falling back to an `nvidia-smi -lms` subprocess when pynvml is unavailable."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (5 ms period)."""
     BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index):
@@ -126,6 +147,16 @@ def pin_to_gpu_numa_node(index):
         return None
 
 
+def host_mem_available_gib():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 2**20
+    except Exception:
+        pass
+    return 0.0
+
+
 # ------------------------------------------------------------------------------------ CPU legs
 def cpu_numpy_port(n, steps):
     """The numpy oracle (bit-identical restatement of fd2d/program/fd2d_3_2.py) on one core."""
@@ -140,11 +171,29 @@ def cpu_numpy_port(n, steps):
     return n * n * steps / dt / 1e6, dt
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: ASSIGN the variable before libgomp reads it, set the count
+    through the OpenMP API as well, and return what the runtime will really use (omp_get_max_threads)."""
+    import ctypes as C
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    try:
+        gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+        gomp.omp_set_dynamic(0)
+        gomp.omp_set_num_threads(cores)
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return cores
+
+
 def cpu_reference_c(nx, ny, steps, warm=1):
-    """The reference's own C/OpenMP dfield/efield/hfield (oracle/_ref/libref_fd2d_3_2.so), all host threads."""
+    """The reference's own C/OpenMP dfield/efield/hfield (oracle/_ref/libref_fd2d_3_2.so), all host threads.
+    -> (Mcell/s, seconds, OpenMP threads used)"""
     import ctypes as C
     from oracle import fdtd_oracle as orc
     from oracle import ref_c
+    threads = use_all_host_threads()
     lib = ref_c.load("3_2")
     g = orc.Grid2D(nx, ny, NPML, np.float32, point=(nx // 2 - 5, ny // 2 - 5))
     ps = ref_c.pml_struct(g.pml)
@@ -160,47 +209,125 @@ def cpu_reference_c(nx, ny, steps, warm=1):
     for t in range(warm + 1, warm + steps + 1):
         one(t)
     dt = time.perf_counter() - t0
-    return nx * ny * steps / dt / 1e6, dt
+    return nx * ny * steps / dt / 1e6, dt, threads
 
 
 def run_reference(args, emit=print):
-    """--impl reference: rank 0 only; a bounded sample (8192 x 8192 of the 32768 x 32768 workload) per step."""
+    """--impl reference: rank 0 only.  The full 32768 x 32768 grid of the GPU arm's N=1 workload (28 GiB of host
+    arrays) when the host has the memory, else an 8192 x 8192 sample of it; the step count is capped so that the run
+    ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import ref_c
-    cores = os.cpu_count() or 1
-    n = 8192
-    steps, warm = max(1, args.steps), max(1, args.warmup)
-    # keep the whole run within a few minutes whatever K the driver asks for
-    steps, warm = min(steps, 40), min(warm, 3)
+    steps, warm = min(max(1, args.steps), 40), min(max(1, args.warmup), 3)
+    n = args.size
+    have = host_mem_available_gib()
+    need = 7 * n * n * 4 / 2**30 * 1.15
+    why = ""
+    if have and have < need:
+        why = f" (host has {have:.0f} GiB available, the {n}x{n} grid needs {need:.0f})"
+        n = 8192
     if ref_c.available("3_2"):
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        v, dt = cpu_reference_c(n, n, steps, warm)
+        v, dt, cores = cpu_reference_c(n, n, steps, warm)
         kind, how = "reference", "reference C/OpenMP step functions (fd2d/clang/test_3_2.c) via oracle/_ref"
     else:
-        n, steps = 4096, min(steps, 10)
+        n, steps = min(n, 4096), min(steps, 10)
         v, dt = cpu_numpy_port(n, steps)
         cores, kind, how = 1, "port", "numpy oracle port (oracle/_ref not built)"
-    sample = f"{n}x{n} fp32 sub-grid of the {N_FULL}x{N_FULL} workload, {steps} steps after {warm} warm-up; {how}"
+    same = n == N_FULL
+    sample = (f"the whole {n}x{n} fp32 grid" if same else f"{n}x{n} fp32 sub-grid of the {N_FULL}x{N_FULL} workload{why}") + \
+        f", {steps} steps after {warm} warm-up, {cores} OpenMP threads (omp_get_max_threads; host has {os.cpu_count()} CPUs); {how}"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mcell-updates/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"fd2d TM+PML {N_FULL}x{N_FULL} fp32 npml={NPML} point sinusoid (BASELINE config 5)",
-                       "sample": sample},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fd2d TM+PML {N_FULL}x{N_FULL} fp32 npml={NPML} point sinusoid 1500 MHz (BASELINE config 5)",
+                       "grid": [n, n], "same_config": same, "sample": sample,
+                       "note": "the CPU arm always runs the one-GPU grid: at N > 1 the GPU arm's weak-scaled grid "
+                               "(N x 28 GiB of host arrays) does not fit a host, and throughput per cell does not depend on it"},
             "cpu_baseline": {"value": v, "unit": "Mcell-updates/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def _timed(fn, sync, world):
+    """CUDA events on the launch stream around fn(), barrier + synchronize on both sides, max over ranks -> ms"""
+    import torch
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    fn()
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def parity_check(world, rank, T):
+    """N-rank slab run (fused peer-store halo exchange, the bench's kernels: 4-wide vectors, 128-row chunks, depth T)
+    against a single-device run of the same problem on EVERY rank's own GPU: the rank's rows of all six arrays must
+    be byte-identical.  -> dict for the JSON line (rank 0) / None; raises SystemExit on mismatch (all ranks)."""
+    import torch
+    import torch.distributed as dist
+    from simulation_b200 import _lib, fd2d, slab, surface
+    nx, ny, npml, ns = 1024 * world, 1536, 40, 61
+    rng = np.random.default_rng(20261018)
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)      # random medium: every cell matters
+    src = fd2d.PointSource(nx // 2 - 5, ny // 2 - 5, surface.Sinusoid(1500e6), hard=True)
+    _lib.lib().fdtd2d_tune(4, 128, 0, 0, 0)                              # the >= 100 M-cell launch plan, on a small grid
+    try:
+        s = slab.SlabFdtd2D(nx, ny, npml, np.float32, tblock=T, source=src, naz=naz, halo="p2p")
+        s.advance(7)                       # ragged split: several calls, several epochs of the flag handshake
+        s.advance(ns - 7)
+        s.synchronize()
+        one = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=src, naz=naz, tblock=T)
+        one.advance(ns)
+        one.synchronize()
+        names = ("dz", "ez", "hx", "hy", "ihx", "ihy")
+        h, equal, peak = hashlib.sha256(), True, 0.0
+        for name in names:
+            mine = s.tensor(name).contiguous()
+            ref = one.tensor(name)[s.row_lo:s.row_hi].contiguous()
+            same = torch.equal(mine.view(torch.int32), ref.view(torch.int32))     # bit view: -0.0 != +0.0
+            equal = equal and bool(same)
+            h.update(mine.cpu().numpy().tobytes())
+            if name == "ez":
+                peak = float(ref.abs().max().item())
+        mode, exchanges = s.halo_mode, s.exchanges
+        digests = [None] * world
+        dist.all_gather_object(digests, (bool(equal), h.hexdigest(), peak))
+        s.close()
+        del s, one
+    finally:
+        _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
+    all_equal = all(d[0] for d in digests)
+    out = {"ranks": world, "halo": mode, "equal": bool(all_equal and mode == "p2p"), "grid": [nx, ny], "steps": ns,
+           "tblock": T, "plan": "V=4, 128-row chunks (fdtd2d_tune), random medium, point sinusoid",
+           "exchanges": exchanges, "arrays": list(names), "peak_abs_ez": max(d[2] for d in digests),
+           "against": "a single-device run of the same problem on every rank's own GPU, owned rows, bit view",
+           "sha256": hashlib.sha256("".join(d[1] for d in digests).encode()).hexdigest(),
+           "per_rank_equal": [d[0] for d in digests]}
+    if not out["equal"]:
+        if rank == 0:
+            sys.stderr.write("bench.py: N-GPU PARITY CHECK FAILED: " + json.dumps(out) + "\n")
+        raise SystemExit(3)
+    return out
+
+
 def run_ours(args, emit=print):
     # run_streamed (the e2e leg) drives one stream per pass level: give the driver enough hardware queues that they do
     # not alias (default 8).  Must be set before the CUDA context exists.
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    import gc
     import torch
     import torch.distributed as dist
-    from simulation_b200 import fd2d, surface
+    from simulation_b200 import _lib, fd2d, surface
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -215,54 +342,85 @@ def run_ours(args, emit=print):
     n, K, W, T = args.size, args.steps, args.warmup, args.tblock
     knobs = ("FDTD_FORCE_V", "FDTD_CHUNK_ROWS", "FDTD_WARPS", "FDTD_RING", "FDTD_CAREFUL")
     if any(k in os.environ for k in knobs):                                                 # tuning sweeps only
-        from simulation_b200 import _lib
         _lib.lib().fdtd2d_tune(*[int(os.environ.get(k, "0")) for k in knobs])
-    nx_global = n * world                       # weak scaling: one n x n slab per GPU
-    wave = surface.Sinusoid(1500e6)
-    src = fd2d.PointSource(nx_global // 2 - 5, n // 2 - 5, wave, hard=True)
-
-    if world > 1:
-        from simulation_b200 import slab
-        sim = slab.SlabFdtd2D(nx_global, n, NPML, np.float32, source=src, tblock=T)
-        barrier = dist.barrier
-    else:
-        sim = fd2d.Fdtd2D(n, n, NPML, np.float32, source=src, tblock=T)
-        barrier = lambda: None
+    barrier = dist.barrier if world > 1 else (lambda: None)
 
     def sync():
         barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput: K steps, inputs already in HBM
-    sim.advance(W)
-    sync()
+    def release(sim):
+        if hasattr(sim, "close"):
+            sim.close()                          # unmap the peers before this rank's arrays are freed
+        del sim
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    # ---- N > 1: the ranks must agree with one device, bit for bit, before anything is timed
+    parity = parity_check(world, rank, T if T else 6) if (world > 1 and not args.no_parity) else None
+
+    wave = surface.Sinusoid(1500e6)
+    peak, peak_src = peaks()
+
+    def measure(nx_global, steps, warm):
+        """K steps device-resident on an nx_global x n grid cut into `world` row slabs -> (sim, ms, depths)"""
+        src = fd2d.PointSource(nx_global // 2 - 5, n // 2 - 5, wave, hard=True)
+        if world > 1:
+            from simulation_b200 import slab
+            sim = slab.SlabFdtd2D(nx_global, n, NPML, np.float32, source=src, tblock=T)
+        else:
+            sim = fd2d.Fdtd2D(nx_global, n, NPML, np.float32, source=src, tblock=T)
+        sim.advance(warm)
+        sync()
+        ms = _timed(lambda: sim.advance(steps), sync, world)
+        eng = getattr(sim, "engine", sim)
+        return sim, src, ms, eng.pass_depths(steps, T)
+
+    strong = args.scaling == "strong"
+    nx_global = n if strong else n * world
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    e0.record()
-    sim.advance(K)
-    e1.record()
-    sync()
-    ms = e0.elapsed_time(e1)
+    sim, src, ms, depths = measure(nx_global, K, W)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    launches = (K + T - 1) // T                  # passes; each pass = interior kernel + edge kernel
+    launches = len(depths)                       # passes; each pass = interior kernel + edge kernel
     cells = float(nx_global) * n
     value = cells * K / (ms * 1e-3) / 1e6
-    peak, peak_src = peaks()
-    per_gpu_cells = float(n) * n
+    per_gpu_cells = cells / world
     achieved = BYTES_PER_CELL_UPDATE * per_gpu_cells * K / (ms * 1e-3) / 1e9      # per GPU, algorithmic GB/s
-    traffic = measured_traffic()
+    dmain = max(depths)
+    traffic, traffic_src = traffic_for(dmain)
+    dram_frac = None
+    if traffic is not None:
+        # real DRAM bytes (ncu, one pass over 32768^2 cells, scaled to this rank's cells) / time / measured copy peak
+        dram_frac = traffic * (per_gpu_cells / (float(N_FULL) * N_FULL)) * launches / (ms * 1e-3) / 1e9 / peak
+    halo_mode = getattr(sim, "halo_mode", "none")
 
     # ---- end to end through the public API with HOST buffers: naz up (pinned), K steps, ez down (pinned)
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(sim, world, rank, n, nx_global, K, T, src, sync)
+        e2e = run_e2e(sim, world, rank, n, nx_global, K, T, src, sync, release)
+    else:
+        release(sim)
+    sim = None
+
+    # ---- the other BASELINE configs, one short measurement each (same timing discipline)
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        if world > 1 and not strong:
+            s2, _, ms2, d2 = measure(n, K, W)                    # configs[4] as worded: ONE 32768^2 grid over the N GPUs
+            configs["c5_strong_32768_over_N"] = {
+                "value": float(n) * n * K / (ms2 * 1e-3) / 1e6, "unit": "Mcell-updates/s", "ms_per_step": ms2 / K,
+                "scaling": "strong", "grid": [n, n], "rows_per_gpu": n // world, "pass_depths": d2,
+                "halo_exchange": getattr(s2, "halo_mode", "none"),
+                "frac": BYTES_PER_CELL_UPDATE * float(n) * n / world * K / (ms2 * 1e-3) / 1e9 / peak,
+                "note": "frac = algorithmic 48 B x this GPU's cells x steps / time / measured copy peak"}
+            release(s2)
+        if rank == 0:
+            configs.update(other_configs(peak, sync=lambda: torch.cuda.synchronize()))
+        if world > 1:
+            dist.barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -274,47 +432,90 @@ def run_ours(args, emit=print):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"fd2d TM+PML {nx_global}x{n} fp32 npml={NPML} point sinusoid 1500 MHz "
-                                       f"(BASELINE config 5{'' if world == 1 else ', weak-scaled row slabs'})",
-                           "grid_per_gpu": [n, n], "tblock": T, "parallelism": f"slab{world}",
-                           "halo_exchange": getattr(sim, "halo_mode", "none"),
-                           "l2": "inputs (52 GB per GPU) far exceed the 126 MB L2; no flush needed",
+                                       f"(BASELINE config 5{'' if world == 1 else (', one grid over row slabs' if strong else ', weak-scaled row slabs')})",
+                           "grid_per_gpu": [nx_global // world, n], "tblock": T, "pass_depths": depths,
+                           "parallelism": f"slab{world}", "halo_exchange": halo_mode,
+                           "l2": "inputs (52 GB per GPU) far exceed the 126 MB L2; no flush needed" if per_gpu_cells >= 2**28
+                                 else "state per GPU exceeds the 126 MB L2 (>= 6 GB); no flush needed",
                            "timing": "CUDA events on the launch stream, barrier+sync both sides, max over ranks"},
                 "gpu_launches": 2 * launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
-                             "kernel": f"k_march<float,V=4,T={T},interior> (+ edge kernel)", "launches": launches,
-                             "avg_launch_ms": ms / launches,
-                             "algorithmic_bytes_per_launch": BYTES_PER_CELL_UPDATE * per_gpu_cells * T,
+                             "dram_frac": dram_frac, "traffic": traffic, "traffic_source": traffic_src,
+                             "kernel": f"k_march interior, fp32 V=4, pass depths {sorted(set(depths), reverse=True)} (+ edge kernel)",
+                             "launches": launches, "avg_launch_ms": ms / launches,
+                             "algorithmic_bytes_per_launch": BYTES_PER_CELL_UPDATE * per_gpu_cells * K / launches,
                              "peak_source": peak_src,
-                             "note": "achieved = 48 B x cells x steps / time; a T-step pass moves ~48 B per cell once, "
-                                     "so frac may exceed 1 (traffic = real DRAM bytes per launch from ncu)"},
+                             "note": "frac = 48 B x cells x steps / time / peak (SURVEY 8d): a T-step pass moves the state "
+                                     "through HBM once, so frac may exceed 1; dram_frac = real DRAM bytes per pass (ncu capture "
+                                     "named in traffic_source) x passes / time / peak -- the physical utilisation"},
                 "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu}
+        if parity is not None:
+            line["parity_check"] = parity
+        if configs:
+            line["configs"] = configs
         emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync):
+def other_configs(peak, sync):
+    """BASELINE configs 2 and 4 on one GPU (rank 0): device-resident, CUDA events, 3+ warm-up passes."""
+    import torch
+    from simulation_b200 import fd1d, fd2d, surface
+    out = {}
+
+    def timed(sim, steps, warm):
+        sim.advance(warm)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sim.advance(steps)
+        e1.record()
+        sync()
+        return e0.elapsed_time(e1)
+
+    # config 2: 1D lossy slab, 1e6 cells, soft sinusoid 700 MHz, ABC (SURVEY 8d)
+    nx, ns = 1_000_000, 10_000
+    ca, cb = surface.dielectric_fdtd(nx, surface.DT, 4.0, 0.04, np.float32, start=nx // 2, stop=nx // 2 + nx // 4)
+    line = fd1d.Fdtd1D(nx, np.float32, source=fd1d.LineSource(1, surface.Sinusoid(700e6)), ca=ca, cb=cb)
+    ms = timed(line, ns, 256)
+    out["c2_1d_lossy_1e6"] = {"value": nx * ns / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s", "ms_per_step": ms / ns,
+                              "steps": ns, "frac": BYTES_1D_LOSSY * nx * ns / (ms * 1e-3) / 1e9 / peak, "dram_frac": None,
+                              "note": "24 B per cell-update algorithmic; the 24 MB state lives in L2 and a pass is 32 steps, "
+                                      "so HBM is not the bound (instruction-bound, DESIGN 4.3)"}
+    del line
+    # config 4: 4096^2 TFSF plane wave + lossy dielectric cylinder (radius 6 m -> 599 cells), npml 80, DFT off
+    n, ns = 4096, 2000
+    md = fd2d.dielectric(n, n, NPML, int(6.0 / surface.DS - 1), surface.DT, 30.0, 0.30, np.float32)
+    grid = fd2d.Fdtd2D(n, n, NPML, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=md.naz, nbz=md.nbz)
+    ms = timed(grid, ns, 48)
+    out["c4_tfsf_lossy_4096"] = {"value": float(n) * n * ns / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s", "ms_per_step": ms / ns,
+                                 "steps": ns, "frac": BYTES_LOSSY * float(n) * n * ns / (ms * 1e-3) / 1e9 / peak, "dram_frac": None,
+                                 "pass_depths": sorted(set(grid.pass_depths(ns, None)), reverse=True),
+                                 "note": "60 B per cell-update algorithmic (iz R+W, nbz R on top of 48); the 0.4 GB state is "
+                                         "3x the L2, launches are a few waves"}
+    del grid, md
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync, release):
     """Same metric through the user-facing call with host buffers: upload the medium (naz) from pinned host
     memory, run K steps, read Ez back into pinned host memory; all inside the timed region.  N > 1: every rank runs
-    the same block wavefront on its slab with a K-row ghost band that is consumed instead of exchanged
+    the same block schedule on its slab with a K-row ghost band that is consumed instead of exchanged
     (communication-avoiding: K steps, no exchange; SlabFdtd2D.run_streamed)."""
-    import gc
     import torch
     import torch.distributed as dist
     if world > 1:
         from simulation_b200 import slab
-        sim.close()                                  # unmap the peers before this rank's arrays are freed
-        del sim
-        gc.collect()
-        torch.cuda.empty_cache()
+        release(sim)
         sim = slab.SlabFdtd2D(nx_global, n, NPML, np.float32, source=src, tblock=T, ghost=K, halo="nccl")
         stored = sim.engine.rows_alloc
     else:
-        stored = n
+        stored = nx_global
     rows = sim.row_hi - sim.row_lo
     host_naz = torch.ones((stored, n), dtype=torch.float32).pin_memory()
     host_ez = torch.empty((rows, n), dtype=torch.float32).pin_memory()
@@ -325,7 +526,7 @@ def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync):
         sim.t = 0
     sim.run_streamed(K, host_naz, host_ez)                         # untimed warm-up of the same call: every pass-level stream is
                                                                    # created and used once (a stream's first use costs tens of ms)
-    runs = []
+    runs, mine = [], []
     for _ in range(E2E_REPEATS):                                   # the whole job, E2E_REPEATS times; the median is reported
         fresh()                                                    # fresh problem: fields start at zero
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -335,21 +536,34 @@ def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync):
         e1.record()
         sync()
         dt = e0.elapsed_time(e1) * 1e-3
+        mine.append(dt)
         if world > 1:
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         runs.append(dt)
     dt = float(np.median(runs))
-    return {"value": float(nx_global) * n * K / dt / 1e6, "unit": "Mcell-updates/s",
-            "h2d_bytes_per_step": stored * n * 4 / K, "d2h_bytes_per_step": rows * n * 4 / K,
-            "runs_ms": [round(x * 1e3, 2) for x in runs],
-            "what": f"pinned naz H2D ({stored * n * 4 / 2**30:.1f} GiB/GPU) + {K} steps + pinned Ez D2H, CUDA events on the launch "
-                    f"stream, max over ranks; run_streamed: row blocks uploaded in order (512..3072 rows), every block stepped through "
-                    f"all its passes as soon as it has arrived (skewed space-time tiling), one stream per pass level, Ez of "
-                    f"finished blocks downloaded behind the stepping (after one untimed run of the same call); "
-                    f"median of {E2E_REPEATS} whole jobs (runs_ms)"
-                    + ("" if world == 1 else f"; per rank a {K}-row ghost band consumed instead of exchanged (no communication in {K} steps)")}
+    h2d, d2h = stored * n * 4, rows * n * 4
+    # what limits it: every rank's own PCIe rate during its median run (its bytes each way / its own time)
+    rate = (h2d + d2h) / float(np.median(mine)) / 1e9
+    rates = [rate]
+    if world > 1:
+        rates = [None] * world
+        dist.all_gather_object(rates, rate)
+    out = {"value": float(nx_global) * n * K / dt / 1e6, "unit": "Mcell-updates/s",
+           "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+           "runs_ms": [round(x * 1e3, 2) for x in runs],
+           "pcie_gbs_per_rank": [round(float(r), 1) for r in rates],
+           "pcie_bound_ms": round(max(h2d, d2h) / 55e9 * 1e3, 1),
+           "what": f"pinned naz H2D ({h2d / 2**30:.1f} GiB/GPU) + {K} steps + pinned Ez D2H, CUDA events on the launch "
+                   f"stream, max over ranks; run_streamed: row blocks uploaded in order (512..3072 rows), every block stepped through "
+                   f"all its passes as soon as it has arrived (skewed space-time tiling), one stream per pass level, Ez of "
+                   f"finished blocks downloaded behind the stepping (after one untimed run of the same call); "
+                   f"median of {E2E_REPEATS} whole jobs (runs_ms); pcie_gbs_per_rank = (H2D + D2H bytes) / the rank's own time, "
+                   f"pcie_bound_ms = one direction at the 55 GB/s measured on these boxes"
+                   + ("" if world == 1 else f"; per rank a {K}-row ghost band consumed instead of exchanged (no communication in {K} steps)")}
+    release(sim)
+    return out
 
 
 def main():
@@ -375,10 +589,14 @@ def _main(emit):
     ap.add_argument("--steps", type=int, default=96)
     ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=N_FULL, help="rows and columns per GPU (default: BASELINE config 5)")
-    ap.add_argument("--tblock", type=int, default=6)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 32768 rows per GPU; strong: one 32768 x 32768 grid over the N GPUs")
+    ap.add_argument("--size", type=int, default=N_FULL, help="rows (per GPU when weak) and columns (default: BASELINE config 5)")
+    ap.add_argument("--tblock", type=int, default=0, help="pass depth (0: chosen by grid size and step count)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of BASELINE configs 2, 4 and the strong split")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-GPU parity check (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

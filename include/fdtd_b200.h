@@ -199,9 +199,10 @@ typedef struct {
      * ghost rows through peer-mapped pointers (cudaIpcOpenMemHandle), row by row while it computes, and the last
      * warp of the pass publishes `epoch` in the neighbours' sync words; the first pass of the next call spins on
      * its own sync words until both neighbours have published epoch-1.  peer_up / peer_dn: the neighbours' two
-     * array sets (entries NULL where there is no neighbour); *_base: global row of their array row 0; sync_*: four
-     * zero-initialised 64-bit words per rank {from_up, from_down, counter, counter}; epoch: 1, 2, ... per call,
-     * the same on every rank.  nsteps <= halo. */
+     * array sets (entries NULL where there is no neighbour); *_base: global row of their array row 0; sync_*: EIGHT
+     * zero-initialised 64-bit words per rank {from_up, from_down, counter, counter, error, reserved x3}; epoch: 1, 2,
+     * ... per call, the same on every rank.  nsteps <= halo.  The wait is bounded (20 s by default, fdtd2d_tune2): a
+     * pass whose neighbour never arrives gives up, raises the error word and ends; fdtd2d_halo_status() reports it. */
     int halo;
     void *peer_up[2][FDTD2D_NFIELDS], *peer_dn[2][FDTD2D_NFIELDS];
     int peer_up_base, peer_dn_base;
@@ -216,8 +217,9 @@ typedef struct {
 } fdtd2d_problem;
 
 /* Advance nsteps full time steps (reference order: ezinct, dfield+source, inctdz, efield, hxinct, hfield,
- * incthx, incthy -- fd2d/python/fd2d_3_4.py:268-277) from state set `cur`, at most tblock (1..8) steps per kernel
- * pass; tblock = 0 lets the library choose depth, vector width and chunking by grid size.
+ * incthx, incthy -- fd2d/python/fd2d_3_4.py:268-277) from state set `cur`, at most tblock (1..12) steps per kernel
+ * pass; tblock = 0 lets the library choose depth, vector width and chunking by grid size and step count
+ * (fdtd2d_plan returns the choice).
  * Rows [row_lo-g, row_hi+g) with g = nsteps must be present and current in set `cur` (clipped to the
  * grid); single device: row_lo=row_base=0, row_hi=rows_alloc=nx and any nsteps is allowed.
  * src: HOST float64 table, one sample per step.  *cur_out = set holding the result. */
@@ -232,12 +234,30 @@ int fdtd2d_check_lossless_outside(const fdtd2d_problem *p, long long *violations
 int fdtd2d_preload(int dtype, int ny, int lossy);
 /* largest supported tblock for a dtype / ny (0 if unsupported) */
 int fdtd2d_max_tblock(int dtype, int ny);
+/* The launch plan fdtd2d_advance(p, cur, nsteps, src, tblock, ...) will use, without launching anything: the pass
+ * depths in order (up to `cap` of them are written to depths[], which may be NULL), the vector width and the rows per
+ * chunk of the first pass.  Only dtype, nx, ny, row_lo, row_hi, flags and nf of `p` are read.  Returns the number of
+ * passes (>= 0) or a negative FDTD_E* code.  Hosts that must know the depth in advance (ghost-band width of a slab,
+ * pass levels of a streamed run) ask here instead of re-deriving it. */
+int fdtd2d_plan(const fdtd2d_problem *p, int nsteps, int tblock, int *depths, int cap, int *vector_width,
+                int *chunk_rows);
+/* Fused halo exchange: *word = 0 while every wait of every pass so far was answered; otherwise epoch*4 + side (1 = the
+ * upper, 2 = the lower neighbour never arrived within the bound) and fdtd_last_error() says so.  Synchronises. */
+int fdtd2d_halo_status(const fdtd2d_problem *p, unsigned long long *word);
 /* Test / tuning hook, process-wide, all zero = defaults: force_v (1, 2, 4) and chunk_rows override the launch plan,
  * warps_per_cta (1..8), ring_depth == 1 runs the edge and interior kernels in stream order instead of forking the
  * edge kernel onto a side stream, force_careful bit 0 sends every warp through the careful (edge) kernel, bit 1
  * ignores the lossless-outside promise.  Results are bit-identical under every setting (that is what the tests use
  * it for). */
 int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, int force_careful);
+/* More process-wide knobs, by key.  FDTD_TUNE_DEEP: 1 (default) = passes of depth 8 and 12 use the kernels with
+ * shared-memory-resident accumulators where they apply (float, 4-wide vectors, no fused DFT), 0 = never (depth <= 8,
+ * register-pipeline kernels only), 2 = additionally run the shared-memory-resident careful (edge) kernel at every
+ * depth.  FDTD_TUNE_HALO_WAIT_MS: bound of the fused halo exchange's wait for a neighbour in milliseconds (0 = the
+ * default of 20 s).  Results are bit-identical under every setting. */
+#define FDTD_TUNE_DEEP 0
+#define FDTD_TUNE_HALO_WAIT_MS 1
+int fdtd2d_tune2(int key, long long value);
 
 #ifdef __cplusplus
 }

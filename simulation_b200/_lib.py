@@ -105,7 +105,11 @@ SYMBOLS = {
     "fdtd2d_preload": (_I, [_I, _I, _I]),
     "fdtd2d_max_tblock": (_I, [_I, _I]),
     "fdtd2d_tune": (_I, [_I, _I, _I, _I, _I]),
+    "fdtd2d_tune2": (_I, [_I, C.c_longlong]),
+    "fdtd2d_plan": (_I, [C.POINTER(Problem2D), _I, _I, C.POINTER(_I), _I, C.POINTER(_I), C.POINTER(_I)]),
+    "fdtd2d_halo_status": (_I, [C.POINTER(Problem2D), C.POINTER(C.c_ulonglong)]),
 }
+TUNE_DEEP, TUNE_HALO_WAIT_MS = 0, 1
 
 _lib = None
 

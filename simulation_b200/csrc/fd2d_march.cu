@@ -13,360 +13,19 @@
 //
 // Arithmetic is the reference's, operation by operation, no FMA contraction (-fmad=false) -> all six
 // arrays are bit-identical to fd2d/program/fd2d_3_3.py run for the same number of steps.
-#include "common.cuh"
+#include "fd2d_march.cuh"
+
+#include <mutex>
 
 namespace {
 
-constexpr int TMAX = 8;          // deepest pipeline instantiated
-constexpr int NFMAX = 3;         // frequencies of the fused running DFT (the reference uses 3 everywhere)
-constexpr int MAX_SPECIAL = 12;  // most edge / TFSF / source strips (or chunks) a split launch can list
-constexpr int MAX_PAIRS = 8;     // most single (strip, chunk) cells handed to the careful kernel (the point source)
-constexpr int MAX_WARPS = 8;     // warps per CTA are independent; a CTA only groups neighbouring strips for L1 locality
+using namespace fdtd_march;
 
-template <typename real>
-struct MarchParams {
-    const real *in_dz, *in_hx, *in_hy, *in_ihx, *in_ihy, *in_iz;
-    real *out_dz, *out_ez, *out_hx, *out_hy, *out_ihx, *out_ihy, *out_iz;
-    const real *naz, *nbz;
-    const real *gx2, *gx3, *fx1, *fx2, *fx3;   // indexed by GLOBAL row
-    const real *gy2, *gy3, *fy1, *fy2, *fy3;   // indexed by column
-    int nx, ny;                                // global grid
-    int row_base;                              // global row of array row 0
-    int in_lo, in_hi;                          // global rows readable in the input set
-    int out_lo, out_hi;                        // global rows this pass must produce
-    int chunk_rows, nstrips, nchunks;
-    int cchunk_rows, ncchunks;                 // row partition of the SPECIAL strips (careful kernel): finer on small launches
-    int tfsf, npml;
-    const real *ezi_hist, *hxi_hist;           // [T][ny], [T][2]
-    int src_i, src_j, src_hard;                // point source on dz (src_i < 0: none)
-    int ident_row_lo, ident_row_hi, ident_col_lo, ident_col_hi;   // rows / cols [lo,hi) with identity PML coefficients
-    int nf;                                    // fused running DFT: frequencies (0 = off, <= NFMAX)
-    real *r_pt, *i_pt;                         // [nf][rows_alloc][ny] accumulators, updated in place by the owner warp
-    long long dft_plane;                       // elements per frequency plane
-    double dft_c[TMAX][NFMAX], dft_s[TMAX][NFMAX];   // phase factors of every sub-step
-    // fused halo exchange over peer memory (multi-GPU): the rows within `halo` of the slab edges are ALSO stored into
-    // the neighbours' ghost rows; completion is announced through flags in the neighbours' memory
-    int push;                                  // this pass pushes its edge rows
-    int halo_on, own_lo, own_hi;               // fused exchange enabled; rows this rank owns (host-side classification)
-    int push_up_end, push_dn_begin;            // rows ro < push_up_end go up, rows ro >= push_dn_begin go down
-    real *up_dz, *up_hx, *up_hy, *up_ihx, *up_ihy, *up_iz;   // neighbour above: its OUT-set arrays (NULL: none)
-    real *dn_dz, *dn_hx, *dn_hy, *dn_ihx, *dn_ihy, *dn_iz;   // neighbour below
-    long long up_shift, dn_shift;              // element offset of a global row in the neighbour's arrays minus mine
-    int wait_flags, signal;                    // first / last pass of a call
-    unsigned long long *sync_local;            // {flag written by up, flag written by down, counter[0], counter[1]}
-    unsigned long long *flag_at_up, *flag_at_dn;   // where this rank announces itself (peer memory)
-    unsigned long long epoch;                  // sequence number of this advance call (1, 2, ...)
-    unsigned total_warps;                      // warps of the careful kernel of the pass (the only ones that touch ghosts)
-    int write_ez;                              // 0: this pass leaves ez untouched (it is never read by a pass)
-    // Lossy problems whose loss is local (a dielectric object in free space): outside rows [lz_row_lo, lz_row_hi) x
-    // cols [lz_col_lo, lz_col_hi) nbz is 0 and iz is +0 in both state sets, where ez = naz*(dz-iz), iz += nbz*ez gives
-    // the bits of ez = naz*dz and leaves iz alone.  Interior warps that stay outside the box then run the lossless
-    // kernel (no iz / nbz traffic); the two interior kernels of a pass share one index space and each warp keeps or
-    // drops itself by this box.
-    int split_lossless;
-    int lz_row_lo, lz_row_hi, lz_col_lo, lz_col_hi;
-    int n_sstrips, n_schunks;                  // sorted ids of the strips / chunks the careful kernel owns
-    int sstrips[MAX_SPECIAL], schunks[MAX_SPECIAL];
-    int n_spairs;                              // single (strip, chunk) cells of otherwise ordinary strips and chunks that the
-    int spairs[MAX_PAIRS][2];                  // careful kernel owns as well: the ones whose rows and columns see the point source
-    double src[TMAX];
-    unsigned long long negzero2;               // two float -0.0 (0x8000000080000000), opaque to the compiler: see pk_mul
-};
-
-// ---- vector global access: V consecutive elements, naturally aligned
-template <typename real, int V> struct VecIO;
-template <> struct VecIO<float, 1> {
-    static __device__ __forceinline__ void ld(const float *p, float (&d)[1]) { d[0] = __ldg(p); }
-    static __device__ __forceinline__ void st(float *p, const float (&d)[1]) { *p = d[0]; }
-};
-template <> struct VecIO<float, 2> {
-    static __device__ __forceinline__ void ld(const float *p, float (&d)[2]) {
-        float2 v = __ldg(reinterpret_cast<const float2 *>(p)); d[0] = v.x; d[1] = v.y;
-    }
-    static __device__ __forceinline__ void st(float *p, const float (&d)[2]) {
-        *reinterpret_cast<float2 *>(p) = make_float2(d[0], d[1]);
-    }
-};
-template <> struct VecIO<float, 4> {
-    static __device__ __forceinline__ void ld(const float *p, float (&d)[4]) {
-        float4 v = __ldg(reinterpret_cast<const float4 *>(p)); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-    static __device__ __forceinline__ void st(float *p, const float (&d)[4]) {
-        *reinterpret_cast<float4 *>(p) = make_float4(d[0], d[1], d[2], d[3]);
-    }
-};
-template <> struct VecIO<double, 1> {
-    static __device__ __forceinline__ void ld(const double *p, double (&d)[1]) { d[0] = __ldg(p); }
-    static __device__ __forceinline__ void st(double *p, const double (&d)[1]) { *p = d[0]; }
-};
-template <> struct VecIO<double, 2> {
-    static __device__ __forceinline__ void ld(const double *p, double (&d)[2]) {
-        double2 v = __ldg(reinterpret_cast<const double2 *>(p)); d[0] = v.x; d[1] = v.y;
-    }
-    static __device__ __forceinline__ void st(double *p, const double (&d)[2]) {
-        *reinterpret_cast<double2 *>(p) = make_double2(d[0], d[1]);
-    }
-};
-
-// ---- cp.async (LDGSTS): global -> shared without a register round trip; src_bytes = 0 zero-fills
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc, int src_bytes) {
-    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
-    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <typename real, int V>
-__device__ __forceinline__ void lds_vec(const void *smem_src, real (&d)[V]) {
-    if constexpr (sizeof(real) * V == 16) {
-        const float4 t = *reinterpret_cast<const float4 *>(smem_src);
-        const real *q = reinterpret_cast<const real *>(&t);
-#pragma unroll
-        for (int v = 0; v < V; ++v) d[v] = q[v];
-    } else if constexpr (sizeof(real) * V == 8) {
-        const float2 t = *reinterpret_cast<const float2 *>(smem_src);
-        const real *q = reinterpret_cast<const real *>(&t);
-#pragma unroll
-        for (int v = 0; v < V; ++v) d[v] = q[v];
-    } else {
-        d[0] = *reinterpret_cast<const real *>(smem_src);
-    }
-}
-
-// One grid row as it lives in registers.  A set is first the ARRIVING row of a stage (state at the stage's
-// input time level; `ez` not yet meaningful), then the row the stage HOLDS (D/E advanced, H not yet), then --
-// updated in place -- the row handed to the next stage.  Sets are never copied: with the row loop unrolled
-// T+1 times the T+1 sets rotate through the roles under compile-time indices (no register moves).
-template <typename real, int V>
-struct RowSet {
-    real dz[V], ez[V], hx[V], hy[V], ihx[V], ihy[V], naz[V], iz[V], nbz[V];
-    real racc[NFMAX][V], iacc[NFMAX][V];       // running-DFT accumulators travelling with the row (DFT kernels only)
-};
-
-template <typename real, int V>
-struct ColCoef {       // per-column PML coefficients and update masks, fixed for the whole march
-    real gy2[V], gy3[V], fy1[V], fy2[V], fy3[V];
-    unsigned dmask, hmask;         // bit v: D / H update applies to column jb+v
-};
-
-// One pipeline stage at sub-step s: finish D,E of the arriving row A (global row rs) and H of the held row Hd
-// (global row rs-1), both in place.  FAST: interior warp -- no edge masks, no TFSF / source cells.
-template <typename real, int V, int MODE, bool FAST, bool NAZR = false>
-__device__ __forceinline__ void march_stage(const MarchParams<real> &p, const ColCoef<real, V> &c, RowSet<real, V> &A,
-                                            RowSet<real, V> &Hd, const int rs, const int s, const int jb,
-                                            const bool tf_cols, const bool src_cols, const void *naz_smem = nullptr,
-                                            const void *naz_held_smem = nullptr) {
-    constexpr bool LOSSY = (MODE & 1) != 0, DFT = (MODE & 2) != 0;
-    static_assert(!NAZR || (FAST && !LOSSY), "the naz ring serves the plain interior kernel only");
-    constexpr unsigned FULL = 0xffffffffu;
-    const real half = real(0.5);
-    const int hr = rs - 1;
-    // FAST warps only touch rows / columns whose ten PML coefficients are the identity set (the host
-    // guarantees it through fdtd2d_problem::ident_*): multiplications by exactly 1 are dropped -- an exact
-    // identity for every input -- while 0*x is kept, because it decides the sign of a zero sum.
-    const int rd = FAST ? rs : min(max(rs, 0), p.nx - 1);
-    const int rh = FAST ? hr : min(max(hr, 0), p.nx - 1);
-    const real gx2 = FAST ? real(1) : __ldg(p.gx2 + rd), gx3 = FAST ? real(1) : __ldg(p.gx3 + rd);
-    const real fx1 = FAST ? real(0) : __ldg(p.fx1 + rh);
-    const real fx2 = FAST ? real(1) : __ldg(p.fx2 + rh), fx3 = FAST ? real(1) : __ldg(p.fx3 + rh);
-    const bool drow = FAST || ((rs >= 1) && (rs < p.nx));
-    const bool hrow = FAST || ((hr >= 0) && (hr <= p.nx - 2));
-
-    // ---- D of row rs:  dz = gx3*gy3*dz + gx2*gy2*0.5*(hy - hy[i-1] - hx + hx[j-1])
-    const real hx_left = __shfl_up_sync(FULL, A.hx[V - 1], 1);
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        const real hxl = (v == 0) ? hx_left : A.hx[v == 0 ? 0 : v - 1];
-        const real curl = ((A.hy[v] - Hd.hy[v]) - A.hx[v]) + hxl;
-        const real gy2 = FAST ? real(1) : c.gy2[v], gy3 = FAST ? real(1) : c.gy3[v];
-        const real dn = ((gx3 * gy3) * A.dz[v]) + (((gx2 * gy2) * half) * curl);
-        if (FAST) A.dz[v] = dn;
-        else A.dz[v] = (drow && ((c.dmask >> v) & 1u)) ? dn : A.dz[v];
-    }
-    if (!FAST) {
-        const int ia = p.npml - 1, iz_ = p.nx - p.npml, ja = p.npml - 1, jz = p.ny - p.npml;
-        if (src_cols && rs == p.src_i) {             // point source (after the stencil, before inctdz)
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                if (jb + v == p.src_j) A.dz[v] = fdtd::inject<real>(A.dz[v], p.src[s], p.src_hard);
-        }
-        if (tf_cols && rs >= ia && rs <= iz_) {      // inctdz: uses hxi of the previous step
-            const real a = half * __ldg(p.hxi_hist + 2 * s), b = half * __ldg(p.hxi_hist + 2 * s + 1);
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                if (jb + v == ja) A.dz[v] = A.dz[v] + a;
-                if (jb + v == jz) A.dz[v] = A.dz[v] - b;
-            }
-        }
-    }
-    // ---- E of row rs
-    real ezA[V], ezH[V];           // Ez of the arriving row (fresh) and of the held row (from the previous row trip)
-    if constexpr (NAZR) {
-        // deep pipelines: naz comes from its shared-memory ring and Ez is not kept in the row sets at all -- the
-        // held row's Ez is the same product naz*dz evaluated again (same operands, same bits)
-        real nzA[V], nzH[V];
-        lds_vec<real, V>(naz_smem, nzA);
-        lds_vec<real, V>(naz_held_smem, nzH);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            ezA[v] = nzA[v] * A.dz[v];
-            ezH[v] = nzH[v] * Hd.dz[v];
-        }
-    } else {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            if (LOSSY) {
-                A.ez[v] = A.naz[v] * (A.dz[v] - A.iz[v]);
-                A.iz[v] = A.iz[v] + A.nbz[v] * A.ez[v];
-            } else {
-                A.ez[v] = A.naz[v] * A.dz[v];
-            }
-            ezA[v] = A.ez[v];
-            ezH[v] = Hd.ez[v];
-        }
-    }
-    if (DFT) {       // fourier of sub-step s on the fresh Ez: float64 product and sum, rounded into the array type
-#pragma unroll
-        for (int f = 0; f < NFMAX; ++f)
-            if (f < p.nf) {
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const double e = static_cast<double>(A.ez[v]);
-                    A.racc[f][v] = static_cast<real>(static_cast<double>(A.racc[f][v]) + p.dft_c[s][f] * e);
-                    A.iacc[f][v] = static_cast<real>(static_cast<double>(A.iacc[f][v]) - p.dft_s[s][f] * e);
-                }
-            }
-    }
-    // ---- H of the held row hr (needs ez[hr][j+1] and ez[rs][j]), in place
-    const real ez_right = __shfl_down_sync(FULL, ezH[0], 1);
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        const real er = (v == V - 1) ? ez_right : ezH[v == V - 1 ? v : v + 1];
-        const real cm = ezH[v] - er;
-        const real cn = ezH[v] - ezA[v];
-        const real sx = Hd.ihx[v] + cm;
-        const real sy = Hd.ihy[v] + cn;
-        const real fy1 = FAST ? real(0) : c.fy1[v], fy2 = FAST ? real(1) : c.fy2[v], fy3 = FAST ? real(1) : c.fy3[v];
-        const real hx2 = (fy3 * Hd.hx[v]) + (fy2 * ((half * cm) + (fx1 * sx)));
-        const real hy2 = (fx3 * Hd.hy[v]) - (fx2 * ((half * cn) + (fy1 * sy)));
-        if (FAST) {
-            Hd.ihx[v] = sx; Hd.ihy[v] = sy; Hd.hx[v] = hx2; Hd.hy[v] = hy2;
-        } else {
-            const bool up = hrow && ((c.hmask >> v) & 1u);
-            Hd.ihx[v] = up ? sx : Hd.ihx[v];
-            Hd.ihy[v] = up ? sy : Hd.ihy[v];
-            Hd.hx[v] = up ? hx2 : Hd.hx[v];
-            Hd.hy[v] = up ? hy2 : Hd.hy[v];
-        }
-    }
-    if (!FAST && p.tfsf) {
-        const int ia = p.npml - 1, iz_ = p.nx - p.npml, ja = p.npml - 1, jz = p.ny - p.npml;
-        if (tf_cols && hr >= ia && hr <= iz_) {      // incthx
-            const real *ez_i = p.ezi_hist + (size_t)s * p.ny;
-            const real a = half * __ldg(ez_i + ja), b = half * __ldg(ez_i + jz);
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                if (jb + v == ja - 1) Hd.hx[v] = Hd.hx[v] + a;
-                if (jb + v == jz) Hd.hx[v] = Hd.hx[v] - b;
-            }
-        }
-        if (hr == ia - 1 || hr == iz_) {             // incthy (two rows of the whole grid)
-            const real *ez_i = p.ezi_hist + (size_t)s * p.ny;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const int j = jb + v;
-                if (j >= ja && j <= jz) {
-                    const real h = half * __ldg(ez_i + j);
-                    if (hr == ia - 1) Hd.hy[v] = Hd.hy[v] - h;
-                    if (hr == iz_) Hd.hy[v] = Hd.hy[v] + h;
-                }
-            }
-        }
-    }
-}
-
-// ---- packed fp32 (sm_100 FADD2 / FFMA2: two IEEE operations per instruction, half the issue slots and code size).
-// Each half rounds exactly like the scalar instruction, so results stay bit-identical to the reference order.  One trap:
-// ptxas contracts a packed multiply with a following packed add into FFMA2 even with --fmad=false (observed with
-// CUDA 12.9: __fmul2_rn + __fadd2_rn -> one FFMA2), which would drop a rounding.  A product is therefore issued as
-// FFMA2(a, b, -0.0) with the -0.0 pair taken from a kernel parameter the compiler cannot see through:
-// a*b + (-0) rounds once, to exactly RN(a*b) (signed zeros included), and an FFMA2 cannot absorb the next add.
-__device__ __forceinline__ float2 pk_add(const float2 a, const float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 pk_sub(const float2 a, const float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
-__device__ __forceinline__ float2 pk_mul(const float2 a, const float2 b, const float2 negzero) { return __ffma2_rn(a, b, negzero); }
-
-// Interior stage in packed arithmetic (float, even V): same operations in the same order as march_stage<.., FAST>.
-template <int V, bool NAZR, bool LOSSY>
-__device__ __forceinline__ void march_stage_pk(RowSet<float, V> &A, RowSet<float, V> &Hd, const float2 negzero,
-                                               const void *naz_smem, const void *naz_held_smem) {
-    static_assert(V % 2 == 0, "packed stage needs column pairs");
-    static_assert(!(NAZR && LOSSY), "the naz ring serves the plain interior kernel only");
-    constexpr unsigned FULL = 0xffffffffu;
-    const float2 half2 = make_float2(0.5f, 0.5f), zero2 = make_float2(0.f, 0.f);
-    // ---- D of the arriving row: dz = dz + 0.5*(((hy - hy[i-1]) - hx) + hx[j-1])
-    const float hx_left = __shfl_up_sync(FULL, A.hx[V - 1], 1);
-#pragma unroll
-    for (int v = 0; v < V; v += 2) {
-        const float2 a1 = pk_sub(make_float2(A.hy[v], A.hy[v + 1]), make_float2(Hd.hy[v], Hd.hy[v + 1]));
-        const float2 a2 = pk_sub(a1, make_float2(A.hx[v], A.hx[v + 1]));
-        const float2 curl = make_float2(a2.x + (v == 0 ? hx_left : A.hx[v == 0 ? 0 : v - 1]), a2.y + A.hx[v]);   // shifted pair: scalar
-        const float2 dn = pk_add(make_float2(A.dz[v], A.dz[v + 1]), pk_mul(half2, curl, negzero));
-        A.dz[v] = dn.x; A.dz[v + 1] = dn.y;
-    }
-    // ---- E of both rows
-    float ezA[V], ezH[V];
-    if constexpr (NAZR) {
-        float nzA[V], nzH[V];
-        lds_vec<float, V>(naz_smem, nzA);
-        lds_vec<float, V>(naz_held_smem, nzH);
-#pragma unroll
-        for (int v = 0; v < V; v += 2) {
-            const float2 a = pk_mul(make_float2(nzA[v], nzA[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
-            const float2 h = pk_mul(make_float2(nzH[v], nzH[v + 1]), make_float2(Hd.dz[v], Hd.dz[v + 1]), negzero);
-            ezA[v] = a.x; ezA[v + 1] = a.y; ezH[v] = h.x; ezH[v + 1] = h.y;
-        }
-    } else {
-#pragma unroll
-        for (int v = 0; v < V; v += 2) {
-            float2 a;
-            if constexpr (LOSSY) {      // ez = naz*(dz - iz); iz = iz + nbz*ez
-                const float2 iz = make_float2(A.iz[v], A.iz[v + 1]);
-                a = pk_mul(make_float2(A.naz[v], A.naz[v + 1]), pk_sub(make_float2(A.dz[v], A.dz[v + 1]), iz), negzero);
-                const float2 i2 = pk_add(iz, pk_mul(make_float2(A.nbz[v], A.nbz[v + 1]), a, negzero));
-                A.iz[v] = i2.x; A.iz[v + 1] = i2.y;
-            } else {
-                a = pk_mul(make_float2(A.naz[v], A.naz[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
-            }
-            A.ez[v] = a.x; A.ez[v + 1] = a.y;
-            ezA[v] = a.x; ezA[v + 1] = a.y; ezH[v] = Hd.ez[v]; ezH[v + 1] = Hd.ez[v + 1];
-        }
-    }
-    // ---- H of the held row: ihx += cm; ihy += cn; hx = hx + (0.5*cm + 0*ihx); hy = hy - (0.5*cn + 0*ihy)
-    const float ez_right = __shfl_down_sync(FULL, ezH[0], 1);
-#pragma unroll
-    for (int v = 0; v < V; v += 2) {
-        const float2 e = make_float2(ezH[v], ezH[v + 1]);
-        const float2 cm = make_float2(ezH[v] - ezH[v + 1], ezH[v + 1] - (v + 2 < V ? ezH[v + 2 < V ? v + 2 : v] : ez_right));   // shifted pair: scalar
-        const float2 cn = pk_sub(e, make_float2(ezA[v], ezA[v + 1]));
-        const float2 sx = pk_add(make_float2(Hd.ihx[v], Hd.ihx[v + 1]), cm);
-        const float2 sy = pk_add(make_float2(Hd.ihy[v], Hd.ihy[v + 1]), cn);
-        const float2 tx = pk_add(pk_mul(half2, cm, negzero), pk_mul(zero2, sx, negzero));
-        const float2 ty = pk_add(pk_mul(half2, cn, negzero), pk_mul(zero2, sy, negzero));
-        const float2 hx2 = pk_add(make_float2(Hd.hx[v], Hd.hx[v + 1]), tx);
-        const float2 hy2 = pk_sub(make_float2(Hd.hy[v], Hd.hy[v + 1]), ty);
-        Hd.ihx[v] = sx.x; Hd.ihx[v + 1] = sx.y; Hd.ihy[v] = sy.x; Hd.ihy[v + 1] = sy.y;
-        Hd.hx[v] = hx2.x; Hd.hx[v + 1] = hx2.y; Hd.hy[v] = hy2.x; Hd.hy[v + 1] = hy2.y;
-    }
-}
 
 // The march of one warp over its (strip, chunk).  Rows are staged through a per-lane ring of RING rows in
 // shared memory filled by cp.async (each lane reads back only the 16 B it copied itself: no barrier, no
 // register cost), keeping RING-1 rows x 6 arrays in flight per warp to cover the HBM latency.
-constexpr int RING = 4;
+// (RING itself is declared in fd2d_march.cuh: the host's row classification needs the fetch run-ahead too.)
 
 // Compile-time shape of one instantiation: register row sets, ring slots, shared memory per warp.
 // NAZR (deep interior pipelines, T >= 7): a row set of 7 arrays x 4 columns x 9 sets does not fit the register
@@ -550,22 +209,7 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
             }
             // halo exchange fused into the pass: peer stores over NVLink, row by row.  Only the careful kernel
             // pushes: the host lists every chunk that owns a pushed row (or reads a ghost row) as special.
-            if (!FAST && p.push) {
-                if (ro < p.push_up_end && p.up_dz != nullptr) {
-                    const long long o = off_s + p.up_shift;
-                    VecIO<real, V>::st(p.up_dz + o, O.dz);   VecIO<real, V>::st(p.up_hx + o, O.hx);
-                    VecIO<real, V>::st(p.up_hy + o, O.hy);   VecIO<real, V>::st(p.up_ihx + o, O.ihx);
-                    VecIO<real, V>::st(p.up_ihy + o, O.ihy);
-                    if (LOSSY) VecIO<real, V>::st(p.up_iz + o, O.iz);
-                }
-                if (ro >= p.push_dn_begin && p.dn_dz != nullptr) {
-                    const long long o = off_s + p.dn_shift;
-                    VecIO<real, V>::st(p.dn_dz + o, O.dz);   VecIO<real, V>::st(p.dn_hx + o, O.hx);
-                    VecIO<real, V>::st(p.dn_hy + o, O.hy);   VecIO<real, V>::st(p.dn_ihx + o, O.ihx);
-                    VecIO<real, V>::st(p.dn_ihy + o, O.ihy);
-                    if (LOSSY) VecIO<real, V>::st(p.dn_iz + o, O.iz);
-                }
-            }
+            if (!FAST && p.push) push_row<real, V, LOSSY>(p, off_s, ro, O.dz, O.hx, O.hy, O.ihx, O.ihy, O.iz);
         }
         off_s += p.ny;
     };
@@ -625,21 +269,6 @@ __device__ __forceinline__ void march_body(const MarchParams<real> &p, const int
     cp_async_wait<0>();
 }
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// k-th id (0-based) of the ascending sequence 0,1,2,... with the sorted ids in `skip` removed
-__device__ __forceinline__ int kth_not_in(int k, const int *skip, int n) {
-    for (int q = 0; q < n; ++q)
-        if (skip[q] <= k) ++k;
-    return k;
-}
 
 // Two launches per pass share this kernel template:
 //   FAST    : interior warps -- (ordinary strips) x (ordinary chunks): every column (halo included) is an
@@ -654,74 +283,11 @@ k_march(const __grid_constant__ MarchParams<real> p, const int all_careful) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned char *const ring = ring_smem + (size_t)(threadIdx.x >> 5) * MarchShape<real, V, T, MODE, FAST>::WARP_SMEM;
-    const int nsf = p.nstrips - p.n_sstrips, ncf = p.nchunks - p.n_schunks;   // ordinary strips / chunks
-    int strip, chunk, crows = p.chunk_rows;     // rows [out_lo + chunk*crows, ...) of the strip
-    if (FAST) {
-        if (w >= nsf * ncf) return;
-        strip = kth_not_in(w % nsf, p.sstrips, p.n_sstrips);
-        chunk = kth_not_in(w / nsf, p.schunks, p.n_schunks);
-        for (int q = 0; q < p.n_spairs; ++q)
-            if (strip == p.spairs[q][0] && chunk == p.spairs[q][1]) return;     // the careful kernel has this one
-        if (p.split_lossless) {
-            // rows and columns this warp touches (warm-up, drain and fetch run-ahead included), as the host classifies them
-            constexpr int W = 32 * V, HALO = ((T + V - 1) / V) * V, USE = W - 2 * HALO;
-            const int c0 = strip * USE - HALO, c1 = c0 + W;
-            const int r0 = p.out_lo + chunk * crows, r1 = min(r0 + crows, p.out_hi);
-            const int lo = r0 - T - 1, hi = r1 + 2 * T + RING + 2;
-            const bool in_box = c0 < p.lz_col_hi && c1 > p.lz_col_lo && lo < p.lz_row_hi && hi > p.lz_row_lo;
-            if (in_box != ((MODE & 1) != 0)) return;     // lossy kernel: warps meeting the box; lossless kernel: the others
-        }
-    } else if (all_careful) {
-        if (w >= p.nstrips * p.nchunks) return;
-        strip = w % p.nstrips;
-        chunk = w / p.nstrips;
-    } else {
-        const int na = p.n_sstrips * p.ncchunks;        // special strips: all rows, in their own (finer) row partition
-        if (w < na) {
-            strip = p.sstrips[w % p.n_sstrips];
-            chunk = w / p.n_sstrips;
-            crows = p.cchunk_rows;
-        } else {
-            const int x = w - na, nb = nsf * p.n_schunks;
-            if (x < nb) {
-                strip = kth_not_in(x % nsf, p.sstrips, p.n_sstrips);
-                chunk = p.schunks[x / nsf];
-            } else {
-                if (x - nb >= p.n_spairs) return;
-                strip = p.spairs[x - nb][0];
-                chunk = p.spairs[x - nb][1];
-            }
-        }
-    }
-    const int i0 = p.out_lo + chunk * crows, i1 = min(i0 + crows, p.out_hi);
-    // Fused halo exchange (multi-GPU).  Ghost rows are read, and edge rows pushed, by careful warps only (the host
-    // lists those chunks as special), so the handshake lives in the careful kernel; the interior kernel carries none.
-    if (!FAST && p.wait_flags) {
-        // neighbours must have finished their previous call: their pushes into my ghost rows have landed, and they no
-        // longer read the ghost rows this call's pushes will overwrite
-        if (lane == 0) {
-            const unsigned long long need = p.epoch - 1;
-            if (p.flag_at_up != nullptr) while (ld_acquire_sys(p.sync_local + 0) < need) { }
-            if (p.flag_at_dn != nullptr) while (ld_acquire_sys(p.sync_local + 1) < need) { }
-        }
-        __syncwarp();
-    }
+    int strip, i0, i1;
+    if (!decode_item<FAST>(p, w, all_careful, V, T, (MODE & 1) != 0, strip, i0, i1)) return;
+    if (!FAST) halo_wait(p, lane);
     march_body<real, V, T, MODE, FAST>(p, strip, i0, i1, lane, ring);
-    if (!FAST && p.signal) {
-        // the last careful warp of the pass announces completion to the neighbours
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) {
-            unsigned long long *counter = p.sync_local + 2 + (p.epoch & 1ull);
-            const unsigned long long done = atomicAdd(counter, 1ull);
-            if (done + 1 == (unsigned long long)p.total_warps) {
-                atomicExch(counter, 0ull);
-                __threadfence_system();
-                if (p.flag_at_up != nullptr) st_release_sys(p.flag_at_up, p.epoch);
-                if (p.flag_at_dn != nullptr) st_release_sys(p.flag_at_dn, p.epoch);
-            }
-        }
-    }
+    if (!FAST) halo_signal(p, lane);
 }
 
 // ---- incident line: T steps of the 1D auxiliary FDTD (ezinct ... hxinct), recording what the 2D pass
@@ -789,23 +355,23 @@ __global__ void k_check_lossless_outside(const real *nbz, const real *iz0, const
     }
 }
 
-int g_force_v = 0;          // test / tuning hooks (fdtd2d_tune)
-int g_chunk_rows = 0;
-int g_warps = 0;
-int g_careful = 0;
+}  // namespace
 
-int g_split = 1;             // 0 = ignore the lossless-outside promise (tests: the lossy kernel everywhere)
-int g_serial = 2;            // 2 = fork the edge kernel onto a side stream (measured +2 %); 1 = edge then interior in order
+namespace fdtd_march {
 
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+Tuning g_tune;               // test / tuning hooks (fdtd2d_tune, fdtd2d_tune2)
 
 // one high-priority side stream + fork/join events per (device, launch stream), created on first use: callers that
-// drive several launch streams at once (Fdtd2D.run_streamed) must not queue behind each other's edge kernels
+// drive several launch streams at once (Fdtd2D.run_streamed) must not queue behind each other's edge kernels.
+// The table is shared by every host thread: guarded by a mutex (entries are never removed, so the returned pointer
+// stays valid).
 SideStream *side_stream(cudaStream_t launch) {
     struct Entry { int dev; cudaStream_t launch; SideStream side; };
     constexpr int CAP = 64;
     static Entry table[CAP];
     static int used = 0;
+    static std::mutex guard;
+    std::lock_guard<std::mutex> lock(guard);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     for (int k = 0; k < used; ++k)
@@ -823,21 +389,30 @@ SideStream *side_stream(cudaStream_t launch) {
     return &e.side;
 }
 
+}  // namespace fdtd_march
+
+namespace {
+
 template <typename real, int V, int T, int MODE, bool FAST>
 int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStream_t st) {
     if (items <= 0) return FDTD_OK;
     const size_t per_warp = MarchShape<real, V, T, MODE, FAST>::WARP_SMEM;
     // 8 independent warps per CTA on big grids; fewer when there are not enough warps to fill every SM
-    int warps = (g_warps >= 1 && g_warps <= MAX_WARPS) ? g_warps : (items >= 32 * fdtd::sm_count() ? 8 : (items >= 8 * fdtd::sm_count() ? 4 : 2));
+    int warps = (g_tune.warps >= 1 && g_tune.warps <= MAX_WARPS) ? g_tune.warps : (items >= 32 * fdtd::sm_count() ? 8 : (items >= 8 * fdtd::sm_count() ? 4 : 2));
     while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) --warps;
     const size_t smem = (size_t)warps * per_warp;
-    static size_t configured[64] = {0};                 // per instantiation and device: largest dynamic smem opted in so far
-    int dev = 0;
-    FDTD_CUDA(cudaGetDevice(&dev));
-    size_t &opted = configured[dev >= 0 && dev < 64 ? dev : 0];
-    if (smem > 48 * 1024 && (smem > opted || dev >= 64)) {
-        FDTD_CUDA(cudaFuncSetAttribute(k_march<real, V, T, MODE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        opted = smem;
+    if (smem > 48 * 1024) {
+        // per instantiation and device: largest dynamic smem opted in so far (shared by every host thread)
+        static size_t configured[64] = {0};
+        static std::mutex guard;
+        std::lock_guard<std::mutex> lock(guard);
+        int dev = 0;
+        FDTD_CUDA(cudaGetDevice(&dev));
+        size_t &opted = configured[dev >= 0 && dev < 64 ? dev : 0];
+        if (smem > opted || dev >= 64) {
+            FDTD_CUDA(cudaFuncSetAttribute(k_march<real, V, T, MODE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            opted = smem;
+        }
     }
     const int grid = (items + warps - 1) / warps;
     k_march<real, V, T, MODE, FAST><<<grid, warps * 32, smem, st>>>(mp, all_careful);
@@ -845,73 +420,23 @@ int launch_one(const MarchParams<real> &mp, int items, int all_careful, cudaStre
     return FDTD_OK;
 }
 
-// classify strips and chunks on the host (same conditions as the kernel relies on) and launch the two kernels
+// classify strips and chunks on the host (classify_pass: the conditions the kernels rely on) and launch the two kernels
 template <typename real, int V, int T, int MODE>
 int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
-    constexpr int W = 32 * V, HALO = ((T + V - 1) / V) * V, USE = W - 2 * HALO;
-    const int ja = mp.npml - 1, jz = mp.ny - mp.npml, ia = mp.npml - 1, iz_ = mp.nx - mp.npml;
-    int ns = 0, nc = 0;
-    bool overflow = g_careful != 0;
-    for (int k = 0; k < mp.nstrips && !overflow; ++k) {
-        const int c0 = k * USE - HALO, c1 = c0 + W;     // columns [c0, c1)
-        bool special = (c0 < max(1, mp.ident_col_lo)) || (c1 > min(mp.ny - 1, mp.ident_col_hi));
-        if (mp.tfsf) special = special || (ja - 1 >= c0 && ja - 1 < c1) || (ja >= c0 && ja < c1) || (jz >= c0 && jz < c1);
-        if (special) {
-            if (ns == MAX_SPECIAL) overflow = true;
-            else mp.sstrips[ns++] = k;
+    const PassCounts pc = classify_pass(mp, V, T);
+    // the careful (edge) warps: the register-shifting kernel of this file or, on request (fdtd2d_tune2 deep = 2), the
+    // shared-memory-resident one of fd2d_deep.cu
+    auto launch_careful = [&](int items, int all, cudaStream_t where) -> int {
+        if constexpr (sizeof(real) == 4 && V == 4 && (MODE & 2) == 0) {
+            if (g_tune.deep == 2) return launch_careful2(mp, T, (MODE & 1) != 0, items, all, where);
         }
-    }
-    for (int k = 0; k < mp.nchunks && !overflow; ++k) {
-        const int i0 = mp.out_lo + k * mp.chunk_rows, i1 = min(i0 + mp.chunk_rows, mp.out_hi);
-        const int lo = i0 - T - 1, hi = i1 + 2 * T + RING + 2; // rows touched (fetch run-ahead included): [lo, hi)
-        bool special = (lo < max(max(1, mp.in_lo), mp.ident_row_lo)) || (hi > min(min(mp.nx - 1, mp.in_hi), mp.ident_row_hi));
-        if (mp.tfsf) special = special || (ia - 1 >= lo && ia - 1 < hi) || (iz_ >= lo && iz_ < hi);
-        // fused halo exchange: chunks that touch a ghost row or own a pushed row carry the handshake
-        if (mp.halo_on) special = special || lo < mp.own_lo || hi > mp.own_hi || i0 < mp.push_up_end || i1 > mp.push_dn_begin;
-        if (special) {
-            if (nc == MAX_SPECIAL) overflow = true;
-            else mp.schunks[nc++] = k;
-        }
-    }
-    // The point source is ONE cell: only the (strip, chunk) cells whose columns and rows see it go to the careful kernel,
-    // not its whole strip and its whole chunk.
-    int np = 0;
-    if (mp.src_i >= 0 && !overflow) {
-        auto listed = [](const int *a, int n, int k) { for (int q = 0; q < n; ++q) if (a[q] == k) return true; return false; };
-        for (int k = 0; k < mp.nstrips && !overflow; ++k) {
-            const int c0 = k * USE - HALO, c1 = c0 + W;
-            if (!(mp.src_j >= c0 && mp.src_j < c1) || listed(mp.sstrips, ns, k)) continue;
-            for (int c = 0; c < mp.nchunks && !overflow; ++c) {
-                const int i0 = mp.out_lo + c * mp.chunk_rows, i1 = min(i0 + mp.chunk_rows, mp.out_hi);
-                const int lo = i0 - T - 1, hi = i1 + 2 * T + RING + 2;
-                if (!(mp.src_i >= lo && mp.src_i < hi) || listed(mp.schunks, nc, c)) continue;
-                if (np == MAX_PAIRS) overflow = true;
-                else { mp.spairs[np][0] = k; mp.spairs[np][1] = c; ++np; }
-            }
-        }
-    }
-    mp.n_spairs = overflow ? 0 : np;
-    if (overflow) {                                      // tiny grids: everything through the careful kernel
-        mp.n_sstrips = mp.n_schunks = 0;
-        mp.cchunk_rows = mp.chunk_rows; mp.ncchunks = mp.nchunks;
-        mp.total_warps = (unsigned)(mp.nstrips * mp.nchunks);
-        return launch_one<real, V, T, MODE, false>(mp, mp.nstrips * mp.nchunks, 1, st);
-    }
-    mp.n_sstrips = ns; mp.n_schunks = nc;
-    const int nsf = mp.nstrips - ns, ncf = mp.nchunks - nc;
-    const int n_fast = nsf * ncf;                        // (np of them exit at once)
-    // A careful warp is ~3x slower per row than an interior warp, and a launch cannot end before its slowest warp.
-    // On big launches (tens of interior waves) that is hidden; on small ones (row blocks of a streamed run, small
-    // grids) the special strips get a finer row partition so that their warps finish with the interior's.
-    const int rows = mp.out_hi - mp.out_lo;
-    const bool small_launch = n_fast < 16 * MAX_WARPS * fdtd::sm_count();
-    mp.cchunk_rows = small_launch ? max(1, min(mp.chunk_rows, max(4 * T, 32))) : mp.chunk_rows;
-    mp.ncchunks = (rows + mp.cchunk_rows - 1) / mp.cchunk_rows;
-    const int n_careful = ns * mp.ncchunks + nsf * nc + np;
-    mp.total_warps = (unsigned)n_careful;
+        return launch_one<real, V, T, MODE, false>(mp, items, all, where);
+    };
+    if (pc.all_careful) return launch_careful(pc.n_careful, 1, st);
+    const int n_fast = pc.n_fast, n_careful = pc.n_careful;
     // The careful kernel is small (edges only) and would run alone at a fraction of a wave: fork it onto a side
     // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
-    SideStream *side = (n_careful > 0 && n_fast > 0 && g_serial == 2) ? side_stream(st) : nullptr;
+    SideStream *side = (n_careful > 0 && n_fast > 0 && g_tune.serial == 2) ? side_stream(st) : nullptr;
     // interior warps: one launch, or -- lossy problem with a lossless-outside promise -- two over the same index space
     // (the lossy kernel keeps the warps that meet the box, the lossless kernel the others)
     auto launch_interior = [&]() -> int {
@@ -924,13 +449,13 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
         return launch_one<real, V, T, MODE, true>(mp, n_fast, 0, st);
     };
     if (side == nullptr) {
-        int rc = launch_one<real, V, T, MODE, false>(mp, n_careful, 0, st);
+        int rc = launch_careful(n_careful, 0, st);
         if (rc != FDTD_OK) return rc;
         return launch_interior();
     }
     FDTD_CUDA(cudaEventRecord(side->fork, st));
     FDTD_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    int rc = launch_one<real, V, T, MODE, false>(mp, n_careful, 0, side->stream);
+    int rc = launch_careful(n_careful, 0, side->stream);
     if (rc != FDTD_OK) return rc;
     FDTD_CUDA(cudaEventRecord(side->join, side->stream));
     rc = launch_interior();
@@ -1015,38 +540,59 @@ template <> int pick_v<double>(int ny) { return ny % 2 == 0 ? 2 : 1; }
 // Launch shape by grid size (cells stored on this device), from the sweeps in profiles/r1_sweep_grid_sizes_3_2.txt:
 // small grids live in L2 and need many short warps (narrow vectors, shallow blocking, 16-row chunks); big grids
 // are HBM-bound and want 4-wide vectors, 6 steps per pass and 128-row chunks.
-struct Plan { int V, T, chunk; };
+struct Plan {
+    int V, T, chunk;
+    bool deep;       // the deep passes of fd2d_deep.cu (depth 8 and 12: float, 4-wide vectors, no fused DFT) are available
+};
 
 template <typename real>
-Plan choose_plan(long cells, int ny, bool lossy) {
+Plan choose_plan(const fdtd2d_problem *q) {
+    // sized by the rows THIS call produces (a slab, or one row block of a streamed run), not by the allocation
+    const long cells = (long)(q->row_hi - q->row_lo) * q->ny;
+    const bool lossy = (q->flags & FDTD_LOSSY) != 0;
+    const int ny = q->ny;
     Plan p;
     if (sizeof(real) == 4) {                            // profiles/r1_v18_sweep_grid_sizes.txt
-        if (cells < 6000000L)        p = {2, 4, 16};
-        else if (cells < 24000000L)  p = {2, 6, 64};
-        else if (cells < 100000000L) p = {lossy ? 2 : 4, 6, 64};
-        else                         p = {lossy ? 2 : 4, 6, 128};   // 7 row sets x 4 columns x 9 lossy fields spill
+        if (cells < 6000000L)        p = {2, 4, 16, false};
+        else if (cells < 24000000L)  p = {2, 6, 64, false};
+        else if (cells < 100000000L) p = {lossy ? 2 : 4, 6, 64, false};
+        else                         p = {lossy ? 2 : 4, 6, 128, false};   // 7 row sets x 4 columns x 9 lossy fields spill
     } else {
-        if (cells < 1500000L)        p = {1, 4, 16};           // profiles/r1_sweep_fp64.txt
-        else if (cells < 12000000L)  p = {2, 4, 16};
-        else if (cells < 150000000L) p = {2, 6, 64};
-        else                         p = {2, 6, 128};
+        if (cells < 1500000L)        p = {1, 4, 16, false};           // profiles/r1_sweep_fp64.txt
+        else if (cells < 12000000L)  p = {2, 4, 16, false};
+        else if (cells < 150000000L) p = {2, 6, 64, false};
+        else                         p = {2, 6, 128, false};
     }
     while (p.V > 1 && ny % p.V != 0) p.V >>= 1;
+    // vector width of the call (the depth-dependent float64 exception is applied per pass)
+    int V = g_tune.force_v ? g_tune.force_v : p.V;
+    if (q->nf > 0 && V == 4) V = 2;                 // fused-DFT kernels: vector width <= 2
+    if (q->nf > 0 && sizeof(real) == 8) V = 1;      // ... and 1 in float64 (register row sets)
+    if (ny % V != 0 || (sizeof(real) == 8 && V == 4)) V = 1;
+    p.V = V;
+    p.deep = sizeof(real) == 4 && V == 4 && q->nf == 0 && g_tune.deep != 0 && deep_supported(12, lossy);
     return p;
+}
+
+// depth of the next pass: at most `left` steps and `tblock` (0: the plan's own depth -- 12 where the deep passes are
+// available), rounded down to an instantiated depth: 1, 2, 3, 4, 6, 8 (+ 12 deep)
+inline int next_depth(const Plan &plan, int tblock, int left, int nf) {
+    int T = min(tblock > 0 ? tblock : (plan.deep ? 12 : plan.T), left);
+    if (nf > 0) T = min(T, 4);                      // fused-DFT kernels: depth <= 4
+    if (T >= 12 && plan.deep) return 12;
+    if (T > 8) T = 8;
+    if (T == 5 || T == 7) --T;
+    return T;
 }
 
 template <typename real>
 int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int tblock, cudaStream_t st,
             int *cur_out) {
-    // sized by the rows THIS call produces (a slab, or one row block of a streamed run), not by the allocation
-    const Plan plan = choose_plan<real>((long)(q->row_hi - q->row_lo) * q->ny, q->ny, (q->flags & FDTD_LOSSY) != 0);
-    if (tblock <= 0) tblock = plan.T;
+    const Plan plan = choose_plan<real>(q);
     const bool lossy = (q->flags & FDTD_LOSSY) != 0, tfsf = (q->flags & FDTD_TFSF) != 0;
     int done = 0;
     while (done < nsteps) {
-        int T = min(tblock, nsteps - done);
-        if (q->nf > 0) T = min(T, 4);                   // fused-DFT kernels: depth <= 4
-        if (T == 5 || T == 7) --T;                      // instantiated depths: 1, 2, 3, 4, 6, 8
+        const int T = next_depth(plan, tblock, nsteps - done, q->nf);
         if (q->halo > 0 && T < nsteps) {
             // the handshake orders whole calls: the last pass pushes into the array set that the neighbour's earlier
             // passes of the same call would still be reading
@@ -1084,6 +630,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.src_i = tfsf ? -1 : q->src_i; mp.src_j = q->src_j; mp.src_hard = q->src_hard;
         for (int s = 0; s < TMAX; ++s) mp.src[s] = (src && s < T) ? src[done + s] : 0.0;
         mp.negzero2 = 0x8000000080000000ull;
+        mp.spin_ns = g_tune.spin_ns;
         {   // fused halo exchange: wait on the first pass of the call, push + announce on the last
             const bool on = q->halo > 0;
             void *const *up = q->peer_up[cur ^ 1];
@@ -1110,7 +657,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         }
         mp.lz_row_lo = q->lossy_row_lo; mp.lz_row_hi = q->lossy_row_hi;
         mp.lz_col_lo = q->lossy_col_lo; mp.lz_col_hi = q->lossy_col_hi;
-        mp.split_lossless = lossy && q->nf == 0 && g_split != 0 && q->lossy_row_hi > q->lossy_row_lo && q->lossy_col_hi > q->lossy_col_lo;
+        mp.split_lossless = lossy && q->nf == 0 && g_tune.split != 0 && q->lossy_row_hi > q->lossy_row_lo && q->lossy_col_hi > q->lossy_col_lo;
         mp.nf = q->nf;
         mp.r_pt = (real *)q->ft.r_pt; mp.i_pt = (real *)q->ft.i_pt;
         mp.dft_plane = (long long)q->rows_alloc * q->ny;
@@ -1121,17 +668,17 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
                 mp.dft_s[s][f] = on ? q->dft_sin[(size_t)(done + s) * q->nf + f] : 0.0;
             }
 
-        int V = g_force_v ? g_force_v : plan.V;
-        if (q->nf > 0 && V == 4) V = 2;                 // fused-DFT kernels: vector width <= 2
-        if (q->nf > 0 && sizeof(real) == 8) V = 1;      // ... and 1 in float64 (register row sets)
-        if (q->ny % V != 0 || (sizeof(real) == 8 && V == 4)) V = 1;
-        if (T == 8 && sizeof(real) == 8) V = 1;         // ... nor do 9 sets of 2 doubles
+        int V = plan.V;
+        if (T == 8 && sizeof(real) == 8) V = 1;         // 9 register sets of 2 doubles do not fit
+        // deep pass (fd2d_deep.cu): accumulators resident in shared memory, depth 12 -- and depth 8 in place of the
+        // register-pipeline kernel with its naz ring
+        const bool deep = plan.deep && (T == 12 || T == 8);
         const int halo = ((T + V - 1) / V) * V;
         const int use = 32 * V - 2 * halo;
         mp.nstrips = (q->ny + use - 1) / use;
         const int rows = mp.out_hi - mp.out_lo;
-        int chunk = g_chunk_rows;
-        if (chunk <= 0) chunk = max(plan.chunk, 4 * T);   // at most ~50 % warm-up/drain recompute on shallow grids
+        int chunk = g_tune.chunk_rows;
+        if (chunk <= 0) chunk = max(deep ? max(plan.chunk, 256) : plan.chunk, 4 * T);   // at most ~50 % warm-up/drain recompute on shallow grids
         chunk = max(1, min(chunk, rows));
         mp.chunk_rows = chunk;
         mp.nchunks = (rows + chunk - 1) / chunk;
@@ -1149,7 +696,8 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         }
         int rc;
         if constexpr (sizeof(real) == 4) {
-            if (V == 4) rc = launch_march_T<real, 4>(T, mp, lossy, st);
+            if (deep) rc = launch_march_deep(mp, T, lossy, st);
+            else if (V == 4) rc = launch_march_T<real, 4>(T, mp, lossy, st);
             else if (V == 2) rc = launch_march_T<real, 2>(T, mp, lossy, st);
             else rc = launch_march_T<real, 1>(T, mp, lossy, st);
         } else {
@@ -1234,6 +782,7 @@ int fdtd2d_preload(int dtype, int ny, int lossy) {
     }
     lossy &= 1;
     if (dtype == FDTD_F32) {
+        preload_deep(lossy != 0);
         touch_V<float, 4>(lossy != 0);
         touch_V<float, 2>(lossy != 0);
         touch_V<float, 1>(lossy != 0);
@@ -1250,18 +799,64 @@ int fdtd2d_preload(int dtype, int ny, int lossy) {
 }
 
 int fdtd2d_max_tblock(int dtype, int ny) {
-    (void)ny;
-    return (dtype == FDTD_F32 || dtype == FDTD_F64) ? 8 : 0;
+    if (dtype == FDTD_F32) return (ny % 4 == 0 && deep_supported(12, false)) ? 12 : 8;
+    return dtype == FDTD_F64 ? 8 : 0;
 }
 
 // tuning / test hook (not part of the reference-facing surface): force the vector width and rows per chunk
 int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, int force_careful) {
-    g_force_v = force_v;
-    g_chunk_rows = chunk_rows;
-    g_warps = warps_per_cta;
-    g_serial = (ring_depth == 1) ? 1 : 2;     // (slot reused) 1 = serialise the edge and interior kernels
-    g_careful = force_careful & 1;            // bit 0: every warp through the careful kernel
-    g_split = (force_careful & 2) ? 0 : 1;    // bit 1: ignore the lossless-outside promise
+    g_tune.force_v = force_v;
+    g_tune.chunk_rows = chunk_rows;
+    g_tune.warps = warps_per_cta;
+    g_tune.serial = (ring_depth == 1) ? 1 : 2;     // (slot reused) 1 = serialise the edge and interior kernels
+    g_tune.careful = force_careful & 1;            // bit 0: every warp through the careful kernel
+    g_tune.split = (force_careful & 2) ? 0 : 1;    // bit 1: ignore the lossless-outside promise
+    return FDTD_OK;
+}
+
+int fdtd2d_tune2(int key, long long value) {
+    switch (key) {
+        case FDTD_TUNE_DEEP:
+            FDTD_REQUIRE(value >= 0 && value <= 2, "fdtd2d_tune2: deep must be 0, 1 or 2");
+            g_tune.deep = (int)value;
+            return FDTD_OK;
+        case FDTD_TUNE_HALO_WAIT_MS:
+            FDTD_REQUIRE(value >= 0, "fdtd2d_tune2: negative wait");
+            g_tune.spin_ns = value == 0 ? HALO_SPIN_NS : (unsigned long long)value * 1000000ull;
+            return FDTD_OK;
+        default:
+            fdtd::set_error("fdtd2d_tune2: unknown key %d", key);
+            return FDTD_EINVAL;
+    }
+}
+
+int fdtd2d_plan(const fdtd2d_problem *q, int nsteps, int tblock, int *depths, int cap, int *vector_width, int *chunk_rows) {
+    FDTD_REQUIRE(q != nullptr, "fdtd2d_plan: null problem");
+    FDTD_REQUIRE(q->dtype == FDTD_F32 || q->dtype == FDTD_F64, "fdtd2d_plan: unknown dtype %d", q->dtype);
+    FDTD_REQUIRE(nsteps >= 0 && tblock >= 0 && tblock <= TMAX, "fdtd2d_plan: nsteps %d / tblock %d out of range", nsteps, tblock);
+    FDTD_REQUIRE(q->row_hi > q->row_lo && q->ny >= 2, "fdtd2d_plan: empty problem");
+    const Plan plan = q->dtype == FDTD_F32 ? choose_plan<float>(q) : choose_plan<double>(q);
+    int n = 0, first = 0;
+    for (int left = nsteps; left > 0; ++n) {
+        const int T = next_depth(plan, tblock, left, q->nf);
+        if (n == 0) first = T;
+        if (depths != nullptr && n < cap) depths[n] = T;
+        left -= T;
+    }
+    if (vector_width) *vector_width = (q->dtype == FDTD_F64 && first == 8) ? 1 : plan.V;
+    if (chunk_rows) {
+        const bool deep = plan.deep && (first == 12 || first == 8);
+        *chunk_rows = g_tune.chunk_rows > 0 ? g_tune.chunk_rows : max(deep ? max(plan.chunk, 256) : plan.chunk, 4 * max(first, 1));
+    }
+    return n;
+}
+
+int fdtd2d_halo_status(const fdtd2d_problem *q, unsigned long long *word) {
+    FDTD_REQUIRE(q && word && q->sync_local, "fdtd2d_halo_status: null argument / no fused halo exchange");
+    FDTD_CUDA(cudaMemcpy(word, (const unsigned long long *)q->sync_local + 4, sizeof(*word), cudaMemcpyDeviceToHost));
+    if (*word != 0)
+        fdtd::set_error("fused halo exchange: the pass of epoch %llu gave up waiting for its %s neighbour (a rank died or skipped a call); "
+                        "ghost rows are stale", *word >> 2, (*word & 3) == 1 ? "upper" : "lower");
     return FDTD_OK;
 }
 
@@ -1270,7 +865,7 @@ int fdtd2d_advance(const fdtd2d_problem *q, int cur, int nsteps, const double *s
     FDTD_REQUIRE(q && cur_out, "fdtd2d_advance: null problem / cur_out");
     FDTD_REQUIRE(cur == 0 || cur == 1, "fdtd2d_advance: cur must be 0 or 1");
     FDTD_REQUIRE(q->nx >= 2 && q->ny >= 2, "fdtd2d_advance: grid %dx%d too small", q->nx, q->ny);
-    FDTD_REQUIRE(tblock >= 0 && tblock <= 8, "fdtd2d_advance: tblock %d outside [0, 8] (0 = choose by grid size)", tblock);
+    FDTD_REQUIRE(tblock >= 0 && tblock <= TMAX, "fdtd2d_advance: tblock %d outside [0, %d] (0 = choose by grid size)", tblock, TMAX);
     FDTD_REQUIRE(nsteps >= 0, "fdtd2d_advance: nsteps < 0");
     FDTD_REQUIRE(q->row_lo >= 0 && q->row_hi <= q->nx && q->row_lo < q->row_hi, "fdtd2d_advance: bad owned rows [%d,%d)", q->row_lo, q->row_hi);
     FDTD_REQUIRE(q->row_base <= q->row_lo && q->row_base + q->rows_alloc >= q->row_hi, "fdtd2d_advance: owned rows outside the stored rows");

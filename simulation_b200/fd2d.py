@@ -154,6 +154,30 @@ def dielectric(nx: int, ny: int, npml: int, rgrid: int, dt: float, epsr: float, 
     return medium(naz, nbz)
 
 
+def plan_depths(nx: int, ny: int, dtype, nsteps: int, tblock: int = 0, rows=None, lossy: bool = False, nf: int = 0):
+    """Pass depths the library will use for ``nsteps`` steps on rows ``rows`` (default: the whole grid) of an
+    ``nx x ny`` problem -- asked from the library (``fdtd2d_plan``), never re-derived here.  ``tblock = 0``: the library's
+    own choice by grid size and step count."""
+    p = _lib.Problem2D()
+    p.dtype = _lib.dtype_code(dtype)
+    p.nx, p.ny = int(nx), int(ny)
+    p.row_lo, p.row_hi = (0, int(nx)) if rows is None else (int(rows[0]), int(rows[1]))
+    p.flags = _lib.LOSSY if lossy else 0
+    p.nf = int(nf)
+    return _plan(p, nsteps, tblock)[0]
+
+
+def _plan(prob: "_lib.Problem2D", nsteps: int, tblock) -> tuple:
+    """-> (pass depths, vector width, rows per chunk) of ``fdtd2d_advance(prob, ..., nsteps, ..., tblock)``"""
+    nsteps, tb = int(nsteps), int(tblock or 0)
+    cap = max(nsteps, 1)
+    depths, v, chunk = (C.c_int * cap)(), C.c_int(0), C.c_int(0)
+    n = lib().fdtd2d_plan(C.byref(prob), nsteps, tb, depths, cap, C.byref(v), C.byref(chunk))
+    if n < 0:
+        check(n, "fdtd2d_plan")
+    return [int(depths[k]) for k in range(n)], int(v.value), int(chunk.value)
+
+
 @dataclass(frozen=True)
 class PointSource:
     """``dz[i, j] = waveform(t)`` (hard) or ``+=`` (soft) after the D update (fd2d_3_1.py:48, fd2d_3_2.py:66)."""
@@ -181,10 +205,28 @@ def ezinct(ny: int, ezi, hxi, bc) -> None:
     check(lib().fdtd2d_ezinct(_code(ezi), ny, _ptr(ezi), _ptr(hxi), _ptr(bc), _stream()), "ezinct")
 
 
-def dfield(t: int, nx: int, ny: int, pml: pmlayer, dz, hx, hy, *, source=None, ezi=None) -> None:
+def dfield(t: int, nx: int, ny: int, *args, source=None, ezi=None) -> None:
     """D update; then the source sample of step ``t``: an :class:`IncidentWave` sets ``ezi[3]``, a
-    :class:`PointSource` sets / adds to ``dz[i, j]``.  (The reference hard-codes the waveform here.)"""
+    :class:`PointSource` sets / adds to ``dz[i, j]``.  (The reference hard-codes the waveform here.)
+
+    All three reference argument lists are accepted positionally: ``dfield(t, nx, ny, dz, hx, hy)`` (free space,
+    fd2d/program/fd2d_3_1.py:44), ``dfield(t, nx, ny, pml, dz, hx, hy)`` (3_2, fd2d_3_2.py:61) and
+    ``dfield(t, nx, ny, pml, ezi, dz, hx, hy)`` (3_3 / 3_4, fd2d_3_3.py:68)."""
+    if args and isinstance(args[0], pmlayer):
+        pml, arrays = args[0], args[1:]
+    else:                                             # program 3_1: no PML -- the identity coefficient set
+        pml, arrays = None, args
+    if len(arrays) == 4:
+        if ezi is not None:
+            raise TypeError("dfield: ezi given both positionally and by keyword")
+        ezi, dz, hx, hy = arrays
+    elif len(arrays) == 3:
+        dz, hx, hy = arrays
+    else:
+        raise TypeError(f"dfield takes (dz, hx, hy) or (ezi, dz, hx, hy) after pml, got {len(arrays)} arrays")
     _require_cuda(dz, hx, hy, ezi)
+    if pml is None:
+        pml = pmlparam(nx, ny, 0, _NP_DT[dz.dtype], dz.device)
     src = None
     if isinstance(source, IncidentWave):
         src = _src_struct(ezi, 3, source.waveform.table(int(t), 1)[0], True)
@@ -200,9 +242,25 @@ def inctdz(nx: int, ny: int, npml: int, hxi, dz) -> None:
     check(lib().fdtd2d_inctdz(_code(dz), nx, ny, npml, _ptr(hxi), _ptr(dz), _stream()), "inctdz")
 
 
-def efield(nx: int, ny: int, md, dz, ez, iz=None) -> None:
-    """``md`` is the ``naz`` tensor (programs 3_1-3_3) or a :class:`medium` (3_4, with ``iz``)."""
+def efield(nx: int, ny: int, md, dz, *rest, iz=None, ez=None) -> None:
+    """Reference argument order, both forms: ``efield(nx, ny, naz, dz, ez)`` (programs 3_1-3_3,
+    fd2d/program/fd2d_3_3.py:81) and ``efield(nx, ny, md, dz, iz, ez)`` with a lossy :class:`medium` (3_4,
+    fd2d/python/fd2d_3_4.py:131).  ``iz`` / ``ez`` may also be given by keyword."""
+    if len(rest) == 2:
+        if iz is not None or ez is not None:
+            raise TypeError("efield: iz / ez given both positionally and by keyword")
+        iz, ez = rest
+    elif len(rest) == 1:
+        if ez is not None:
+            raise TypeError("efield: ez given both positionally and by keyword")
+        ez = rest[0]
+    elif len(rest) != 0:
+        raise TypeError(f"efield takes (dz, ez) or (dz, iz, ez) after the medium, got {1 + len(rest)} arrays")
+    if ez is None:
+        raise TypeError("efield: ez is missing")
     md = md if isinstance(md, medium) else medium(md)
+    if (md.nbz is None) != (iz is None):
+        raise _lib.FdtdError("efield: a lossy medium (nbz) and iz go together -- efield(nx, ny, md, dz, iz, ez)")
     _require_cuda(md.naz, md.nbz, dz, ez, iz)
     ms = _lib.Medium2D(md.naz.data_ptr(), None if md.nbz is None else md.nbz.data_ptr())
     check(lib().fdtd2d_efield(_code(dz), nx, ny, C.byref(ms), _ptr(dz), _ptr(iz), _ptr(ez), _stream()), "efield")
@@ -434,9 +492,10 @@ class Fdtd2D:
         if nsteps <= 0:
             return
         if self.ft is not None and len(self.freqs) > 3:
-            # more frequencies than the fused kernels carry: one fused single-step pass + the fourier kernel per step
+            # more frequencies than the fused kernels carry: one fused single-step pass WITHOUT the accumulators
+            # attached, then the fourier kernel -- which alone updates them -- per step
             for _ in range(int(nsteps)):
-                self._advance_fused(1, 1, False, None)
+                self._advance_fused(1, 1, False, None, carry_dft=False)
                 self._fourier(self.t)
             return
         self._advance_fused(int(nsteps), tblock, lazy_ez, epoch)
@@ -446,7 +505,7 @@ class Fdtd2D:
             fourier(t, len(self.freqs), self.rows_alloc, self.ny, self.dt, self.freqs, self.ezi,
                     self.tensor("ez", stored=True), self.ft)
 
-    def _advance_fused(self, nsteps: int, tblock, lazy_ez: bool, epoch: Optional[int] = None) -> None:
+    def _advance_fused(self, nsteps: int, tblock, lazy_ez: bool, epoch: Optional[int] = None, carry_dft: bool = True) -> None:
         tb = int(tblock if tblock is not None else self.tblock)
         if tb > self.max_tblock:
             raise _lib.FdtdError(f"tblock {tb} exceeds the deepest supported time block {self.max_tblock}")
@@ -470,7 +529,7 @@ class Fdtd2D:
                         getattr(p, key)[s][k] = nb["sets"][s].get(n)          # peer-mapped raw pointers
                 setattr(p, key + "_base", int(nb["row_base"]))
                 setattr(p, "sync_" + side, nb["sync"])
-        if self.ft is not None:
+        if self.ft is not None and carry_dft:
             # running DFT fused into the passes: per-step phase factors, evaluated as the reference evaluates them
             nf = len(self.freqs)
             cos_t, sin_t = _phase_tables(self.freqs, self.dt, self.t + 1, nsteps, False, self.np_dtype)
@@ -488,17 +547,18 @@ class Fdtd2D:
         self.t += int(nsteps)
 
     # ---- streamed run: host medium in, host Ez out, PCIe overlapped with the time stepping ----------------
-    def _depths(self, nsteps: int, tblock=None):
-        """Pass depths the library will use for ``nsteps`` (instantiated depths: 1, 2, 3, 4, 6, 8)."""
-        tb = int(tblock if tblock else (self.tblock or (6 if self.np_dtype == np.float32 else 4)))
-        out, left = [], int(nsteps)
-        while left > 0:
-            d = min(tb, left)
-            if d in (5, 7):
-                d -= 1
-            out.append(d)
-            left -= d
-        return out
+    def pass_depths(self, nsteps: int, tblock=None, rows=None):
+        """Pass depths ``advance(nsteps, tblock)`` will use, asked from the library (``fdtd2d_plan``): it chooses them by
+        the rows a call produces (``rows``: one block of a streamed run), the step count, dtype and features."""
+        p = _lib.Problem2D()
+        p.dtype = _lib.dtype_code(self.np_dtype)
+        p.nx, p.ny = self.nx, self.ny
+        p.row_lo, p.row_hi = (self.row_lo, self.row_hi) if rows is None else (int(rows[0]), int(rows[1]))
+        p.flags = _lib.LOSSY if self.lossy else 0
+        p.nf = 0 if self.ft is None else min(len(self.freqs), 3)
+        return _plan(p, nsteps, tblock if tblock is not None else self.tblock)[0]
+
+    _depths = pass_depths
 
     def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, blocks: Optional[int] = None,
                      tblock=None, streams: int = 16, trace: Optional[list] = None, block_rows=None,
@@ -790,7 +850,10 @@ class Fdtd2D:
             dfield(t, nx, ny, self.pml, s["dz"], s["hx"], s["hy"], source=self.source, ezi=self.ezi)
             if self.tfsf:
                 inctdz(nx, ny, n, self.hxi, s["dz"])
-            efield(nx, ny, medium(self.naz, self.nbz), s["dz"], s["ez"], s.get("iz"))
+            if self.lossy:
+                efield(nx, ny, medium(self.naz, self.nbz), s["dz"], s["iz"], s["ez"])
+            else:
+                efield(nx, ny, self.naz, s["dz"], s["ez"])
             if self.ft is not None:
                 fourier(t, len(self.freqs), nx, ny, self.dt, self.freqs, self.ezi, s["ez"], self.ft)
             if self.tfsf:

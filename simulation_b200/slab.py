@@ -44,8 +44,22 @@ class SlabFdtd2D:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.nx, self.ny = int(nx), int(ny)
-        self.ghost = int(ghost if ghost is not None else tblock)
         self.row_lo, self.row_hi = partition(self.nx, self.world, self.rank)
+        if ghost is None:
+            if tblock:
+                ghost = int(tblock)
+            elif engine_factory is None:
+                # the library chooses the pass depth by slab size: ask it (the thinnest slab decides for everybody)
+                from .fd2d import plan_depths
+                thin = partition(self.nx, self.world, self.world - 1)
+                freqs = engine_kw.get("freqs")
+                ghost = plan_depths(self.nx, self.ny, dtype, 1 << 10, 0, rows=thin, lossy=engine_kw.get("nbz") is not None,
+                                    nf=0 if freqs is None else min(len(freqs), 3))[0]
+            else:
+                ghost = 4
+        self.ghost = int(ghost)
+        if self.world > 1 and self.ghost < 1:
+            raise ValueError(f"ghost band of {self.ghost} rows: at least one ghost row is needed between exchanges")
         if self.world > 1 and (self.row_hi - self.row_lo) < self.ghost:
             raise ValueError(f"slab of {self.row_hi - self.row_lo} rows is thinner than the ghost band {self.ghost}")
         want = halo or os.environ.get("FDTD_SLAB_HALO", "p2p")          # "p2p" (fused into the pass) or "nccl"
@@ -100,6 +114,35 @@ class SlabFdtd2D:
 
     def synchronize(self):
         self.engine.synchronize()
+        self.check_halo()
+
+    def check_halo(self) -> None:
+        """Raise if a pass of the fused halo exchange gave up waiting for a neighbour (a rank that died or skipped a
+        call): the library bounds that wait and records the failure instead of hanging (``fdtd2d_halo_status``)."""
+        eng = self.engine
+        if eng is None or getattr(eng, "p2p", None) is None:
+            return
+        from . import _lib
+        import ctypes as C
+        prob = _lib.Problem2D()
+        prob.sync_local = eng.p2p["sync"].ptr
+        word = C.c_ulonglong(0)
+        with torch.cuda.device(eng.device):
+            _lib.check(_lib.lib().fdtd2d_halo_status(C.byref(prob), C.byref(word)), "fdtd2d_halo_status")
+        if word.value:
+            raise _lib.FdtdError("fused halo exchange failed: " + _lib.lib().fdtd_last_error().decode(errors="replace"))
+
+    # ---- checkpoint / restore ------------------------------------------------------------------------
+    def checkpoint(self) -> dict:
+        """This rank's part of a checkpoint (owned rows, see :meth:`fd2d.Fdtd2D.checkpoint`); collective only in
+        that every rank should take it after the same ``advance`` calls."""
+        return self.engine.checkpoint()
+
+    def restore(self, ckpt: dict) -> None:
+        """Inverse of :meth:`checkpoint` on every rank.  The engine restores the owned rows only, so the ghost rows
+        are marked stale and refreshed from the neighbours before the next block of steps."""
+        self.engine.restore(ckpt)
+        self._ghost_dirty = self.world > 1
 
     # ---- fused halo exchange over peer memory ------------------------------------------------------------
     def _enable_p2p(self) -> None:
@@ -109,7 +152,7 @@ class SlabFdtd2D:
         eng = self.engine
         names = self._names()
         with torch.cuda.device(eng.device):
-            sync = _lib.DeviceBuffer((4,), np.int64)
+            sync = _lib.DeviceBuffer((8,), np.int64)          # {from_up, from_down, counter, counter, error, reserved}
             mine = {"row_base": eng.row_base, "sync": sync.ipc_handle(),
                     "sets": [{n: eng._ipc_handles[s][n] for n in names} for s in range(2)]}
             everyone = [None] * self.world
@@ -196,7 +239,7 @@ class SlabFdtd2D:
                 # the pass pushes its edge rows into the neighbours' ghost rows and waits on their flags itself.
                 # ONE pass per call: the push lands in the set the neighbour's earlier passes of a multi-pass call
                 # would still be reading (the per-call handshake only orders whole calls)
-                n_one = self.engine._depths(n, tblock)[0]
+                n_one = self.engine.pass_depths(n, tblock)[0]
                 left += n - n_one
                 n = n_one
                 self._epoch += 1

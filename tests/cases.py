@@ -55,7 +55,7 @@ LINE_MAIN = {"1_1": (512, 300), "1_2": (512, 570), "1_3": (512, 740), "1_4": (51
              "1_5": (512, 740), "2_1": (512, 740), "2_2": (512, 740), "2_3": (512, 740)}
 
 
-def grid_program(prog, nx, ny, ns, dtype, npml=8, naz=None, radius=0.15, dft=True):
+def grid_program(prog, nx, ny, ns, dtype, npml=8, naz=None, radius=0.15, dft=True, freqs=(50e6, 300e6, 700e6)):
     """2D programs 3_1 .. 3_4 at arbitrary size / dtype."""
     if prog == "3_1":
         g = orc.Grid2D(nx, ny, 0, dtype, point=(nx // 2, ny // 2), naz=naz)
@@ -70,7 +70,7 @@ def grid_program(prog, nx, ny, ns, dtype, npml=8, naz=None, radius=0.15, dft=Tru
         rgrid = int(radius / 0.01 - 1)
         md_naz, md_nbz = orc.cylinder_medium(nx, ny, npml, rgrid, DT, 30.0, 0.30, dtype)
         g = orc.Grid2D(nx, ny, npml, dtype, tfsf=True, lossy=True, naz=md_naz, nbz=md_nbz,
-                       freqs=np.array((50e6, 300e6, 700e6), dtype=dtype) if dft else None)
+                       freqs=np.array(freqs, dtype=dtype) if dft else None)
         src = orc.source_table("gaussian", ns, t0=20, spread=8.0)
     else:
         raise KeyError(prog)

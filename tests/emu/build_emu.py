@@ -108,6 +108,7 @@ ASM = [  # the kernels' inline PTX, statement by statement -> its emulation (tes
     (r'asm volatile\("cp\.async\.wait_group %0;" ::"n"\((\w+)\) : "memory"\);', r'emu::cp_async_wait(\1);'),
     (r'asm volatile\("ld\.acquire\.sys\.global\.u64 %0, \[%1\];" : "=l"\((\w+)\) : "l"\((\w+)\) : "memory"\);', r'\1 = emu::ld_acquire(\2);'),
     (r'asm volatile\("st\.release\.sys\.global\.u64 \[%0\], %1;" ::"l"\((\w+)\), "l"\((\w+)\) : "memory"\);', r'emu::st_release(\1, \2);'),
+    (r'asm volatile\("mov\.u64 %0, %%globaltimer;" : "=l"\((\w+)\)\);', r'\1 = emu::global_timer_ns();'),
 ]
 
 
@@ -126,7 +127,8 @@ def rewrite_device_code(src: str) -> str:
 def build(*source_names: str) -> str:
     """-> path of the emulated shared object made of simulation_b200/csrc/<source_names>"""
     srcs = {n: open(os.path.join(CSRC, n)).read() for n in source_names}
-    hdr = open(os.path.join(HERE, "cuda_runtime.h")).read() + open(os.path.join(CSRC, "common.cuh")).read() \
+    cuh = {n: open(os.path.join(CSRC, n)).read() for n in sorted(os.listdir(CSRC)) if n.endswith(".cuh")}
+    hdr = open(os.path.join(HERE, "cuda_runtime.h")).read() + "".join(cuh.values()) \
         + open(os.path.join(ROOT, "include", "fdtd_b200.h")).read() + open(__file__).read()
     tag = hashlib.sha256(("".join(srcs.values()) + hdr).encode()).hexdigest()[:16]
     bdir = os.path.join(HERE, "_build")
@@ -144,6 +146,12 @@ def build(*source_names: str) -> str:
         return so
     stubs = STUBS if "fd2d_steps.cu" not in srcs else STUBS.replace(STUBS[STUBS.index("int launch_fourier"):STUBS.index("}\nextern")], "")
     assert "capi_misc.cu" not in srcs, "capi_misc.cu is replaced by the stubs"
+    # the kernels' shared headers carry inline PTX too: rewritten copies shadow the originals on the include path
+    inc = os.path.join(bdir, f"inc_{tag}")
+    os.makedirs(inc, exist_ok=True)
+    for n, text in cuh.items():
+        with open(os.path.join(inc, n), "w") as f:
+            f.write(rewrite_device_code(text).replace('"../../include/fdtd_b200.h"', '"fdtd_b200.h"'))
     units = {"stubs": '#include "common.cuh"\n' + stubs}
     for n, src in srcs.items():
         units[os.path.splitext(n)[0]] = f'#line 1 "{n}"\n' + rewrite_launches(rewrite_device_code(src))
@@ -154,7 +162,7 @@ def build(*source_names: str) -> str:
             f.write(text)
         obj = os.path.join(bdir, f"emu_{name}_{tag}.o")
         subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fno-strict-aliasing", "-fPIC", "-pthread", "-w",
-                        "-I", HERE, "-I", CSRC, "-x", "c++", "-c", cpp, "-o", obj], check=True)
+                        "-I", inc, "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-x", "c++", "-c", cpp, "-o", obj], check=True)
         os.remove(cpp)
         return obj
 
@@ -168,7 +176,7 @@ def build(*source_names: str) -> str:
     return so
 
 
-ALL_SOURCES = ("fd1d.cu", "fd2d_steps.cu", "fd2d_march.cu")
+ALL_SOURCES = ("fd1d.cu", "fd2d_steps.cu", "fd2d_march.cu", "fd2d_deep.cu")
 
 
 def build_library() -> str:

@@ -65,4 +65,6 @@ def install(monkeypatch):
         monkeypatch.setattr(mod, "_stream", no_stream)
         monkeypatch.setattr(mod, "_require_cuda", accept)
     h.fdtd2d_tune(0, 0, 0, 0, 0)
+    h.fdtd2d_tune2(0, 1)            # deep passes on (default), default halo wait
+    h.fdtd2d_tune2(1, 0)
     return h

@@ -57,7 +57,7 @@ def test_argument_validation_without_a_device():
     p = _lib.Problem2D()
     p.nx = p.ny = 64
     p.row_hi = p.rows_alloc = 64
-    assert h.fdtd2d_advance(C.byref(p), 0, 1, None, 9, None, C.byref(out)) == -1
+    assert h.fdtd2d_advance(C.byref(p), 0, 1, None, 13, None, C.byref(out)) == -1
     assert b"tblock" in h.fdtd_last_error()
     q = _lib.Problem1D()
     q.nx = 2

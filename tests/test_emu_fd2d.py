@@ -25,15 +25,17 @@ def emu(monkeypatch):
     return device.install(monkeypatch)
 
 
-def _run(emu, prog, nx, ny, npml, ns, dtype, tblock=None, radius=0.12, tune=(0, 0, 0, 0, 0), parts=None):
+def _run(emu, prog, nx, ny, npml, ns, dtype, tblock=None, radius=0.12, tune=(0, 0, 0, 0, 0), parts=None, deep=1):
     before = emu.emu_launches()
     emu.fdtd2d_tune(*tune)
+    emu.fdtd2d_tune2(0, deep)
     try:
         sim = _sim_for(prog, nx, ny, dtype, npml=npml, radius=radius, device="cpu")
         for part in (parts or (ns,)):
             sim.advance(part, tblock=tblock)
     finally:
         emu.fdtd2d_tune(0, 0, 0, 0, 0)
+        emu.fdtd2d_tune2(0, 1)
     assert sim.t == ns and emu.emu_launches() > before
     g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=radius, dft=False)
     orc.advance_2d(g, src)
@@ -200,10 +202,11 @@ def test_emulated_streamed_run_on_a_slab(emu, schedule):
 
 
 class _SyncWords:
-    """stands in for the library-allocated sync words of slab.py: {flag from up, flag from down, counter 0, counter 1}"""
+    """stands in for the library-allocated sync words of slab.py: {flag from up, flag from down, counter 0, counter 1,
+    error word, reserved x 3}"""
 
     def __init__(self):
-        self.words = np.zeros(4, dtype=np.int64)
+        self.words = np.zeros(8, dtype=np.int64)
         self.ptr = self.words.ctypes.data
 
 
@@ -247,6 +250,175 @@ def test_emulated_fused_halo_exchange(emu, prog, nslab, order):
     for n in names + ["ez"]:
         got = np.concatenate([s.get(n) for s in slabs])
         assert got.tobytes() == getattr(g, n).tobytes(), (n, np.argwhere(got != getattr(g, n))[:4].tolist())
+
+
+# ---------------------------------------------------------------------------------------- deep passes (fd2d_deep.cu)
+@pytest.mark.parametrize("tblock,chunk_rows", [(12, 40), (8, 40), (12, 0), (8, 64)])
+@pytest.mark.parametrize("prog,nx,ny,npml", [("3_2", 300, 1100, 8), ("3_3", 280, 1000, 12)])
+def test_emulated_deep_passes(emu, prog, nx, ny, npml, tblock, chunk_rows):
+    """Depth 8 and 12: the interior kernel with shared-memory-resident accumulators (dz, hx, hy in registers; ihx, ihy,
+    naz in each lane's own shared-memory column; Ez re-evaluated) + the shared-memory-ring careful kernel, on grids with
+    a true interior; ragged last strips and chunks, a remainder pass of the register-pipeline kernels at the end."""
+    before = emu.emu_launches()
+    sim = _run(emu, prog, nx, ny, npml, 2 * tblock + 3, np.float32, tblock, radius=0.3, tune=(4, chunk_rows, 0, 0, 0))
+    emu.fdtd2d_tune(4, chunk_rows, 0, 0, 0)
+    try:
+        assert sim.pass_depths(2 * tblock + 3, tblock) == [tblock, tblock, 3]
+    finally:
+        emu.fdtd2d_tune(0, 0, 0, 0, 0)
+    assert sim.max_tblock == 12
+    if chunk_rows:       # 3 passes x (careful + interior [+ incident line]) + the two identity checks of the setup
+        assert emu.emu_launches() - before == 3 * (3 if prog == "3_3" else 2) + 2, "an interior kernel did not run in every pass"
+
+
+def test_emulated_deep_equals_register_pipeline(emu):
+    """Same problem through the deep passes (8 + 8 + 8), the register-pipeline kernels alone (deep off: 8 + 8 + 8 with
+    the naz ring) and depth 6: all arrays byte-identical."""
+    nx, ny, npml, ns = 300, 900, 10, 24
+    a = _run(emu, "3_3", nx, ny, npml, ns, np.float32, 8, tune=(4, 48, 0, 0, 0), deep=1)
+    b = _run(emu, "3_3", nx, ny, npml, ns, np.float32, 8, tune=(4, 48, 0, 0, 0), deep=0)
+    c = _run(emu, "3_3", nx, ny, npml, ns, np.float32, 6, tune=(4, 48, 0, 0, 0))
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert a.get(name).tobytes() == b.get(name).tobytes() == c.get(name).tobytes(), name
+
+
+@pytest.mark.parametrize("prog,tblock", [("3_2", 6), ("3_3", 4), ("3_4", 6), ("3_4", 3), ("3_1", 8), ("3_3", 12)])
+def test_emulated_ring_careful_kernel_at_every_depth(emu, prog, tblock):
+    """fdtd2d_tune2(deep = 2): the shared-memory-ring careful kernel (run-time depth, rolled stages) replaces the
+    register-shifting one in every float / 4-wide pass -- lossless and lossy, TFSF, point source; once for the whole
+    grid (force_careful) and once beside the interior kernels."""
+    for force in (1, 0):
+        _run(emu, prog, 150, 560, 0 if prog == "3_1" else 9, 2 * tblock + 1, np.float32, tblock, radius=0.3,
+             tune=(4, 24, 0, 0, force), deep=2)
+
+
+def test_emulated_plan_query(emu):
+    """fdtd2d_plan is what advance() does: depths by grid size and step count, without launching anything."""
+    from simulation_b200 import fd2d
+    before = emu.emu_launches()
+    assert fd2d.plan_depths(32768, 32768, np.float32, 20) == [12, 8]                  # the driver's bench call
+    assert fd2d.plan_depths(32768, 32768, np.float32, 96) == [12] * 8
+    assert fd2d.plan_depths(32768, 32768, np.float32, 96, tblock=6) == [6] * 16
+    assert fd2d.plan_depths(32768, 32768, np.float32, 31, tblock=7) == [6] * 5 + [1]
+    assert fd2d.plan_depths(32768, 32768, np.float64, 20) == [6, 6, 6, 2]               # float64: register pipeline only
+    assert fd2d.plan_depths(32768, 32766, np.float32, 20) == [6, 6, 6, 2]               # ny not a multiple of 4
+    assert fd2d.plan_depths(32768, 32768, np.float32, 20, lossy=True) == [6, 6, 6, 2]   # lossy: 2-wide register pipeline
+    assert fd2d.plan_depths(32768, 32768, np.float32, 20, nf=3) == [4] * 5              # fused DFT: depth <= 4
+    assert fd2d.plan_depths(1024, 1024, np.float32, 20) == [4] * 5                      # small grids: shallow, many warps
+    assert fd2d.plan_depths(8 * 32768, 32768, np.float32, 12, rows=(4096, 8192)) == [12]   # a slab of the strong split
+    emu.fdtd2d_tune2(0, 0)
+    try:
+        assert fd2d.plan_depths(32768, 32768, np.float32, 20) == [6, 6, 6, 2]
+    finally:
+        emu.fdtd2d_tune2(0, 1)
+    assert emu.emu_launches() == before
+
+
+def test_emulated_fused_halo_exchange_deep_and_missing_neighbour(emu):
+    """The fused exchange at depth 12 (deep interior + ring careful kernel carrying the handshake), then a rank that
+    SKIPS an epoch: its neighbour's wait is bounded -- it gives up, raises the error word and the host reports it
+    instead of hanging."""
+    import ctypes as C
+    from simulation_b200 import _lib, fd2d
+    nx, ny, npml, T, nslab, dtype = 360, 640, 8, 12, 3, np.float32
+    emu.fdtd2d_tune(4, 24, 0, 0, 0)
+    try:
+        cuts = np.linspace(0, nx, nslab + 1).astype(int)
+        slabs = [_sim_for("3_2", nx, ny, dtype, npml=npml, rows=(int(lo), int(hi)), ghost=T, tblock=T, device="cpu")
+                 for lo, hi in zip(cuts[:-1], cuts[1:])]
+        names = [n for n in fd2d.FIELD_NAMES if n not in ("ez", "iz")]
+        for s in slabs:
+            s._sync_words = _SyncWords()
+        for r, s in enumerate(slabs):
+            def peer(q):
+                if q is None:
+                    return None
+                o = slabs[q]
+                return {"row_base": o.row_base, "sync": o._sync_words.ptr,
+                        "sets": [{n: o._sets[k][n].data_ptr() for n in names} for k in range(2)]}
+            s.p2p = {"halo": T, "sync": s._sync_words, "up": peer(r - 1 if r > 0 else None), "dn": peer(r + 1 if r < nslab - 1 else None)}
+        for epoch in (1, 2, 3):
+            for r in (1, 0, 2):
+                slabs[r].advance(T, tblock=T, lazy_ez=epoch < 3, epoch=epoch)
+        g, src = cases.grid_program("3_2", nx, ny, 3 * T, dtype, npml=npml, dft=False)
+        orc.advance_2d(g, src)
+        for n in names + ["ez"]:
+            got = np.concatenate([s.get(n) for s in slabs])
+            assert got.tobytes() == getattr(g, n).tobytes(), (n, np.argwhere(got != getattr(g, n))[:4].tolist())
+        assert all(int(s._sync_words.words[4]) == 0 for s in slabs)
+        # epoch 4: rank 0 runs, rank 1 skips it; epoch 5 on rank 0 then needs rank 1's epoch-4 flag, which never comes
+        emu.fdtd2d_tune2(1, 50)                    # bound the wait to 50 ms
+        slabs[0].advance(T, tblock=T, epoch=4)
+        slabs[0].advance(T, tblock=T, epoch=5)     # returns (the emulated kernel gives up after the bound)
+        word = C.c_ulonglong(0)
+        prob = _lib.Problem2D()
+        prob.sync_local = slabs[0]._sync_words.ptr
+        assert emu.fdtd2d_halo_status(C.byref(prob), C.byref(word)) == 0
+        assert word.value == (5 << 2) | 2, word.value          # epoch 5, lower neighbour
+        assert b"gave up" in emu.fdtd_last_error() and b"lower" in emu.fdtd_last_error()
+    finally:
+        emu.fdtd2d_tune(0, 0, 0, 0, 0)
+        emu.fdtd2d_tune2(1, 0)
+
+
+def test_emulated_more_than_three_dft_frequencies(emu):
+    """advance() with 4 frequencies: the fused kernels carry at most 3, so every step is one single-step pass (WITHOUT
+    the accumulators attached) + the fourier kernel; bit-identical to the oracle's per-step accumulation."""
+    nx, ny, npml, ns = 60, 72, 8, 23
+    freqs = [50e6, 300e6, 700e6, 1100e6]
+    from simulation_b200 import fd2d, surface
+    g, src = cases.grid_program("3_4", nx, ny, ns, np.float32, npml=npml, radius=0.12, dft=True, freqs=freqs)
+    sim = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)),
+                      naz=g.naz.copy(), nbz=g.nbz.copy(), freqs=g.freqs, device="cpu")
+    sim.advance(9)
+    sim.advance(ns - 9, tblock=4)
+    orc.advance_2d(g, src)
+    for name in ("dz", "ez", "iz", "hx", "hy", "r_pt", "i_pt", "r_in", "i_in"):
+        got, want = sim.get(name), getattr(g, name)
+        assert got.tobytes() == want.tobytes(), (name, np.argwhere(got != want)[:4].tolist())
+
+
+def test_emulated_reference_positional_argument_lists(emu):
+    """The module-level step functions take the reference's own positional argument lists (fd2d/program/fd2d_3_1.py:44,
+    fd2d_3_3.py:68,81; fd2d/python/fd2d_3_4.py:131): dfield with and without pml / ezi, efield(md, dz, iz, ez)."""
+    from simulation_b200 import fd2d, surface
+    nx, ny, npml, ns = 48, 64, 6, 30
+    rgrid = 9
+    naz, nbz = surface.dielectric_cylinder(nx, ny, npml, rgrid, surface.DT, 30.0, 0.30, np.float32)
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float32)
+    ezi, hxi, bc = z(ny), z(ny), z(4)
+    dz, ez, iz, hx, hy, ihx, ihy = (z(nx, ny) for _ in range(7))
+    pml = fd2d.pmlparam(nx, ny, npml, np.float32, device="cpu")
+    md = fd2d.medium(torch.from_numpy(naz), torch.from_numpy(nbz))
+    wave = fd2d.IncidentWave(surface.Gaussian(20, 8.0))
+    for t in range(1, ns + 1):
+        fd2d.ezinct(ny, ezi, hxi, bc)
+        fd2d.dfield(t, nx, ny, pml, ezi, dz, hx, hy, source=wave)          # reference 3_3 / 3_4 order
+        fd2d.inctdz(nx, ny, npml, hxi, dz)
+        fd2d.efield(nx, ny, md, dz, iz, ez)                                # reference 3_4 order
+        fd2d.hxinct(ny, ezi, hxi)
+        fd2d.hfield(nx, ny, pml, ez, ihx, ihy, hx, hy)
+        fd2d.incthx(nx, ny, npml, ezi, hx)
+        fd2d.incthy(nx, ny, npml, ezi, hy)
+    g = orc.Grid2D(nx, ny, npml, np.float32, tfsf=True, lossy=True, naz=naz.copy(), nbz=nbz.copy())
+    orc.advance_2d(g, orc.source_table("gaussian", ns, t0=20, spread=8.0))
+    for name, got in (("dz", dz), ("ez", ez), ("iz", iz), ("hx", hx), ("hy", hy), ("ihx", ihx), ("ihy", ihy)):
+        assert got.numpy().tobytes() == getattr(g, name).tobytes(), name
+    # free space (program 3_1): dfield(t, nx, ny, dz, hx, hy) without a pmlayer, efield(nx, ny, naz, dz, ez)
+    dz, ez, hx, hy = (z(nx, ny) for _ in range(4))
+    one = torch.ones(nx, ny)
+    src = fd2d.PointSource(nx // 2, ny // 2, surface.Gaussian(20, 6.0))
+    for t in range(1, 21):
+        fd2d.dfield(t, nx, ny, dz, hx, hy, source=src)
+        fd2d.efield(nx, ny, one, dz, ez)
+        fd2d.hfield(nx, ny, fd2d.pmlparam(nx, ny, 0, np.float32, device="cpu"), ez, z(nx, ny), z(nx, ny), hx, hy)
+    g = orc.Grid2D(nx, ny, 0, np.float32, point=(nx // 2, ny // 2))
+    orc.advance_2d(g, orc.source_table("gaussian", 20, t0=20, spread=6.0))
+    assert np.array_equal(ez.numpy(), g.ez) and np.array_equal(hx.numpy(), g.hx)
+    with pytest.raises(TypeError):
+        fd2d.efield(nx, ny, md, dz)                                        # ez missing
+    with pytest.raises(Exception):
+        fd2d.efield(nx, ny, md, dz, ez)                                    # lossy medium without iz
 
 
 def test_emulated_lossless_outside_split(emu):

@@ -213,6 +213,65 @@ def test_fused_dft_all_depths(nx, ny, npml, tblock):
         assert got.tobytes() == want.tobytes(), (name, np.argwhere(got != want)[:4].tolist())
 
 
+def test_more_than_three_dft_frequencies():
+    """4 frequencies: beyond what the fused kernels carry -- one single-step pass (accumulators NOT attached) + the
+    fourier kernel per step; bit-identical to the oracle (regression: the accumulators used to be attached and the
+    library refused nf = 4)."""
+    from simulation_b200 import fd2d, surface
+    nx, ny, npml, ns = 60, 72, 8, 23
+    freqs = [50e6, 300e6, 700e6, 1100e6]
+    g, src = cases.grid_program("3_4", nx, ny, ns, np.float32, npml=npml, radius=0.12, dft=True, freqs=freqs)
+    sim = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)),
+                      naz=g.naz.copy(), nbz=g.nbz.copy(), freqs=g.freqs)
+    sim.advance(9)
+    sim.advance(ns - 9, tblock=4)
+    orc.advance_2d(g, src)
+    for name in ("dz", "ez", "iz", "hx", "hy", "r_pt", "i_pt", "r_in", "i_in"):
+        got, want = sim.get(name), getattr(g, name)
+        assert got.tobytes() == want.tobytes(), (name, np.argwhere(got != want)[:4].tolist())
+
+
+def test_reference_positional_argument_lists():
+    """The module-level step functions take the reference's own positional argument lists: dfield(t, nx, ny, pml, ezi,
+    dz, hx, hy) (fd2d/program/fd2d_3_3.py:68), efield(nx, ny, md, dz, iz, ez) (fd2d/python/fd2d_3_4.py:131), and the
+    free-space dfield(t, nx, ny, dz, hx, hy) of fd2d_3_1.py:44."""
+    from simulation_b200 import fd2d, surface
+    nx, ny, npml, ns = 48, 64, 6, 30
+    naz, nbz = surface.dielectric_cylinder(nx, ny, npml, 9, surface.DT, 30.0, 0.30, np.float32)
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device="cuda")
+    ezi, hxi, bc = z(ny), z(ny), z(4)
+    dz, ez, iz, hx, hy, ihx, ihy = (z(nx, ny) for _ in range(7))
+    pml = fd2d.pmlparam(nx, ny, npml, np.float32)
+    md = fd2d.medium(torch.from_numpy(naz).cuda(), torch.from_numpy(nbz).cuda())
+    wave = fd2d.IncidentWave(surface.Gaussian(20, 8.0))
+    for t in range(1, ns + 1):
+        fd2d.ezinct(ny, ezi, hxi, bc)
+        fd2d.dfield(t, nx, ny, pml, ezi, dz, hx, hy, source=wave)
+        fd2d.inctdz(nx, ny, npml, hxi, dz)
+        fd2d.efield(nx, ny, md, dz, iz, ez)
+        fd2d.hxinct(ny, ezi, hxi)
+        fd2d.hfield(nx, ny, pml, ez, ihx, ihy, hx, hy)
+        fd2d.incthx(nx, ny, npml, ezi, hx)
+        fd2d.incthy(nx, ny, npml, ezi, hy)
+    g = orc.Grid2D(nx, ny, npml, np.float32, tfsf=True, lossy=True, naz=naz.copy(), nbz=nbz.copy())
+    orc.advance_2d(g, orc.source_table("gaussian", ns, t0=20, spread=8.0))
+    for name, got in (("dz", dz), ("ez", ez), ("iz", iz), ("hx", hx), ("hy", hy), ("ihx", ihx), ("ihy", ihy)):
+        assert got.cpu().numpy().tobytes() == getattr(g, name).tobytes(), name
+    dz, ez, hx, hy = (z(nx, ny) for _ in range(4))
+    src = fd2d.PointSource(nx // 2, ny // 2, surface.Gaussian(20, 6.0))
+    for t in range(1, 21):
+        fd2d.dfield(t, nx, ny, dz, hx, hy, source=src)
+        fd2d.efield(nx, ny, torch.ones_like(dz), dz, ez)
+        fd2d.hfield(nx, ny, fd2d.pmlparam(nx, ny, 0, np.float32), ez, z(nx, ny), z(nx, ny), hx, hy)
+    g = orc.Grid2D(nx, ny, 0, np.float32, point=(nx // 2, ny // 2))
+    orc.advance_2d(g, orc.source_table("gaussian", 20, t0=20, spread=6.0))
+    assert np.array_equal(ez.cpu().numpy(), g.ez) and np.array_equal(hx.cpu().numpy(), g.hx)
+    with pytest.raises(TypeError):
+        fd2d.efield(nx, ny, md, dz)
+    with pytest.raises(Exception):
+        fd2d.efield(nx, ny, md, dz, ez)
+
+
 def test_fused_dft_lossless_point_source_fp64():
     """DFT on a lossless problem without TFSF (no source-sample accumulators), float64."""
     from simulation_b200 import fd2d, surface
@@ -363,6 +422,111 @@ def test_full_size_linearity_32768():
     assert float(a.tensor("ez").abs().max()) > 0.0
 
 
+# ------------------------------------------------------------------ deep passes (fd2d_deep.cu) and the bench's own launch plan
+@pytest.mark.parametrize("deep", [1, 2])
+@pytest.mark.parametrize("chunk_rows,tblock", [(40, 12), (24, 8), (0, 12), (64, 6)])
+@pytest.mark.parametrize("prog,nx,ny,npml", [("3_2", 420, 1100, 8), ("3_3", 400, 1000, 12), ("3_4", 380, 1040, 10)])
+def test_deep_passes_and_ring_careful_kernel(prog, nx, ny, npml, chunk_rows, tblock, deep):
+    """Depth 8 / 12 passes (shared-memory-resident accumulators + the shared-memory-ring careful kernel) and, with
+    deep = 2, the ring careful kernel at every depth, on grids with a true interior; bit-for-bit vs the oracle.  The
+    lossy program has no deep interior kernel: it exercises the fallback (register pipeline) and the lossy ring
+    careful kernel."""
+    from simulation_b200 import _lib
+    ns = 2 * tblock + 5
+    _lib.lib().fdtd2d_tune(4, chunk_rows, 0, 0, 0)
+    _lib.lib().fdtd2d_tune2(_lib.TUNE_DEEP, deep)
+    try:
+        sim = _sim_for(prog, nx, ny, np.float32, npml=npml, radius=0.3)
+        sim.advance(ns, tblock=tblock)
+        sim.synchronize()
+    finally:
+        _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
+        _lib.lib().fdtd2d_tune2(_lib.TUNE_DEEP, 1)
+    g, src = cases.grid_program(prog, nx, ny, ns, np.float32, npml=npml, radius=0.3, dft=False)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, prog)
+
+
+@pytest.mark.parametrize("tblock,chunk", [(0, 0), (6, 128), (8, 0)])
+def test_bench_launch_plan_vs_oracle(tblock, chunk):
+    """The launch plan bench.py runs at 32768^2 -- 4-wide vectors; depth 12 / 8 deep passes on 256-row chunks (tblock 0:
+    the library's own choice), or depth 6 on 128-row chunks (round 1's plan) -- forced onto a grid the numpy oracle can
+    still reach: 2304 x 4096, npml 80, several chunks and 40 strips, interior and careful kernels, 61 steps = depths
+    12 x 5 + 1.  Every array bit-for-bit."""
+    from simulation_b200 import _lib
+    nx, ny, npml, ns = 2304, 4096, 80, 61
+    rng = np.random.default_rng(5)
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    _lib.lib().fdtd2d_tune(4, chunk, 0, 0, 0)
+    try:
+        sim = _sim_for("3_2", nx, ny, np.float32, npml=npml, naz=naz, tblock=tblock)
+        depths = sim.pass_depths(ns)
+        sim.advance(ns)
+        sim.synchronize()
+    finally:
+        _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
+    assert depths == {0: [12] * 5 + [1], 6: [6] * 10 + [1], 8: [8] * 7 + [4, 1]}[tblock]
+    g, src = cases.grid_program("3_2", nx, ny, ns, np.float32, npml=npml, naz=naz.copy())
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, "3_2")
+    assert float(np.abs(g.ez).max()) > 0.1
+
+
+def test_baseline_config_5_full_size_vs_reference_c_openmp():
+    """BASELINE config 5 AT SIZE and with the bench's own call: 32768 x 32768 fp32, npml 80, point sinusoid, 24 steps
+    through Fdtd2D.advance (depths 12 + 12) against the REFERENCE's C/OpenMP step functions (oracle/_ref,
+    fd2d/clang/test_3_2.c) run on the host for the same 24 steps.  Tolerance as for config 4 (the C form 0.5f*a-0.5f*b
+    differs from numpy's 0.5*(a-b) only on subnormals); the numpy programs themselves are matched bit-for-bit by
+    test_bench_launch_plan_vs_oracle on the same kernels.  Needs 28 GiB of host memory and 52 GiB on the device."""
+    import os
+    from oracle import ref_c
+    from simulation_b200 import fd2d, surface
+    if not ref_c.available("3_2"):
+        pytest.skip("oracle/_ref not built")
+    n, npml, ns = 32768, 80, 24
+    avail = 0.0
+    for line in open("/proc/meminfo"):
+        if line.startswith("MemAvailable:"):
+            avail = int(line.split()[1]) / 2**20
+    if avail < 40:
+        pytest.skip(f"needs ~32 GiB of host memory, {avail:.0f} GiB available")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 13 * n * n * 4 * 1.05:
+        pytest.skip("needs 52 GiB of device memory")
+    import ctypes as C
+    cores = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+        gomp.omp_set_num_threads(cores)
+    except OSError:
+        pass
+    src = fd2d.PointSource(n // 2 - 5, n // 2 - 5, surface.Sinusoid(1500e6), hard=True)
+    sim = fd2d.Fdtd2D(n, n, npml, np.float32, source=src)
+    assert sim.pass_depths(ns) == [12, 12]
+    sim.advance(ns)
+    g = orc.Grid2D(n, n, npml, np.float32, point=(n // 2 - 5, n // 2 - 5))
+    table = orc.source_table("sine", ns, freq=1500e6)
+    lib = ref_c.load("3_2")
+    for k, t in enumerate(orc.step_indices(ns)):
+        ref_c.step_3_2(lib, t, g, table[k])
+    sim.synchronize()
+    i0, j0 = n // 2 - 5, n // 2 - 5
+    peak = float(np.abs(g.ez[i0 - 40:i0 + 40, j0 - 40:j0 + 40]).max())
+    assert peak > 0.1
+    band = 2048
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        want, got_t = getattr(g, name), sim.tensor(name)
+        worst = 0.0
+        for r in range(0, n, band):
+            got = got_t[r:r + band].cpu().numpy()
+            worst = max(worst, float(np.abs(got.astype(np.float64) - want[r:r + band]).max()))
+        assert worst <= 1e-5 * peak, (name, worst)                 # north-star tolerance
+        assert worst <= 5e-7 * peak, (name, worst)                 # in fact a few ulp
+    # the wave front has travelled 12 cells (0.5 cell per step): everything farther away is still exactly zero
+    assert not sim.tensor("ez")[:i0 - 30].any() and not sim.tensor("ez")[i0 + 30:].any()
+
+
 def test_baseline_config_4_vs_reference_c_openmp():
     """BASELINE config 4 at full size: 4096x4096 fp32, npml=80, TFSF Gaussian, lossy dielectric cylinder
     (eps_r=30, sigma=0.3, radius 6 m -> 599 cells), 300 steps -- the fused GPU path against the REFERENCE's own
@@ -375,7 +539,7 @@ def test_baseline_config_4_vs_reference_c_openmp():
     from simulation_b200 import fd2d, surface
     if not ref_c.available("3_4"):
         pytest.skip("oracle/_ref not built")
-    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     n, npml, ns = 4096, 80, 300
     rgrid = int(6.0 / 0.01 - 1)
     naz, nbz = surface.dielectric_cylinder(n, n, npml, rgrid, surface.DT, 30.0, 0.30, np.float32)

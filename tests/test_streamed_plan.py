@@ -19,9 +19,20 @@ import pytest
 from simulation_b200 import fd2d
 
 
+def _split(nsteps, tb):
+    """pass depths as the library cuts them (fdtd2d_plan): greedy, instantiated depths 1, 2, 3, 4, 6, 8, 12"""
+    out, left = [], int(nsteps)
+    while left > 0:
+        d = min(tb, left)
+        d = 12 if d >= 12 else (8 if d > 8 else (d - 1 if d in (5, 7) else d))
+        out.append(d)
+        left -= d
+    return out
+
+
 def _planner(rows_alloc, row_base=0, tblock=6):
     stub = types.SimpleNamespace(row_base=row_base, rows_alloc=rows_alloc, tblock=tblock, np_dtype=np.dtype(np.float32))
-    stub._depths = lambda n, tb=None: fd2d.Fdtd2D._depths(stub, n, tb)
+    stub._depths = lambda n, tb=None: _split(n, tb or tblock)      # (the product asks the library: Fdtd2D.pass_depths)
     stub._default_block_rows = lambda schedule, least: fd2d.Fdtd2D._default_block_rows(stub, schedule, least)
     return lambda *a, **k: fd2d.Fdtd2D.streamed_plan(stub, *a, **k)
 
@@ -117,6 +128,10 @@ CONFIGS = [
     (45, 0, 13, {"block_rows": [60, 111], "schedule": "wavefront"}),
     (4096, 0, 600, {}),                                                     # long run on a short grid: falls back to the wavefront
     (9000, 0, 61, {"tblock": 1, "streams": 16, "block_rows": 700}),
+    (32768, 0, 96, {"tblock": 12}),                                         # deep passes: 8 levels of 12 steps
+    (32768, 0, 20, {"tblock": 12}),                                         # the driver's bench call: depths 12 + 8
+    (32768 + 40, 32768 - 20, 20, {"tblock": 12}),                           # ... on a slab with a 20-row ghost band
+    (16384, 0, 50, {"tblock": 12, "block_rows": 1024, "streams": 3}),       # depths 12 x 4 + 2
 ]
 
 
