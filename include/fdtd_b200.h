@@ -257,6 +257,7 @@ int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, 
  * default of 20 s).  Results are bit-identical under every setting. */
 #define FDTD_TUNE_DEEP 0
 #define FDTD_TUNE_HALO_WAIT_MS 1
+#define FDTD_TUNE_VARIANT 2          /* kernel-shape experiments of the deep passes (0 = the shipped shape) */
 int fdtd2d_tune2(int key, long long value);
 
 #ifdef __cplusplus

@@ -31,34 +31,55 @@ constexpr int DV = 4;                 // columns per lane
 constexpr int DLB = DV * 4;           // bytes per lane per array row
 constexpr int DROWB = 32 * DLB;       // bytes per array row of a warp
 
-// Compile-time shape of one instantiation.  Staged per row (cp.async ring of DRING rows): dz hx hy ihx ihy naz [iz nbz];
-// resident per register row set (T+1 rows, compile-time slots): ihx ihy naz [iz nbz ez].
-template <int T, bool LOSSY, int DRING>
+// Compile-time shape of one instantiation.  Staged per row (cp.async ring of DRING rows): dz hx hy ihx ihy naz [iz nbz].
+// Resident per register row set (T+1 rows, compile-time slots): naz, and whichever of ihx / ihy / ez the registers do
+// not hold (KEEP bits) [lossy: iz nbz ez as well].  Shared-memory bandwidth is what bounds these kernels (128 B per
+// clock per SM: one LDS.128 / STS.128 of a warp is four cycles of the data pipe), so every array kept in registers
+// buys back eight (accumulators: read + write) or four (ez: the second read of naz) of the ~31 cycles a stage costs.
+constexpr int KEEP_IHX = 1, KEEP_EZ = 2, KEEP_IHY = 4;
+
+template <int T, bool LOSSY, int DRING, int WARPS_ = MAX_WARPS, int KEEP = 0>
 struct DeepShape {
     static constexpr int NS = T + 1;
     static constexpr int NSTG = LOSSY ? 8 : 6;
-    static constexpr int NRES = LOSSY ? 6 : 3;
+    static constexpr bool IHX_REG = (KEEP & KEEP_IHX) != 0, IHY_REG = (KEEP & KEEP_IHY) != 0;
+    static constexpr bool EZ_REG = (KEEP & KEEP_EZ) != 0 && !LOSSY;
+    // resident array slots, in order: naz [ihx] [ihy] [iz nbz ez]
+    static constexpr int R_NAZ = 0;
+    static constexpr int R_IHX = 1;                               // (meaningful only when !IHX_REG)
+    static constexpr int R_IHY = R_IHX + (IHX_REG ? 0 : 1);       // (meaningful only when !IHY_REG)
+    static constexpr int R_IZ = R_IHY + (IHY_REG ? 0 : 1);
+    static constexpr int R_NBZ = R_IZ + 1, R_EZ = R_IZ + 2;
+    static constexpr int NRES = R_IZ + (LOSSY ? 3 : 0);
     static constexpr int SLOT = NSTG * DROWB;             // staging bytes per row
     static constexpr int RA = NS * DROWB;                 // bytes of one resident array
     static constexpr int WARP_SMEM = DRING * SLOT + NRES * RA;
     static constexpr int MAXW = (227 * 1024) / WARP_SMEM;
-    static constexpr int WARPS = MAXW < MAX_WARPS ? MAXW : MAX_WARPS;
+    static constexpr int WARPS = MAXW < WARPS_ ? MAXW : WARPS_;
 };
-enum { R_IHX = 0, R_IHY, R_NAZ, R_IZ, R_NBZ, R_EZ };
 
-struct DeepRow { float dz[DV], hx[DV], hy[DV]; };
+struct DeepRow { float dz[DV], hx[DV], hy[DV], ihx[DV], ihy[DV], ez[DV]; };   // (ihx / ihy / ez: only where KEEP says so)
 
 __device__ __forceinline__ void sts4(void *dst, const float (&d)[DV]) {
     *reinterpret_cast<float4 *>(dst) = make_float4(d[0], d[1], d[2], d[3]);
 }
+// values computed in register PAIRS leave as two 64-bit halves: assembling an aligned quad for a 128-bit store costs
+// four moves (same bytes, same banks)
+__device__ __forceinline__ void sts22(void *dst, const float (&d)[DV]) {
+    *reinterpret_cast<float2 *>(dst) = make_float2(d[0], d[1]);
+    *reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(dst) + 8) = make_float2(d[2], d[3]);
+}
 
 // One stage in packed arithmetic: D, E of the arriving row A and H of the held row Hd, operation for operation what
-// march_stage_pk<4, NAZR = true> does -- with ihx / ihy read from and written back to the held row's resident slot.
-// resA / resH: this lane's 16 bytes in the resident slot of the arriving / the held row (array k at + k * RA).
-template <bool LOSSY, int RA>
+// march_stage_pk<4, ...> does -- with the accumulators that live in shared memory read from and written back to the
+// held row's resident slot.  resA / resH: this lane's 16 bytes in the resident slot of the arriving / the held row
+// (array k at + k * RA).
+template <typename Shape>
 __device__ __forceinline__ void deep_stage(DeepRow &A, DeepRow &Hd, unsigned char *const resA, unsigned char *const resH,
                                            const float2 negzero) {
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int RA = Shape::RA;
+    constexpr bool LOSSY = Shape::NSTG == 8;
     const float2 half2 = make_float2(0.5f, 0.5f), zero2 = make_float2(0.f, 0.f);
     // ---- D of the arriving row: dz = dz + 0.5*(((hy - hy[i-1]) - hx) + hx[j-1])
     const float hx_left = __shfl_up_sync(FULL, A.hx[DV - 1], 1);
@@ -72,11 +93,11 @@ __device__ __forceinline__ void deep_stage(DeepRow &A, DeepRow &Hd, unsigned cha
     }
     // ---- E of both rows
     float ezA[DV], ezH[DV], nzA[DV];
-    lds_vec<float, DV>(resA + R_NAZ * RA, nzA);
+    lds_vec<float, DV>(resA + Shape::R_NAZ * RA, nzA);
     if constexpr (LOSSY) {          // ez = naz*(dz - iz); iz = iz + nbz*ez -- ez kept for the next trip, iz in place
         float iz[DV], nb[DV];
-        lds_vec<float, DV>(resA + R_IZ * RA, iz);
-        lds_vec<float, DV>(resA + R_NBZ * RA, nb);
+        lds_vec<float, DV>(resA + Shape::R_IZ * RA, iz);
+        lds_vec<float, DV>(resA + Shape::R_NBZ * RA, nb);
 #pragma unroll
         for (int v = 0; v < DV; v += 2) {
             const float2 i0 = make_float2(iz[v], iz[v + 1]);
@@ -85,12 +106,19 @@ __device__ __forceinline__ void deep_stage(DeepRow &A, DeepRow &Hd, unsigned cha
             iz[v] = i2.x; iz[v + 1] = i2.y;
             ezA[v] = a.x; ezA[v + 1] = a.y;
         }
-        sts4(resA + R_IZ * RA, iz);
-        sts4(resA + R_EZ * RA, ezA);
-        lds_vec<float, DV>(resH + R_EZ * RA, ezH);
-    } else {
+        sts22(resA + Shape::R_IZ * RA, iz);
+        sts22(resA + Shape::R_EZ * RA, ezA);
+        lds_vec<float, DV>(resH + Shape::R_EZ * RA, ezH);
+    } else if constexpr (Shape::EZ_REG) {     // Ez travels with the row set
+#pragma unroll
+        for (int v = 0; v < DV; v += 2) {
+            const float2 a = pk_mul(make_float2(nzA[v], nzA[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
+            A.ez[v] = a.x; A.ez[v + 1] = a.y;
+            ezA[v] = a.x; ezA[v + 1] = a.y; ezH[v] = Hd.ez[v]; ezH[v + 1] = Hd.ez[v + 1];
+        }
+    } else {                                  // the held row's Ez is naz*dz evaluated again (same operands, same bits)
         float nzH[DV];
-        lds_vec<float, DV>(resH + R_NAZ * RA, nzH);
+        lds_vec<float, DV>(resH + Shape::R_NAZ * RA, nzH);
 #pragma unroll
         for (int v = 0; v < DV; v += 2) {
             const float2 a = pk_mul(make_float2(nzA[v], nzA[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
@@ -101,8 +129,18 @@ __device__ __forceinline__ void deep_stage(DeepRow &A, DeepRow &Hd, unsigned cha
     // ---- H of the held row: ihx += cm; ihy += cn; hx = hx + (0.5*cm + 0*ihx); hy = hy - (0.5*cn + 0*ihy)
     const float ez_right = __shfl_down_sync(FULL, ezH[0], 1);
     float ihx[DV], ihy[DV];
-    lds_vec<float, DV>(resH + R_IHX * RA, ihx);
-    lds_vec<float, DV>(resH + R_IHY * RA, ihy);
+    if constexpr (Shape::IHX_REG) {
+#pragma unroll
+        for (int v = 0; v < DV; ++v) ihx[v] = Hd.ihx[v];
+    } else {
+        lds_vec<float, DV>(resH + Shape::R_IHX * RA, ihx);
+    }
+    if constexpr (Shape::IHY_REG) {
+#pragma unroll
+        for (int v = 0; v < DV; ++v) ihy[v] = Hd.ihy[v];
+    } else {
+        lds_vec<float, DV>(resH + Shape::R_IHY * RA, ihy);
+    }
 #pragma unroll
     for (int v = 0; v < DV; v += 2) {
         const float2 e = make_float2(ezH[v], ezH[v + 1]);
@@ -117,16 +155,25 @@ __device__ __forceinline__ void deep_stage(DeepRow &A, DeepRow &Hd, unsigned cha
         ihx[v] = sx.x; ihx[v + 1] = sx.y; ihy[v] = sy.x; ihy[v + 1] = sy.y;
         Hd.hx[v] = hx2.x; Hd.hx[v + 1] = hx2.y; Hd.hy[v] = hy2.x; Hd.hy[v + 1] = hy2.y;
     }
-    sts4(resH + R_IHX * RA, ihx);
-    sts4(resH + R_IHY * RA, ihy);
+    if constexpr (Shape::IHX_REG) {
+#pragma unroll
+        for (int v = 0; v < DV; ++v) Hd.ihx[v] = ihx[v];
+    } else {
+        sts22(resH + Shape::R_IHX * RA, ihx);
+    }
+    if constexpr (Shape::IHY_REG) {
+#pragma unroll
+        for (int v = 0; v < DV; ++v) Hd.ihy[v] = ihy[v];
+    } else {
+        sts22(resH + Shape::R_IHY * RA, ihy);
+    }
 }
 
 // The march of one interior warp over its (strip, chunk): every column (halo included) is an ordinary cell and every
 // row touched is an ordinary stored row (the host's classification guarantees it), so there are no masks at all.
-template <int T, bool LOSSY, int DRING>
+template <typename Shape, int T, bool LOSSY, int DRING>
 __device__ __forceinline__ void deep_body(const MarchParams<float> &p, const int strip, const int i0, const int i1,
                                           const int lane, unsigned char *const smem) {
-    using Shape = DeepShape<T, LOSSY, DRING>;
     constexpr int W = 32 * DV;
     constexpr int HALO = ((T + DV - 1) / DV) * DV;
     constexpr int USE = W - 2 * HALO;
@@ -140,7 +187,7 @@ __device__ __forceinline__ void deep_body(const MarchParams<float> &p, const int
 #pragma unroll
     for (int k = 0; k < NS; ++k)
 #pragma unroll
-        for (int v = 0; v < DV; ++v) S[k].dz[v] = S[k].hx[v] = S[k].hy[v] = 0.f;
+        for (int v = 0; v < DV; ++v) S[k].dz[v] = S[k].hx[v] = S[k].hy[v] = S[k].ihx[v] = S[k].ihy[v] = S[k].ez[v] = 0.f;
 
     unsigned char *const lane_ring = smem + lane * DLB;                     // staging ring, this lane's column
     unsigned char *const lane_res = smem + DRING * SLOT + lane * DLB;       // resident arrays, this lane's column
@@ -166,7 +213,7 @@ __device__ __forceinline__ void deep_body(const MarchParams<float> &p, const int
         cp_async_commit();
         off_f += p.ny;
     };
-    // a landed row: the chain arrays into the register set, the accumulators and coefficients into its resident slot
+    // a landed row: the chain arrays into the register set, the rest into its resident slot
     auto take = [&](const int k, DeepRow &row, const int set) {
         const unsigned char *src = lane_ring + k * SLOT;
         lds_vec<float, DV>(src + 0 * DROWB, row.dz);
@@ -174,12 +221,14 @@ __device__ __forceinline__ void deep_body(const MarchParams<float> &p, const int
         lds_vec<float, DV>(src + 2 * DROWB, row.hy);
         unsigned char *res = lane_res + set * DROWB;
         float t[DV];
-        lds_vec<float, DV>(src + 3 * DROWB, t); sts4(res + R_IHX * RA, t);
-        lds_vec<float, DV>(src + 4 * DROWB, t); sts4(res + R_IHY * RA, t);
-        lds_vec<float, DV>(src + 5 * DROWB, t); sts4(res + R_NAZ * RA, t);
+        if constexpr (Shape::IHX_REG) lds_vec<float, DV>(src + 3 * DROWB, row.ihx);
+        else { lds_vec<float, DV>(src + 3 * DROWB, t); sts4(res + Shape::R_IHX * RA, t); }
+        if constexpr (Shape::IHY_REG) lds_vec<float, DV>(src + 4 * DROWB, row.ihy);
+        else { lds_vec<float, DV>(src + 4 * DROWB, t); sts4(res + Shape::R_IHY * RA, t); }
+        lds_vec<float, DV>(src + 5 * DROWB, t); sts4(res + Shape::R_NAZ * RA, t);
         if (LOSSY) {
-            lds_vec<float, DV>(src + 6 * DROWB, t); sts4(res + R_IZ * RA, t);
-            lds_vec<float, DV>(src + 7 * DROWB, t); sts4(res + R_NBZ * RA, t);
+            lds_vec<float, DV>(src + 6 * DROWB, t); sts4(res + Shape::R_IZ * RA, t);
+            lds_vec<float, DV>(src + 7 * DROWB, t); sts4(res + Shape::R_NBZ * RA, t);
         }
     };
     float2 negzero;
@@ -198,58 +247,79 @@ __device__ __forceinline__ void deep_body(const MarchParams<float> &p, const int
             st2(p.out_hx + off_s, O.hx);
             st2(p.out_hy + off_s, O.hy);
             float t[DV];
-            lds_vec<float, DV>(res + R_IHX * RA, t); VecIO<float, DV>::st(p.out_ihx + off_s, t);
-            lds_vec<float, DV>(res + R_IHY * RA, t); VecIO<float, DV>::st(p.out_ihy + off_s, t);
+            if constexpr (Shape::IHX_REG) st2(p.out_ihx + off_s, O.ihx);
+            else { lds_vec<float, DV>(res + Shape::R_IHX * RA, t); VecIO<float, DV>::st(p.out_ihx + off_s, t); }
+            if constexpr (Shape::IHY_REG) st2(p.out_ihy + off_s, O.ihy);
+            else { lds_vec<float, DV>(res + Shape::R_IHY * RA, t); VecIO<float, DV>::st(p.out_ihy + off_s, t); }
             if (LOSSY) {
-                lds_vec<float, DV>(res + R_IZ * RA, t); VecIO<float, DV>::st(p.out_iz + off_s, t);
-                if (p.write_ez) { lds_vec<float, DV>(res + R_EZ * RA, t); VecIO<float, DV>::st(p.out_ez + off_s, t); }
-            } else if (p.write_ez) {         // the last pass evaluates naz*dz once more (same operands, same bits)
-                float e[DV];
-                lds_vec<float, DV>(res + R_NAZ * RA, t);
+                lds_vec<float, DV>(res + Shape::R_IZ * RA, t); VecIO<float, DV>::st(p.out_iz + off_s, t);
+                if (p.write_ez) { lds_vec<float, DV>(res + Shape::R_EZ * RA, t); VecIO<float, DV>::st(p.out_ez + off_s, t); }
+            } else if (p.write_ez) {
+                if constexpr (Shape::EZ_REG) {
+                    st2(p.out_ez + off_s, O.ez);
+                } else {                          // the last pass evaluates naz*dz once more (same operands, same bits)
+                    float e[DV];
+                    lds_vec<float, DV>(res + Shape::R_NAZ * RA, t);
 #pragma unroll
-                for (int v = 0; v < DV; v += 2) {
-                    const float2 a = pk_mul(make_float2(t[v], t[v + 1]), make_float2(O.dz[v], O.dz[v + 1]), negzero);
-                    e[v] = a.x; e[v + 1] = a.y;
+                    for (int v = 0; v < DV; v += 2) {
+                        const float2 a = pk_mul(make_float2(t[v], t[v + 1]), make_float2(O.dz[v], O.dz[v + 1]), negzero);
+                        e[v] = a.x; e[v + 1] = a.y;
+                    }
+                    st2(p.out_ez + off_s, e);
                 }
-                st2(p.out_ez + off_s, e);
             }
         }
         off_s += p.ny;
     };
 
+    // Staging ring.  DRING >= 3: DRING-1 rows in flight, the slot consumed one sub-iteration ago is refilled right after the
+    // take.  DRING == 2 (deepest shapes, where shared memory decides how many warps fit): the slot just consumed is
+    // refilled at the END of the sub-iteration -- every value read from it has been used by then -- so one row is in
+    // flight during the T stages and two across the boundary.
+    constexpr bool LATE = DRING == 2;
+    constexpr int AHEAD = LATE ? 2 : DRING - 1;       // rows fetched before the first take
 #pragma unroll
-    for (int k = 0; k < DRING - 1; ++k) fetch(k);
+    for (int k = 0; k < AHEAD; ++k) fetch(k);
     int slot = 0;                                     // staging slot of the row consumed next
 #pragma unroll 1                                      // the body is T*(T+1) stages already
     for (int r = r_begin; r < r_end; r += NS) {
 #pragma unroll
         for (int u = 0; u < NS; ++u) {
             const int rr = r + u;                     // global row arriving at stage 0 (may overrun r_end)
-            cp_async_wait<DRING - 2>();               // the oldest of the DRING-1 pending rows has landed
+            cp_async_wait<AHEAD - 1>();               // the oldest pending row has landed
             take(slot, S[u], u);
-            fetch(slot == 0 ? DRING - 1 : slot - 1);  // refill the slot consumed one sub-iteration ago with row rr + DRING - 1
-            slot = (slot + 1 == DRING) ? 0 : slot + 1;
+            if (!LATE) fetch(slot == 0 ? DRING - 1 : slot - 1);  // refill the slot consumed one sub-iteration ago with row rr + DRING - 1
 #pragma unroll
             for (int s = 0; s < T; ++s) {             // stage s: row rr-s arrives, row rr-s-1 is held
                 const int sa = (u - s + 2 * NS) % NS, sh = (u - s - 1 + 2 * NS) % NS;
-                deep_stage<LOSSY, RA>(S[sa], S[sh], lane_res + sa * DROWB, lane_res + sh * DROWB, negzero);
+                deep_stage<Shape>(S[sa], S[sh], lane_res + sa * DROWB, lane_res + sh * DROWB, negzero);
             }
             store_row(S[(u + 1) % NS], rr - T, (u + 1) % NS);     // the set held by the last stage: row rr-T at time t+T
+            if (LATE) fetch(slot);                    // row rr + 2 into the slot taken above
+            slot = (slot + 1 == DRING) ? 0 : slot + 1;
         }
     }
     cp_async_wait<0>();
 }
 
-template <int T, bool LOSSY, int DRING>
-__global__ void __launch_bounds__(MAX_WARPS * 32)
+// Register budget stated directly.  Each of the four sub-partitions of an SM has its own file of 16384 registers and
+// the warps of a CTA are dealt round-robin, so W warps per CTA put ceil(W/4) on one file: that, not 65536 / W, bounds the
+// registers per thread (9..12 warps: 168).
+constexpr int deep_maxnreg(int warps) {
+    const int r = (16384 / ((warps + 3) / 4) / 32) / 8 * 8;
+    return r > 255 ? 255 : r;
+}
+template <int T, bool LOSSY, int DRING, int WARPS, int KEEP>
+__global__ void __maxnreg__(deep_maxnreg(DeepShape<T, LOSSY, DRING, WARPS, KEEP>::WARPS))
 k_march_deep(const __grid_constant__ MarchParams<float> p) {
+    using Shape = DeepShape<T, LOSSY, DRING, WARPS, KEEP>;
     extern __shared__ __align__(16) unsigned char deep_smem[];
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    unsigned char *const mine = deep_smem + (size_t)(threadIdx.x >> 5) * DeepShape<T, LOSSY, DRING>::WARP_SMEM;
+    unsigned char *const mine = deep_smem + (size_t)(threadIdx.x >> 5) * Shape::WARP_SMEM;
     int strip, i0, i1;
     if (!decode_item<true>(p, w, 0, DV, T, LOSSY, strip, i0, i1)) return;
-    deep_body<T, LOSSY, DRING>(p, strip, i0, i1, lane, mine);
+    deep_body<Shape, T, LOSSY, DRING>(p, strip, i0, i1, lane, mine);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -465,20 +535,18 @@ int launch_careful2_k(const MarchParams<float> &mp, int T, int items, int all_ca
     return FDTD_OK;
 }
 
-constexpr int DRING_OF_8 = 3, DRING_OF_12 = 3;
-
-template <int T, bool LOSSY, int DRING>
+template <int T, bool LOSSY, int DRING, int WARPS, int KEEP>
 int launch_deep_interior(const MarchParams<float> &mp, int items, cudaStream_t st) {
     if (items <= 0) return FDTD_OK;
-    using Shape = DeepShape<T, LOSSY, DRING>;
+    using Shape = DeepShape<T, LOSSY, DRING, WARPS, KEEP>;
     int warps = (g_tune.warps >= 1 && g_tune.warps <= Shape::WARPS) ? g_tune.warps : Shape::WARPS;
     const size_t smem = (size_t)warps * Shape::WARP_SMEM;
     static size_t configured[64] = {0};
     static std::mutex guard;
-    const int rc = opt_in_smem(k_march_deep<T, LOSSY, DRING>, smem, configured, guard);
+    const int rc = opt_in_smem(k_march_deep<T, LOSSY, DRING, WARPS, KEEP>, smem, configured, guard);
     if (rc != FDTD_OK) return rc;
     const int grid = (items + warps - 1) / warps;
-    k_march_deep<T, LOSSY, DRING><<<grid, warps * 32, smem, st>>>(mp);
+    k_march_deep<T, LOSSY, DRING, WARPS, KEEP><<<grid, warps * 32, smem, st>>>(mp);
     FDTD_LAUNCH_CHECK("k_march_deep");
     return FDTD_OK;
 }
@@ -499,8 +567,12 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
     const PassCounts pc = classify_pass(mp, DV, T);
     if (pc.all_careful) return launch_careful2(mp, T, lossy, pc.n_careful, 1, st);
     auto launch_interior = [&]() -> int {
-        return T == 12 ? launch_deep_interior<12, false, DRING_OF_12>(mp, pc.n_fast, st)
-                       : launch_deep_interior<8, false, DRING_OF_8>(mp, pc.n_fast, st);
+        if (T == 12) return launch_deep_interior<12, false, 2, 8, 0>(mp, pc.n_fast, st);
+        switch (g_tune.variant) {       // experiments (fdtd2d_tune2 FDTD_TUNE_VARIANT); 0 = the shipped shape
+            case 1: return launch_deep_interior<8, false, 3, 8, 0>(mp, pc.n_fast, st);
+            case 2: return launch_deep_interior<8, false, 2, 8, KEEP_IHX>(mp, pc.n_fast, st);
+            default: return launch_deep_interior<8, false, 3, 8, KEEP_IHX>(mp, pc.n_fast, st);
+        }
     };
     // the careful kernel is small (edges only): fork it onto a side stream so the interior kernel backfills the SMs it
     // leaves idle, and join before the next pass
@@ -523,8 +595,8 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
 
 void preload_deep(bool lossy) {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, k_march_deep<12, false, DRING_OF_12>);
-    cudaFuncGetAttributes(&a, k_march_deep<8, false, DRING_OF_8>);
+    cudaFuncGetAttributes(&a, k_march_deep<12, false, 2, 8, 0>);
+    cudaFuncGetAttributes(&a, k_march_deep<8, false, 3, 8, KEEP_IHX>);
     cudaFuncGetAttributes(&a, k_careful2<float, DV, 0>);
     if (lossy) cudaFuncGetAttributes(&a, k_careful2<float, DV, 1>);
 }

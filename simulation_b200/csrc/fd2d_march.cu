@@ -574,10 +574,33 @@ Plan choose_plan(const fdtd2d_problem *q) {
     return p;
 }
 
-// depth of the next pass: at most `left` steps and `tblock` (0: the plan's own depth -- 12 where the deep passes are
-// available), rounded down to an instantiated depth: 1, 2, 3, 4, 6, 8 (+ 12 deep)
+// Depth of the next pass: at most `left` steps and `tblock`, rounded down to an instantiated depth: 1, 2, 3, 4, 6, 8
+// (+ 12 on explicit request where the deep passes apply).  tblock = 0: the library's choice.  Where the deep passes
+// apply that is the split of the remaining steps into passes of depth 8, 6 and <= 4 with the least total cost: every
+// pass moves the state through HBM once, so a shallow pass costs about as much as a depth-6 one (HBM-bound: 8.3 ms at
+// 32768^2), while a depth-8 pass (shared-memory-bound) costs 10.9 ms -- e.g. 20 steps = 8 + 6 + 6, 96 steps = 12 x 8
+// (profiles/r2_deep_variants.txt).
 inline int next_depth(const Plan &plan, int tblock, int left, int nf) {
-    int T = min(tblock > 0 ? tblock : (plan.deep ? 12 : plan.T), left);
+    if (tblock <= 0 && plan.deep && nf == 0) {
+        // cost of a pass by depth, in units of a depth-6 pass; least-cost split by dynamic programming over `left`
+        static const int depths[] = {8, 6, 4, 3, 2, 1};
+        static const double cost[] = {1.31, 1.00, 0.97, 0.96, 0.95, 0.94};
+        constexpr int HORIZON = 48;                     // beyond this many steps the split starts with a depth-8 pass anyway
+        if (left > HORIZON) return 8;
+        double best[HORIZON + 1];
+        int first[HORIZON + 1];
+        best[0] = 0.0; first[0] = 0;
+        for (int n = 1; n <= left; ++n) {
+            best[n] = 1e30; first[n] = 1;
+            for (int k = 0; k < 6; ++k) {
+                if (depths[k] > n) continue;
+                const double c = cost[k] + best[n - depths[k]];
+                if (c < best[n] - 1e-9) { best[n] = c; first[n] = depths[k]; }
+            }
+        }
+        return first[left];
+    }
+    int T = min(tblock > 0 ? tblock : plan.T, left);
     if (nf > 0) T = min(T, 4);                      // fused-DFT kernels: depth <= 4
     if (T >= 12 && plan.deep) return 12;
     if (T > 8) T = 8;
@@ -823,6 +846,9 @@ int fdtd2d_tune2(int key, long long value) {
         case FDTD_TUNE_HALO_WAIT_MS:
             FDTD_REQUIRE(value >= 0, "fdtd2d_tune2: negative wait");
             g_tune.spin_ns = value == 0 ? HALO_SPIN_NS : (unsigned long long)value * 1000000ull;
+            return FDTD_OK;
+        case FDTD_TUNE_VARIANT:
+            g_tune.variant = (int)value;
             return FDTD_OK;
         default:
             fdtd::set_error("fdtd2d_tune2: unknown key %d", key);

@@ -508,6 +508,7 @@ struct Tuning {
     int force_v = 0, chunk_rows = 0, warps = 0, careful = 0;
     int split = 1;               // 0 = ignore the lossless-outside promise (tests: the lossy kernel everywhere)
     int serial = 2;              // 2 = fork the edge kernel onto a side stream (measured +2 %); 1 = edge then interior in order
+    int variant = 0;             // kernel-shape experiments of the deep passes (0 = the shipped shape)
     int deep = 1;                // 0 = never use the deep passes of fd2d_deep.cu; 2 = the smem-resident careful kernel at every depth
     unsigned long long spin_ns = HALO_SPIN_NS;
 };

@@ -28,6 +28,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __grid_constant__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __restrict__
 #define __align__(n) alignas(n)
 
