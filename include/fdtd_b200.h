@@ -164,6 +164,11 @@ int fdtd2d_incthy(int dtype, int nx, int ny, int npml, const void *ezi, void *hy
 int fdtd2d_dielectric_cylinder(int dtype, int nx, int ny, int npml, int rgrid, double dt, double epsr, double sigma,
                                int row_lo, int row_hi, void *naz, void *nbz, void *stream);
 
+/* setup on the device: the ten PML vectors of pmlparam (fd2d/program/fd2d_3_3.py:113-122; defaults :147-158) written
+ * into the arrays `pml` points to (x-vectors: nx entries, y-vectors: ny), float64 evaluation of the reference's Python
+ * statements rounded on store, bit-identical to them.  npml = 0: the identity set (free space). */
+int fdtd2d_pmlparam(int dtype, int nx, int ny, int npml, const fdtd_pmlayer *pml, void *stream);
+
 /* --------------------------------------------------------------------- 2D: fused time-blocked path */
 enum { FDTD2D_DZ = 0, FDTD2D_EZ, FDTD2D_HX, FDTD2D_HY, FDTD2D_IHX, FDTD2D_IHY, FDTD2D_IZ, FDTD2D_NFIELDS };
 

@@ -701,7 +701,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.nstrips = (q->ny + use - 1) / use;
         const int rows = mp.out_hi - mp.out_lo;
         int chunk = g_tune.chunk_rows;
-        if (chunk <= 0) chunk = max(deep ? max(plan.chunk, 256) : plan.chunk, 4 * T);   // at most ~50 % warm-up/drain recompute on shallow grids
+        if (chunk <= 0) chunk = max(plan.chunk, 4 * T);   // at most ~50 % warm-up/drain recompute on shallow grids
         chunk = max(1, min(chunk, rows));
         mp.chunk_rows = chunk;
         mp.nchunks = (rows + chunk - 1) / chunk;
@@ -870,10 +870,7 @@ int fdtd2d_plan(const fdtd2d_problem *q, int nsteps, int tblock, int *depths, in
         left -= T;
     }
     if (vector_width) *vector_width = (q->dtype == FDTD_F64 && first == 8) ? 1 : plan.V;
-    if (chunk_rows) {
-        const bool deep = plan.deep && (first == 12 || first == 8);
-        *chunk_rows = g_tune.chunk_rows > 0 ? g_tune.chunk_rows : max(deep ? max(plan.chunk, 256) : plan.chunk, 4 * max(first, 1));
-    }
+    if (chunk_rows) *chunk_rows = g_tune.chunk_rows > 0 ? g_tune.chunk_rows : max(plan.chunk, 4 * max(first, 1));
     return n;
 }
 

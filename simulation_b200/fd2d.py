@@ -132,10 +132,24 @@ def fourier(t: int, nf: int, nx: int, ny: int, dt: float, freq, ezi, ez, ft: ftr
                                C.byref(fs), _stream()), "fourier")
 
 
-def pmlparam(nx: int, ny: int, npml: int, dtype=np.float32, device=None) -> pmlayer:
-    """Host-evaluated reference formulas (surface.pmlparam), uploaded."""
-    host = surface.pmlparam(nx, ny, npml, dtype)
-    return pmlayer(*[torch.from_numpy(a).to(device or "cuda") for a in host])
+def pmlparam(nx: int, ny: int, npml: int, dtype=np.float32, device=None, where: str = "host") -> pmlayer:
+    """The ten PML vectors on the device.  ``where="host"`` (default): the reference formulas evaluated by
+    surface.pmlparam and uploaded; ``where="device"``: evaluated by the library's kernel (``fdtd2d_pmlparam``, float64
+    with a correctly rounded cube) -- bit-identical, no host arrays at all (profiles/r2_pmlparam_host_vs_device.txt)."""
+    if where == "host":
+        host = surface.pmlparam(nx, ny, npml, dtype)
+        return pmlayer(*[torch.from_numpy(a).to(device or "cuda") for a in host])
+    if where != "device":
+        raise ValueError(where)
+    if npml < 0 or 2 * npml > min(nx, ny):
+        raise ValueError(f"npml={npml} does not fit a {nx}x{ny} grid")
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    tdt = _TORCH_DT[np.dtype(dtype)]
+    out = pmlayer(*[torch.empty(n, dtype=tdt, device=dev) for n in (nx, nx, nx, ny, ny, ny, nx, nx, ny, ny)])
+    ps = out.as_struct()
+    with torch.cuda.device(dev):
+        check(lib().fdtd2d_pmlparam(_lib.dtype_code(dtype), int(nx), int(ny), int(npml), C.byref(ps), _stream()), "pmlparam")
+    return out
 
 
 def dielectric(nx: int, ny: int, npml: int, rgrid: int, dt: float, epsr: float, sigma: float, dtype=np.float32,

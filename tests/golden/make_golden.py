@@ -184,8 +184,60 @@ def golden_drives():
          naz=naz, **{k: v for k, v in drive_3_2(48, 40, 6, 90, np.float32, naz=naz).items()})
 
 
+# ------------------------------------------------------------------ benchdef_* (2D test_* twins, what they PRINT)
+def run_twin_2d(relpath, nx, ny, ns, npml=None, radius=None):
+    """A 2D ``test_*`` benchmark program executed with ONLY its size literals reduced; returns what it prints after the
+    compute-time line (``ez[2][0:50]``, and ``amplt[2][0:ny-50]`` for 3_4) and the arrays it hands to its plot helpers."""
+    src = open(os.path.join(refload.REFERENCE_ROOT, relpath)).read()
+    subs = [(r"nx: int = \d+", f"nx: int = {nx}"), (r"ny: int = \d+", f"ny: int = {ny}"), (r"ns: int = \d+", f"ns: int = {ns}")]
+    if npml is not None:
+        subs.append((r"npml: int = \d+", f"npml: int = {npml}"))
+    if radius is not None:
+        subs.append((r"radius: float = [0-9.]+", f"radius: float = {radius}"))
+    for pat, rep in subs:
+        src, n = re.subn(pat, rep, src)
+        assert n == 1, (relpath, pat, n)
+    refload.load("fd1d/program/fd1d_1_1.py")             # installs the matplotlib stubs
+    glb = {"__name__": "twin"}
+    exec(compile(src, relpath, "exec"), glb)
+    seen = {}
+    for fn in ("surfaceplot", "contourplot", "amplitudeplot"):
+        if fn in glb:
+            glb[fn] = (lambda name: (lambda *a, **k: seen.__setitem__(name, a)))(fn)
+    printed = []
+    glb["print"] = lambda *a, **k: printed.append(a[0])
+    glb["main"]()
+    return seen, printed
+
+
+def golden_benchdefs():
+    """The reference's 2D benchmark definitions at reduced size: the numpy twins (fd2d/program/test_3_1..3_3.py, bit-stable)
+    and the numba twins (fd2d/python/test_3_1..3_4.py: fastmath, float32 arrays evaluated through float64 literals --
+    compared within the north-star tolerance)."""
+    nx, ny, ns, npml = 168, 200, 260, 20
+    for prog in ("3_1", "3_2", "3_3"):
+        seen, printed = run_twin_2d(f"fd2d/program/test_{prog}.py", nx, ny, ns, None if prog == "3_1" else npml)
+        ez = seen["surfaceplot"][-1]
+        assert ez.dtype == np.float32 and ez.shape == (nx, ny) and np.array_equal(printed[1], ez[2][0:50])
+        save(f"benchdef_numpy_{prog}", ez=ez, printed_ez=np.asarray(printed[1]), text_ez=np.array(str(printed[1])),
+             nx=np.int64(nx), ny=np.int64(ny), ns=np.int64(ns), npml=np.int64(0 if prog == "3_1" else npml))
+    for prog in ("3_1", "3_2", "3_3", "3_4"):
+        seen, printed = run_twin_2d(f"fd2d/python/test_{prog}.py", nx, ny, ns, None if prog == "3_1" else npml,
+                                    0.30 if prog == "3_4" else None)
+        ez = seen["surfaceplot"][-1]
+        out = dict(ez=ez, printed_ez=np.asarray(printed[1]), nx=np.int64(nx), ny=np.int64(ny), ns=np.int64(ns),
+                   npml=np.int64(0 if prog == "3_1" else npml))
+        if prog == "3_4":
+            out.update(printed_amplt=np.asarray(printed[2]), radius=np.float64(0.30))
+        save(f"benchdef_numba_{prog}", **out)
+
+
 if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
+    if len(sys.argv) > 1 and sys.argv[1] == "benchdefs":
+        golden_benchdefs()
+        sys.exit(0)
     golden_mains()
     golden_twins()
+    golden_benchdefs()
     golden_drives()

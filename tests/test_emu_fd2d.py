@@ -423,6 +423,17 @@ def test_emulated_reference_positional_argument_lists(emu):
         fd2d.efield(nx, ny, md, dz, ez)                                    # lossy medium without iz
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_emulated_device_pmlparam(emu, dtype):
+    """fdtd2d_pmlparam (float64 on the device, correctly rounded cube) == surface.pmlparam == the reference's Python."""
+    from simulation_b200 import fd2d, surface
+    for nx, ny, npml in ((60, 60, 8), (100, 131, 0), (97, 64, 32), (401, 300, 150), (1024, 777, 80), (2, 2, 1), (7, 9, 3)):
+        host = surface.pmlparam(nx, ny, npml, dtype)
+        dev = fd2d.pmlparam(nx, ny, npml, dtype, device="cpu", where="device")
+        for name, h, d in zip(host._fields, host, dev):
+            assert d.numpy().tobytes() == h.tobytes(), (nx, ny, npml, name)
+
+
 def test_emulated_lossless_outside_split(emu):
     """A lossy object in free space: interior warps outside the object's box run the lossless kernel.  Same bits as the
     lossy kernel everywhere (split disabled), as the oracle, and the promise is re-derived when iz is uploaded."""

@@ -561,6 +561,24 @@ def test_baseline_config_4_vs_reference_c_openmp():
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_device_pmlparam_equals_host_setup(dtype):
+    """fdtd2d_pmlparam == surface.pmlparam (== the reference's Python statements) for EVERY layer index of every PML
+    depth up to 300, both ends, odd sizes: the device evaluates x**3 in double-double, Python through glibc's pow."""
+    from simulation_b200 import fd2d, surface
+    for npml in list(range(0, 301)) + [512, 1000]:
+        nx, ny = 2 * npml + 37, 2 * npml + (npml % 5)
+        if ny < 2:
+            ny = 2
+        host = surface.pmlparam(nx, ny, npml, dtype)
+        dev = fd2d.pmlparam(nx, ny, npml, dtype, where="device")
+        for name, h, d in zip(host._fields, host, dev):
+            assert d.cpu().numpy().tobytes() == h.tobytes(), (npml, name)
+    big = fd2d.pmlparam(262144, 32768, 80, dtype, where="device")
+    ref = surface.pmlparam(262144, 32768, 80, dtype)
+    assert all(d.cpu().numpy().tobytes() == h.tobytes() for h, d in zip(ref, big))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_device_dielectric_equals_host_setup(dtype):
     """fd2d.dielectric (device rasteriser) == surface.dielectric_cylinder (host, == the reference's Python)."""
     from simulation_b200 import fd2d, surface
@@ -650,7 +668,7 @@ def test_errors_are_reported_not_swallowed():
     from simulation_b200 import _lib, fd2d, surface
     sim = _sim_for("3_3", 64, 64, np.float32, npml=8)
     with pytest.raises(_lib.FdtdError):
-        sim.advance(4, tblock=9)                                 # tblock out of range
+        sim.advance(4, tblock=13)                                # tblock out of range (1..12)
     with pytest.raises(_lib.FdtdError):
         fd2d.inctdz(64, 64, 40, sim.hxi, sim.tensor("dz"))       # 2*npml > nx
     with pytest.raises(_lib.FdtdError):
