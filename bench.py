@@ -495,12 +495,32 @@ def other_configs(peak, sync):
     md = fd2d.dielectric(n, n, NPML, int(6.0 / surface.DS - 1), surface.DT, 30.0, 0.30, np.float32)
     grid = fd2d.Fdtd2D(n, n, NPML, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=md.naz, nbz=md.nbz)
     ms = timed(grid, ns, 48)
+    # the same job end to end with HOST buffers: the medium (naz, nbz) up from pinned memory, ns steps from zero fields,
+    # Ez back into pinned memory -- what the reference main() of fd2d/python/fd2d_3_4.py does around its loop
+    h_naz, h_nbz = md.naz.cpu().pin_memory(), md.nbz.cpu().pin_memory()
+    h_ez = torch.empty((n, n), dtype=torch.float32).pin_memory()
+    job = fd2d.Fdtd2D(n, n, NPML, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), naz=md.naz, nbz=md.nbz)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    job.naz.copy_(h_naz, non_blocking=True)
+    job.nbz.copy_(h_nbz, non_blocking=True)
+    job.invalidate_lossy_box()
+    job.advance(ns)
+    h_ez.copy_(job.tensor("ez"), non_blocking=True)
+    e1.record()
+    sync()
+    ms_e2e = e0.elapsed_time(e1)
     out["c4_tfsf_lossy_4096"] = {"value": float(n) * n * ns / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s", "ms_per_step": ms / ns,
                                  "steps": ns, "frac": BYTES_LOSSY * float(n) * n * ns / (ms * 1e-3) / 1e9 / peak, "dram_frac": None,
                                  "pass_depths": sorted(set(grid.pass_depths(ns, None)), reverse=True),
+                                 "e2e": {"value": float(n) * n * ns / (ms_e2e * 1e-3) / 1e6, "unit": "Mcell-updates/s",
+                                         "h2d_bytes_per_step": 2 * n * n * 4 / ns, "d2h_bytes_per_step": n * n * 4 / ns,
+                                         "what": "pinned naz + nbz H2D, 2000 steps, pinned Ez D2H (192 MiB over PCIe against 0.1 s "
+                                                 "of stepping: copies around advance(), no streaming needed)"},
                                  "note": "60 B per cell-update algorithmic (iz R+W, nbz R on top of 48); the 0.4 GB state is "
                                          "3x the L2, launches are a few waves"}
-    del grid, md
+    del grid, md, job
     torch.cuda.empty_cache()
     return out
 
@@ -557,13 +577,13 @@ def run_e2e(sim, world, rank, n, nx_global, K, T, src, sync, release):
            "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
            "runs_ms": [round(x * 1e3, 2) for x in runs],
            "pcie_gbs_per_rank": [round(float(r), 1) for r in rates],
-           "pcie_bound_ms": round(max(h2d, d2h) / 55e9 * 1e3, 1),
+           "pcie_bound_ms": round(max(h2d, d2h) / 44e9 * 1e3, 1),
            "what": f"pinned naz H2D ({h2d / 2**30:.1f} GiB/GPU) + {K} steps + pinned Ez D2H, CUDA events on the launch "
                    f"stream, max over ranks; run_streamed: row blocks uploaded in order (512..3072 rows), every block stepped through "
                    f"all its passes as soon as it has arrived (skewed space-time tiling), one stream per pass level, Ez of "
                    f"finished blocks downloaded behind the stepping (after one untimed run of the same call); "
                    f"median of {E2E_REPEATS} whole jobs (runs_ms); pcie_gbs_per_rank = (H2D + D2H bytes) / the rank's own time, "
-                   f"pcie_bound_ms = one direction at the 55 GB/s measured on these boxes"
+                   f"pcie_bound_ms = either direction at the 44 GB/s these boxes sustain when BOTH directions are busy (55 GB/s alone; profiles/r1_box_topology_and_pcie.txt)"
                    + ("" if world == 1 else f"; per rank a {K}-row ghost band consumed instead of exchanged (no communication in {K} steps)")}
     release(sim)
     return out

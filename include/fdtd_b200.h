@@ -51,6 +51,10 @@ extern "C" {
                                   required -- every step then invalidates one more stored row from each open end
                                   (communication-avoiding runs: k steps with k ghost rows and no exchange) */
 
+#define FDTD_INCIDENT_READY 128 /* 2D advance with FDTD_TFSF: ezi_hist / hxi_hist already hold the incident-line history of this
+                                  call's steps (fdtd2d_incident_line) -- the incident line is NOT advanced again.  For hosts that
+                                  run one pass over several row blocks (streamed runs); one pass per call. */
+
 /* structs of device pointers, in the reference's declaration order
  * (fd2d/cuda/test_3_4.cu:20-36, fd1d/cuda/test_2_3.cu:17-27) */
 typedef struct { const void *fx1, *fx2, *fx3, *fy1, *fy2, *fy3, *gx2, *gx3, *gy2, *gy3; } fdtd_pmlayer;
@@ -246,6 +250,13 @@ int fdtd2d_max_tblock(int dtype, int ny);
  * pass levels of a streamed run) ask here instead of re-deriving it. */
 int fdtd2d_plan(const fdtd2d_problem *p, int nsteps, int tblock, int *depths, int cap, int *vector_width,
                 int *chunk_rows);
+/* Advance the TFSF incident line of `p` (ezi, hxi, bc; ezinct ... hxinct with the hard source ezi[3] = src[k],
+ * fd2d/program/fd2d_3_3.py:60-65,72,86-88) by nsteps <= 12 steps and record what a pass over those steps needs: ezi after
+ * ezinct + source of every step (ezi_hist: nsteps x ny) and hxi[npml-2], hxi[ny-npml] before hxinct (hxi_hist: nsteps x 2).
+ * fdtd2d_advance does this itself once per pass; hosts that cut one pass into row blocks call it once per pass and hand
+ * the history to every block's call with FDTD_INCIDENT_READY. */
+int fdtd2d_incident_line(const fdtd2d_problem *p, int nsteps, const double *src, void *ezi_hist, void *hxi_hist,
+                         void *stream);
 /* Fused halo exchange: *word = 0 while every wait of every pass so far was answered; otherwise epoch*4 + side (1 = the
  * upper, 2 = the lower neighbour never arrived within the bound) and fdtd_last_error() says so.  Synchronises. */
 int fdtd2d_halo_status(const fdtd2d_problem *p, unsigned long long *word);

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libfdtd_b200.so")
 
 F32, F64 = 0, 1
-TFSF, LOSSY, ABC, FLUX, DEBYE, LAZY_EZ, GHOST_DECAY = 1, 2, 4, 8, 16, 32, 64
+TFSF, LOSSY, ABC, FLUX, DEBYE, LAZY_EZ, GHOST_DECAY, INCIDENT_READY = 1, 2, 4, 8, 16, 32, 64, 128
 DZ, EZ, HX, HY, IHX, IHY, IZ, NFIELDS = range(8)
 
 
@@ -108,6 +108,7 @@ SYMBOLS = {
     "fdtd2d_tune": (_I, [_I, _I, _I, _I, _I]),
     "fdtd2d_tune2": (_I, [_I, C.c_longlong]),
     "fdtd2d_plan": (_I, [C.POINTER(Problem2D), _I, _I, C.POINTER(_I), _I, C.POINTER(_I), C.POINTER(_I)]),
+    "fdtd2d_incident_line": (_I, [C.POINTER(Problem2D), _I, C.POINTER(_D), _P, _P, _P]),
     "fdtd2d_halo_status": (_I, [C.POINTER(Problem2D), C.POINTER(C.c_ulonglong)]),
 }
 TUNE_DEEP, TUNE_HALO_WAIT_MS = 0, 1

@@ -706,7 +706,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.chunk_rows = chunk;
         mp.nchunks = (rows + chunk - 1) / chunk;
 
-        if (tfsf) {
+        if (tfsf && !(q->flags & FDTD_INCIDENT_READY)) {
             SrcTable tab;
             for (int s = 0; s < TMAX; ++s) tab.v[s] = mp.src[s];
             tab.nf = (mp.nf > 0 && q->ft.r_in && q->ft.i_in) ? mp.nf : 0;
@@ -872,6 +872,27 @@ int fdtd2d_plan(const fdtd2d_problem *q, int nsteps, int tblock, int *depths, in
     if (vector_width) *vector_width = (q->dtype == FDTD_F64 && first == 8) ? 1 : plan.V;
     if (chunk_rows) *chunk_rows = g_tune.chunk_rows > 0 ? g_tune.chunk_rows : max(plan.chunk, 4 * max(first, 1));
     return n;
+}
+
+int fdtd2d_incident_line(const fdtd2d_problem *q, int nsteps, const double *src, void *ezi_hist, void *hxi_hist, void *stream) {
+    FDTD_REQUIRE(q && src && ezi_hist && hxi_hist, "fdtd2d_incident_line: null argument");
+    FDTD_REQUIRE(q->dtype == FDTD_F32 || q->dtype == FDTD_F64, "fdtd2d_incident_line: unknown dtype %d", q->dtype);
+    FDTD_REQUIRE((q->flags & FDTD_TFSF) && q->ezi && q->hxi && q->bc, "fdtd2d_incident_line: a TFSF problem with its incident line");
+    FDTD_REQUIRE(nsteps >= 1 && nsteps <= TMAX, "fdtd2d_incident_line: %d steps outside [1, %d]", nsteps, TMAX);
+    FDTD_REQUIRE(q->npml >= 2 && 2 * q->npml <= q->ny && q->ny >= 8, "fdtd2d_incident_line: bad TFSF geometry");
+    SrcTable tab;
+    for (int s = 0; s < TMAX; ++s) tab.v[s] = s < nsteps ? src[s] : 0.0;
+    tab.nf = 0;
+    for (int s = 0; s < TMAX; ++s)
+        for (int f = 0; f < NFMAX; ++f) tab.c[s][f] = tab.s[s][f] = 0.0;
+    if (q->dtype == FDTD_F32)
+        k_incident_line<float><<<1, 1024, 0, fdtd::as_stream(stream)>>>(q->ny, q->npml, nsteps, (float *)q->ezi, (float *)q->hxi, (float *)q->bc,
+                                                                        (float *)ezi_hist, (float *)hxi_hist, nullptr, nullptr, tab);
+    else
+        k_incident_line<double><<<1, 1024, 0, fdtd::as_stream(stream)>>>(q->ny, q->npml, nsteps, (double *)q->ezi, (double *)q->hxi, (double *)q->bc,
+                                                                         (double *)ezi_hist, (double *)hxi_hist, nullptr, nullptr, tab);
+    FDTD_LAUNCH_CHECK("k_incident_line");
+    return FDTD_OK;
 }
 
 int fdtd2d_halo_status(const fdtd2d_problem *q, unsigned long long *word) {

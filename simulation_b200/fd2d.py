@@ -431,7 +431,7 @@ class Fdtd2D:
             self.tensor(name).copy_(torch.from_numpy(np.ascontiguousarray(a)))
 
     # ---- the fused path -----------------------------------------------------------------------------
-    def _problem(self) -> _lib.Problem2D:
+    def _problem(self, lossy_box=None) -> _lib.Problem2D:
         p = _lib.Problem2D()
         p.dtype = _lib.dtype_code(self.np_dtype)
         p.nx, p.ny = self.nx, self.ny
@@ -455,7 +455,7 @@ class Fdtd2D:
         p.ident_row_lo, p.ident_row_hi = self._ident(self.nx)
         p.ident_col_lo, p.ident_col_hi = self._ident(self.ny)
         if self.lossy:
-            p.lossy_row_lo, p.lossy_row_hi, p.lossy_col_lo, p.lossy_col_hi = self._lossy_box()
+            p.lossy_row_lo, p.lossy_row_hi, p.lossy_col_lo, p.lossy_col_hi = lossy_box if lossy_box is not None else self._lossy_box()
         return p
 
     def _lossy_box(self):
@@ -576,7 +576,8 @@ class Fdtd2D:
 
     def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, blocks: Optional[int] = None,
                      tblock=None, streams: int = 16, trace: Optional[list] = None, block_rows=None,
-                     schedule: str = "skewed", window: Optional[int] = 2, priorities: bool = False) -> None:
+                     schedule: str = "skewed", window: Optional[int] = 2, priorities: bool = False,
+                     nbz_host: Optional[torch.Tensor] = None) -> None:
         """The whole job a reference ``main()`` does -- medium from the host, ``nsteps`` steps from zero fields,
         Ez back on the host -- with the PCIe transfers hidden behind the kernels.
 
@@ -599,14 +600,21 @@ class Fdtd2D:
         shift would not fit the first block).
 
         Same kernels, same arithmetic, same result as ``set naz; advance(nsteps); get ez``.  ``naz_host``: pinned CPU
-        tensor over the stored rows, ``ez_host`` over the owned rows (both (nx, ny) on a single device).  Point source
-        or no source only (the TFSF incident line is advanced once per whole-grid pass).
+        tensor over the stored rows, ``ez_host`` over the owned rows (both (nx, ny) on a single device); a lossy
+        medium also brings ``nbz_host`` (stored rows), uploaded with the same blocks.  With a TFSF source the incident
+        line is advanced ONCE per pass level up front (``fdtd2d_incident_line``: one tiny launch per level, its history
+        kept per level) and every block's pass reads that history (``FDTD_INCIDENT_READY``) -- the reference ``main()``
+        this replaces is fd2d/python/fd2d_3_4.py:211-293.  No running DFT.
 
         On a slab (``rows=``, ``ghost=g``) the run is communication-avoiding: at most g steps, during which the
         ghost band is consumed one row per step instead of being exchanged (``FDTD_GHOST_DECAY``) -- the owned rows come
         out exact, the ghost rows must be refreshed before stepping on (``SlabFdtd2D.run_streamed`` does)."""
-        if self.tfsf or self.ft is not None:
-            raise _lib.FdtdError("run_streamed: point source (or none) and no running DFT")
+        if self.ft is not None:
+            raise _lib.FdtdError("run_streamed: no running DFT (its accumulators would have to stream too)")
+        if self.lossy != (nbz_host is not None):
+            raise _lib.FdtdError("run_streamed: a lossy medium brings nbz_host (and only a lossy medium does)")
+        if nbz_host is not None and tuple(nbz_host.shape) != (self.rows_alloc, self.ny):
+            raise _lib.FdtdError("run_streamed: nbz_host must cover the stored rows (rows_alloc, ny)")
         slab = self.rows_alloc != self.nx
         rows_own = self.row_hi - self.row_lo
         if slab and int(nsteps) > self.ghost:
@@ -639,11 +647,33 @@ class Fdtd2D:
             lanes, up, down = self._lanes[:S], self._lanes[S], self._lanes[S + 1]
             for st in lanes + [up, down]:
                 st.wait_stream(caller)
+            # nbz is still arriving block by block: no lossless-outside promise can be derived from it (the whole grid is
+            # "the box": every interior warp runs the lossy kernel)
+            whole = (0, self.nx, 0, self.ny) if self.lossy else None
+            hist = None
+            if self.tfsf:
+                # the incident line does not depend on the 2D grid: its history for every pass level, computed once on
+                # the caller's stream before any block starts (the lanes wait for the caller above... and again here)
+                dmax = max(depths)
+                if getattr(self, "_level_hist", None) is None or self._level_hist[0].shape[0] < P or self._level_hist[0].shape[1] < dmax * self.ny:
+                    self._level_hist = (torch.zeros((P, dmax * self.ny), dtype=self.dtype, device=self.device),
+                                        torch.zeros((P, dmax * 2), dtype=self.dtype, device=self.device))
+                hist = self._level_hist
+                base = self._problem(lossy_box=whole)
+                for p_idx in range(P):
+                    k0 = int(first_step[p_idx])
+                    check(lib().fdtd2d_incident_line(C.byref(base), depths[p_idx], src[k0:].ctypes.data_as(D),
+                                                     C.c_void_p(hist[0][p_idx].data_ptr()), C.c_void_p(hist[1][p_idx].data_ptr()),
+                                                     C.c_void_p(caller.cuda_stream)), "fdtd2d_incident_line")
+                for st in lanes:
+                    st.wait_stream(caller)
             uploaded = []
             with torch.cuda.stream(up):
                 for b in range(B):
                     a, z = edges[b] - lo_all, edges[b + 1] - lo_all
                     self.naz[a:z].copy_(naz_host[a:z], non_blocking=True)
+                    if nbz_host is not None:
+                        self.nbz[a:z].copy_(nbz_host[a:z], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(up)
                     uploaded.append(ev)
@@ -654,12 +684,15 @@ class Fdtd2D:
                 lane = lanes[item["lane"]]
                 for kind, key in item["waits"]:
                     lane.wait_event(uploaded[key] if kind == "upload" else done[key])
-                prob = self._problem()
+                prob = self._problem(lossy_box=whole)
                 prob.row_lo, prob.row_hi = item["rows"]
                 if p_idx < P - 1:
                     prob.flags |= _lib.LAZY_EZ
                 if slab:
                     prob.flags |= _lib.GHOST_DECAY          # the ghost band is consumed instead of exchanged
+                if hist is not None:
+                    prob.flags |= _lib.INCIDENT_READY       # this level's incident-line history is already there
+                    prob.ezi_hist, prob.hxi_hist = hist[0][p_idx].data_ptr(), hist[1][p_idx].data_ptr()
                 out = C.c_int(-1)
                 k0 = int(first_step[p_idx])
                 if trace is not None:                                  # timeline probe (tools/probe_streamed.py)
@@ -685,6 +718,7 @@ class Fdtd2D:
                 caller.wait_stream(st)
         self._cur = (cur0 + P) % 2
         self.t += int(nsteps)
+        self._lossy_box_cache = None                # nbz was replaced
 
     def streamed_plan(self, nsteps: int, tblock=None, streams: int = 16, blocks: Optional[int] = None, block_rows=None,
                       schedule: str = "skewed", window: Optional[int] = 2) -> dict:

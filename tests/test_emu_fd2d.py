@@ -183,6 +183,36 @@ def test_emulated_streamed_run(emu, plan, ns, schedule):
     assert b.t == ns and float(host_ez.abs().max()) > 1e-3
 
 
+@pytest.mark.parametrize("prog,plan,ns,tblock", [("3_3", 4, 41, None), ("3_4", [40, 90, 130], 33, None), ("3_3", 3, 29, 8),
+                                                 ("3_4", 2, 50, 4)])
+@pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
+def test_emulated_streamed_run_tfsf_and_lossy(emu, prog, plan, ns, tblock, schedule):
+    """run_streamed with a TFSF plane wave (the incident line advanced once per pass level up front, every block's pass
+    reading that level's history) and with the lossy cylinder of program 3_4 (nbz streamed beside naz; iz carried):
+    the plain run's bits on every array, the incident line included."""
+    from simulation_b200 import fd2d, surface
+    nx, ny, npml = 400, 132, 12
+    a = _sim_for(prog, nx, ny, np.float32, npml=npml, radius=0.3, device="cpu")
+    a.advance(ns, tblock=tblock)
+    naz, nbz = a.naz.clone(), (a.nbz.clone() if prog == "3_4" else None)
+    kw = dict(nbz=torch.zeros_like(nbz)) if nbz is not None else {}
+    b = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), device="cpu", **kw)
+    host_ez = torch.empty((nx, ny), dtype=torch.float32)
+    bk = {"block_rows": plan} if isinstance(plan, list) else {"blocks": plan}
+    b.run_streamed(ns, naz, host_ez, streams=5, schedule=schedule, tblock=tblock, nbz_host=nbz, **bk)
+    assert torch.equal(host_ez, a.tensor("ez"))
+    names = ["dz", "ez", "hx", "hy", "ihx", "ihy"] + (["iz"] if prog == "3_4" else [])
+    for name in names:
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+    for name in ("ezi", "hxi", "bc"):
+        assert a.get(name).tobytes() == b.get(name).tobytes(), name
+    assert b.t == ns and float(host_ez.abs().max()) > 1e-3
+    b.advance(7)                                   # and the run goes on from there (incident line, lossy box, ping-pong)
+    a.advance(7)
+    for name in names:
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+
+
 @pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
 def test_emulated_streamed_run_on_a_slab(emu, schedule):
     from simulation_b200 import fd2d, surface

@@ -663,6 +663,36 @@ def test_streamed_run_on_a_slab_consumes_its_ghost_band(rows, ghost, ns, schedul
         part.run_streamed(ghost + 1, host_naz, host_ez)              # more steps than ghost rows
 
 
+@pytest.mark.parametrize("prog,blocks,ns,tblock", [("3_3", 5, 61, None), ("3_4", 4, 50, None), ("3_3", 3, 40, 8), ("3_4", 6, 37, 4)])
+@pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
+def test_streamed_run_tfsf_and_lossy(prog, blocks, ns, tblock, schedule):
+    """run_streamed with the TFSF plane wave (incident-line history per pass level, computed once up front) and the
+    lossy cylinder of program 3_4 (nbz streamed beside naz) on real streams: host medium in, host Ez out, the plain
+    run's bits on every array and on the incident line; then the run continues with advance()."""
+    from simulation_b200 import fd2d, surface
+    nx, ny, npml = 1500, 1024, 20
+    a = _sim_for(prog, nx, ny, np.float32, npml=npml, radius=2.0)
+    a.advance(ns, tblock=tblock)
+    naz = a.naz.cpu().pin_memory()
+    nbz = a.nbz.cpu().pin_memory() if prog == "3_4" else None
+    kw = dict(nbz=torch.zeros((nx, ny), dtype=torch.float32)) if nbz is not None else {}
+    b = fd2d.Fdtd2D(nx, ny, npml, np.float32, source=fd2d.IncidentWave(surface.Gaussian(20, 8.0)), **kw)
+    host_ez = torch.empty((nx, ny), dtype=torch.float32).pin_memory()
+    b.run_streamed(ns, naz, host_ez, blocks=blocks, streams=6, schedule=schedule, tblock=tblock, nbz_host=nbz)
+    b.synchronize()
+    assert torch.equal(host_ez, a.tensor("ez").cpu())
+    names = ["dz", "ez", "hx", "hy", "ihx", "ihy"] + (["iz"] if prog == "3_4" else [])
+    for name in names:
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+    for name in ("ezi", "hxi", "bc"):
+        assert a.get(name).tobytes() == b.get(name).tobytes(), name
+    a.advance(9)
+    b.advance(9)
+    for name in names:
+        assert torch.equal(a.tensor(name), b.tensor(name)), name
+    assert float(host_ez.abs().max()) > 0.5
+
+
 # ------------------------------------------------------------------ error behaviour of the boundary
 def test_errors_are_reported_not_swallowed():
     from simulation_b200 import _lib, fd2d, surface
