@@ -170,8 +170,12 @@ int fdtd2d_dielectric_cylinder(int dtype, int nx, int ny, int npml, int rgrid, d
 
 /* setup on the device: the ten PML vectors of pmlparam (fd2d/program/fd2d_3_3.py:113-122; defaults :147-158) written
  * into the arrays `pml` points to (x-vectors: nx entries, y-vectors: ny), float64 evaluation of the reference's Python
- * statements rounded on store, bit-identical to them.  npml = 0: the identity set (free space). */
-int fdtd2d_pmlparam(int dtype, int nx, int ny, int npml, const fdtd_pmlayer *pml, void *stream);
+ * statements rounded on store.  npml = 0: the identity set (free space).
+ * `cubes`: NULL, or 2*npml doubles ON THE DEVICE holding the host's ((npml-n)/npml)**3, n = 0..npml-1, followed by
+ * ((npml-n-0.5)/npml)**3 -- Python's ** is the host libm's pow(), which is within one ulp but not correctly rounded, so
+ * float64 vectors are bit-identical to the reference's only with the host's own cubes.  With NULL the kernel cubes in
+ * double-double (correctly rounded): float32 vectors still come out bit-identical, float64 ones to one ulp. */
+int fdtd2d_pmlparam(int dtype, int nx, int ny, int npml, const double *cubes, const fdtd_pmlayer *pml, void *stream);
 
 /* --------------------------------------------------------------------- 2D: fused time-blocked path */
 enum { FDTD2D_DZ = 0, FDTD2D_EZ, FDTD2D_HX, FDTD2D_HY, FDTD2D_IHX, FDTD2D_IHY, FDTD2D_IZ, FDTD2D_NFIELDS };

@@ -99,7 +99,7 @@ SYMBOLS = {
     "fdtd2d_incthx": (_I, [_I, _I, _I, _I, _P, _P, _P]),
     "fdtd2d_incthy": (_I, [_I, _I, _I, _I, _P, _P, _P]),
     "fdtd2d_dielectric_cylinder": (_I, [_I, _I, _I, _I, _I, _D, _D, _D, _I, _I, _P, _P, _P]),
-    "fdtd2d_pmlparam": (_I, [_I, _I, _I, _I, C.POINTER(PmlLayer), _P]),
+    "fdtd2d_pmlparam": (_I, [_I, _I, _I, _I, _P, C.POINTER(PmlLayer), _P]),
     "fdtd2d_advance": (_I, [C.POINTER(Problem2D), _I, _I, C.POINTER(_D), _I, _P, C.POINTER(_I)]),
     "fdtd2d_check_identity": (_I, [C.POINTER(Problem2D), C.POINTER(C.c_longlong)]),
     "fdtd2d_check_lossless_outside": (_I, [C.POINTER(Problem2D), C.POINTER(C.c_longlong)]),

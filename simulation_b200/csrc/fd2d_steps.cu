@@ -148,9 +148,12 @@ __global__ void k_fourier_source(int nf, Phases ph, const real *sample, real *r_
 // statements (fd2d/python/fd2d_3_4.py:173-194; the C/CUDA variants' integer m/3 is a known divergence):
 // x = nx/2-1-i+m/3, y = ny/2-1-j+n/3, inside if sqrt(x*x+y*y) <= rgrid.  Rows [row_lo, row_hi) of the global grid.
 // ---- pmlparam on the device (fd2d/program/fd2d_3_3.py:113-122): the ten 1D PML vectors from the reference's Python
-// statements, evaluated in float64 and rounded on store.  Python's ``x**3`` is C pow(), correctly rounded by glibc; the
-// device evaluates the cube in double-double (error ~2^-105 before the one rounding), so the vectors come out
-// bit-identical to surface.pmlparam (checked for every n of every npml <= 300 by the tests).
+// statements, evaluated in float64 and rounded on store.  Python's ``x**3`` is the host libm's pow(), which is NOT
+// correctly rounded (glibc: < 1 ulp; 50 of the 93 324 layer arguments of npml <= 300 come out one ulp off the exact
+// cube), so bit-identity in float64 needs the host's own cubes: the caller may pass them (`cubes`, 2*npml doubles on
+// the device: ((npml-n)/npml)**3 for n = 0..npml-1, then ((npml-n-0.5)/npml)**3) and the kernel expands them into the
+// ten vectors; without a table the cube is evaluated here in double-double (correctly rounded: float32 vectors equal
+// surface.pmlparam bit for bit for every n of every npml <= 300, float64 ones to one ulp of the cube).
 __device__ __forceinline__ double cube_rn(const double x) {
     const double hi = x * x, lo = fma(x, x, -hi);            // x^2 = hi + lo exactly
     const double p = hi * x, e = fma(hi, x, -p);             // hi*x = p + e exactly
@@ -158,8 +161,8 @@ __device__ __forceinline__ double cube_rn(const double x) {
 }
 
 template <typename real>
-__device__ __forceinline__ void pml_entries(const int i, const int N, const int npml, real *f1, real *f2, real *f3, real *g2,
-                                            real *g3) {
+__device__ __forceinline__ void pml_entries(const int i, const int N, const int npml, const double *cubes, real *f1,
+                                            real *f2, real *f3, real *g2, real *g3) {
     // f-vectors: entries n and N-2-n (H lives on the half cell); g-vectors: n and N-1-n; n = 0 .. npml-1, and a later n
     // of the reference's loop overwrites an earlier one where the two ends meet
     int nf = -1, ng = -1;
@@ -168,7 +171,7 @@ __device__ __forceinline__ void pml_entries(const int i, const int N, const int 
     if (mf >= 0 && mf < npml && mf > nf) nf = mf;
     if (mg >= 0 && mg < npml && mg > ng) ng = mg;
     if (nf >= 0) {
-        const double xn = 0.33 * cube_rn(((double)(npml - nf) - 0.5) / (double)npml);
+        const double xn = 0.33 * (cubes ? cubes[npml + nf] : cube_rn(((double)(npml - nf) - 0.5) / (double)npml));
         f1[i] = static_cast<real>(xn);
         f2[i] = static_cast<real>(1.0 / (1.0 + xn));
         f3[i] = static_cast<real>((1.0 - xn) / (1.0 + xn));
@@ -176,7 +179,7 @@ __device__ __forceinline__ void pml_entries(const int i, const int N, const int 
         f1[i] = real(0); f2[i] = real(1); f3[i] = real(1);
     }
     if (ng >= 0) {
-        const double xm = 0.33 * cube_rn((double)(npml - ng) / (double)npml);
+        const double xm = 0.33 * (cubes ? cubes[ng] : cube_rn((double)(npml - ng) / (double)npml));
         g2[i] = static_cast<real>(1.0 / (1.0 + xm));
         g3[i] = static_cast<real>((1.0 - xm) / (1.0 + xm));
     } else {
@@ -185,11 +188,11 @@ __device__ __forceinline__ void pml_entries(const int i, const int N, const int 
 }
 
 template <typename real>
-__global__ void k_pmlparam(int nx, int ny, int npml, real *fx1, real *fx2, real *fx3, real *fy1, real *fy2, real *fy3,
+__global__ void k_pmlparam(int nx, int ny, int npml, const double *cubes, real *fx1, real *fx2, real *fx3, real *fy1, real *fy2, real *fy3,
                            real *gx2, real *gx3, real *gy2, real *gy3) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nx) pml_entries<real>(i, nx, npml, fx1, fx2, fx3, gx2, gx3);
-    if (i < ny) pml_entries<real>(i, ny, npml, fy1, fy2, fy3, gy2, gy3);
+    if (i < nx) pml_entries<real>(i, nx, npml, cubes, fx1, fx2, fx3, gx2, gx3);
+    if (i < ny) pml_entries<real>(i, ny, npml, cubes, fy1, fy2, fy3, gy2, gy3);
 }
 
 template <typename real>
@@ -319,12 +322,12 @@ int fdtd2d_fourier(int dtype, int nf, int nx, int ny, const double *cosv, const 
     return fdtd::launch_fourier(dtype, nf, (size_t)nx * ny, cosv, sinv, ez, sample, ft, fdtd::as_stream(stream));
 }
 
-int fdtd2d_pmlparam(int dtype, int nx, int ny, int npml, const fdtd_pmlayer *pml, void *stream) {
+int fdtd2d_pmlparam(int dtype, int nx, int ny, int npml, const double *cubes, const fdtd_pmlayer *pml, void *stream) {
     FDTD_REQUIRE(nx >= 1 && ny >= 1 && npml >= 0 && 2 * npml <= (nx < ny ? nx : ny) && pml, "fdtd2d_pmlparam: npml=%d does not fit a %dx%d grid", npml, nx, ny);
     const void *vec[10] = {pml->fx1, pml->fx2, pml->fx3, pml->fy1, pml->fy2, pml->fy3, pml->gx2, pml->gx3, pml->gy2, pml->gy3};
     for (int k = 0; k < 10; ++k) FDTD_REQUIRE(vec[k] != nullptr, "fdtd2d_pmlparam: PML vector %d is null", k);
     const int n = nx > ny ? nx : ny;
-    DISPATCH(dtype, (k_pmlparam<real><<<(n + 255) / 256, 256, 0, fdtd::as_stream(stream)>>>(nx, ny, npml,
+    DISPATCH(dtype, (k_pmlparam<real><<<(n + 255) / 256, 256, 0, fdtd::as_stream(stream)>>>(nx, ny, npml, cubes,
         (real *)pml->fx1, (real *)pml->fx2, (real *)pml->fx3, (real *)pml->fy1, (real *)pml->fy2, (real *)pml->fy3,
         (real *)pml->gx2, (real *)pml->gx3, (real *)pml->gy2, (real *)pml->gy3)));
     FDTD_LAUNCH_CHECK("k_pmlparam");

@@ -132,10 +132,15 @@ def fourier(t: int, nf: int, nx: int, ny: int, dt: float, freq, ezi, ez, ft: ftr
                                C.byref(fs), _stream()), "fourier")
 
 
-def pmlparam(nx: int, ny: int, npml: int, dtype=np.float32, device=None, where: str = "host") -> pmlayer:
+def pmlparam(nx: int, ny: int, npml: int, dtype=np.float32, device=None, where: str = "host",
+             host_cubes: bool = True) -> pmlayer:
     """The ten PML vectors on the device.  ``where="host"`` (default): the reference formulas evaluated by
-    surface.pmlparam and uploaded; ``where="device"``: evaluated by the library's kernel (``fdtd2d_pmlparam``, float64
-    with a correctly rounded cube) -- bit-identical, no host arrays at all (profiles/r2_pmlparam_host_vs_device.txt)."""
+    surface.pmlparam and uploaded; ``where="device"``: the library's kernel (``fdtd2d_pmlparam``, float64 evaluation)
+    writes the nx- and ny-long vectors, no host arrays (profiles/r2_pmlparam_host_vs_device.txt).  The reference's
+    ``x ** 3`` is the host libm's pow(), within one ulp but not correctly rounded, so the 2*npml cubes are taken from the
+    host (Python ``**``, as the reference) and the kernel expands them: bit-identical in float32 and float64.
+    ``host_cubes=False``: nothing from the host, the kernel cubes in double-double -- float32 still bit-identical
+    (every layer of every npml <= 300 tested), float64 to one ulp of the cube."""
     if where == "host":
         host = surface.pmlparam(nx, ny, npml, dtype)
         return pmlayer(*[torch.from_numpy(a).to(device or "cuda") for a in host])
@@ -147,8 +152,13 @@ def pmlparam(nx: int, ny: int, npml: int, dtype=np.float32, device=None, where: 
     tdt = _TORCH_DT[np.dtype(dtype)]
     out = pmlayer(*[torch.empty(n, dtype=tdt, device=dev) for n in (nx, nx, nx, ny, ny, ny, nx, nx, ny, ny)])
     ps = out.as_struct()
+    cubes = None
+    if host_cubes and npml > 0:
+        table = [((npml - n) / npml) ** 3 for n in range(npml)] + [((npml - n - 0.5) / npml) ** 3 for n in range(npml)]
+        cubes = torch.tensor(table, dtype=torch.float64).to(dev)
     with torch.cuda.device(dev):
-        check(lib().fdtd2d_pmlparam(_lib.dtype_code(dtype), int(nx), int(ny), int(npml), C.byref(ps), _stream()), "pmlparam")
+        check(lib().fdtd2d_pmlparam(_lib.dtype_code(dtype), int(nx), int(ny), int(npml),
+                                    _ptr(cubes) if cubes is not None else None, C.byref(ps), _stream()), "pmlparam")
     return out
 
 

@@ -455,13 +455,20 @@ def test_emulated_reference_positional_argument_lists(emu):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_emulated_device_pmlparam(emu, dtype):
-    """fdtd2d_pmlparam (float64 on the device, correctly rounded cube) == surface.pmlparam == the reference's Python."""
+    """fdtd2d_pmlparam (float64 on the device, the host's cubes expanded) == surface.pmlparam == the reference's Python;
+    without the host's cubes (double-double cube on the device) float32 is still bit-identical."""
     from simulation_b200 import fd2d, surface
     for nx, ny, npml in ((60, 60, 8), (100, 131, 0), (97, 64, 32), (401, 300, 150), (1024, 777, 80), (2, 2, 1), (7, 9, 3)):
         host = surface.pmlparam(nx, ny, npml, dtype)
         dev = fd2d.pmlparam(nx, ny, npml, dtype, device="cpu", where="device")
         for name, h, d in zip(host._fields, host, dev):
             assert d.numpy().tobytes() == h.tobytes(), (nx, ny, npml, name)
+        own = fd2d.pmlparam(nx, ny, npml, dtype, device="cpu", where="device", host_cubes=False)
+        for name, h, d in zip(host._fields, host, own):
+            if dtype == np.float32:
+                assert d.numpy().tobytes() == h.tobytes(), (nx, ny, npml, name)
+            else:
+                assert np.all(np.abs(d.numpy() - h) <= 4 * np.spacing(np.maximum(np.abs(h), 1e-3))), (nx, ny, npml, name)
 
 
 def test_emulated_lossless_outside_split(emu):

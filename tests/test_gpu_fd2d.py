@@ -563,16 +563,27 @@ def test_baseline_config_4_vs_reference_c_openmp():
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_device_pmlparam_equals_host_setup(dtype):
     """fdtd2d_pmlparam == surface.pmlparam (== the reference's Python statements) for EVERY layer index of every PML
-    depth up to 300, both ends, odd sizes: the device evaluates x**3 in double-double, Python through glibc's pow."""
+    depth up to 300, both ends, odd sizes.  With the host's 2*npml cubes (Python ** = libm pow, not correctly rounded):
+    bit-identical in both types.  Without them the device cubes in double-double: float32 bit-identical, float64 within
+    one ulp of the cube (a few ulp of the quotient (1-x)/(1+x))."""
     from simulation_b200 import fd2d, surface
+    off = 0
     for npml in list(range(0, 301)) + [512, 1000]:
         nx, ny = 2 * npml + 37, 2 * npml + (npml % 5)
         if ny < 2:
             ny = 2
         host = surface.pmlparam(nx, ny, npml, dtype)
         dev = fd2d.pmlparam(nx, ny, npml, dtype, where="device")
-        for name, h, d in zip(host._fields, host, dev):
+        own = fd2d.pmlparam(nx, ny, npml, dtype, where="device", host_cubes=False)
+        for name, h, d, o in zip(host._fields, host, dev, own):
             assert d.cpu().numpy().tobytes() == h.tobytes(), (npml, name)
+            o = o.cpu().numpy()
+            if dtype == np.float32:
+                assert o.tobytes() == h.tobytes(), (npml, name)
+            else:
+                off += int((o != h).sum())
+                assert np.all(np.abs(o - h) <= 4 * np.spacing(np.maximum(np.abs(h), 1e-3))), (npml, name)
+    assert dtype == np.float32 or 0 < off < 2000          # the libm-vs-exact cube cases exist and are rare
     big = fd2d.pmlparam(262144, 32768, 80, dtype, where="device")
     ref = surface.pmlparam(262144, 32768, 80, dtype)
     assert all(d.cpu().numpy().tobytes() == h.tobytes() for h, d in zip(ref, big))
