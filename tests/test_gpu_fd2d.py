@@ -701,7 +701,9 @@ def test_streamed_run_tfsf_and_lossy(prog, blocks, ns, tblock, schedule):
     b.advance(9)
     for name in names:
         assert torch.equal(a.tensor(name), b.tensor(name)), name
-    assert float(host_ez.abs().max()) > 0.5
+    # the Gaussian peaks at step 20 at the head of the incident line and moves half a cell per step: the short runs
+    # have only its leading edge inside the total-field box
+    assert float(host_ez.abs().max()) > (0.5 if ns >= 50 else 1e-6)
 
 
 # ------------------------------------------------------------------ error behaviour of the boundary
@@ -768,3 +770,9 @@ def test_snapshots_match_oracle_frames(prog, every, tblock):
         if (k + 1) % every == 0:
             assert frames[(k + 1) // every - 1].numpy().tobytes() == g.ez.tobytes(), f"frame after step {k + 1}"
     _assert_same(sim, g, prog)
+
+
+def test_graft_entry_smoke_runs():
+    """The driver's smoke() (one small fused advance per path against the oracle) -- kept green by the suite."""
+    import __graft_entry__
+    __graft_entry__.smoke()
