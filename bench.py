@@ -62,17 +62,27 @@ def measured_traffic():
     return None
 
 
-def traffic_for(depth):
-    """-> (bytes per pass of 32768^2 cells at this depth or None, provenance string)"""
+def traffic_for(depths, writes_ez=True):
+    """DRAM bytes one advance() with these pass depths moves over 32768^2 cells, from the committed ncu captures
+    -> (bytes or None, bytes of the deepest pass or None, provenance string)"""
     t = measured_traffic()
     if not t:
-        return None, "no committed ncu capture"
-    per = t.get("by_depth", {}).get(str(depth))
-    if per is None and depth == 6 and "dram_bytes_per_launch" in t:
-        per = {"dram_bytes_per_pass": t["dram_bytes_per_launch"], "source": t.get("source", "profiles/roofline_traffic.json")}
-    if per is None:
-        return None, f"no ncu capture for pass depth {depth} in profiles/roofline_traffic.json"
-    return float(per["dram_bytes_per_pass"]), "from profile " + per.get("source", "?") + ", commit " + str(per.get("commit", t.get("commit", "?")))
+        return None, None, "no committed ncu capture"
+    by = t.get("by_depth", {})
+    if "6" not in by and "dram_bytes_per_launch" in t:
+        by = dict(by, **{"6": {"dram_bytes_per_pass": t["dram_bytes_per_launch"], "source": t.get("source", "profiles/roofline_traffic.json")}})
+    total, used = 0.0, {}
+    for d in depths:
+        per = by.get(str(d)) or (by.get("6") if d < 6 else None)       # a shallow pass moves the state once as well
+        if per is None:
+            return None, None, f"no ncu capture for pass depth {d} in profiles/roofline_traffic.json"
+        total += float(per["dram_bytes_per_pass"]) + float(t.get("careful_bytes_per_pass", {}).get(str(d if str(d) in by else 6), 0.0))
+        used[str(d if str(d) in by else 6)] = per
+    if writes_ez:
+        total += float(t.get("ez_store_bytes_last_pass", 0.0))
+    top = by.get(str(max(depths))) or by.get("6")
+    src = "; ".join(f"depth {k}: {v.get('source', '?')}, commit {v.get('commit', t.get('commit', '?'))}" for k, v in sorted(used.items()))
+    return total, float(top["dram_bytes_per_pass"]), "from profiles/roofline_traffic.json -- " + src
 
 
 class ClockSampler:
@@ -391,12 +401,12 @@ def run_ours(args, emit=print):
     value = cells * K / (ms * 1e-3) / 1e6
     per_gpu_cells = cells / world
     achieved = BYTES_PER_CELL_UPDATE * per_gpu_cells * K / (ms * 1e-3) / 1e9      # per GPU, algorithmic GB/s
-    dmain = max(depths)
-    traffic, traffic_src = traffic_for(dmain)
+    job_bytes, traffic, traffic_src = traffic_for(depths)
     dram_frac = None
-    if traffic is not None:
-        # real DRAM bytes (ncu, one pass over 32768^2 cells, scaled to this rank's cells) / time / measured copy peak
-        dram_frac = traffic * (per_gpu_cells / (float(N_FULL) * N_FULL)) * launches / (ms * 1e-3) / 1e9 / peak
+    if job_bytes is not None:
+        # real DRAM bytes of the K-step job (ncu captures per pass depth, interior + edge kernel, + the one ez store;
+        # measured over 32768^2 cells, scaled to this rank's cells) / time / measured copy peak
+        dram_frac = job_bytes * (per_gpu_cells / (float(N_FULL) * N_FULL)) / (ms * 1e-3) / 1e9 / peak
     halo_mode = getattr(sim, "halo_mode", "none")
 
     # ---- end to end through the public API with HOST buffers: naz up (pinned), K steps, ez down (pinned)

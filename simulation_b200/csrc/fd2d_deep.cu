@@ -567,6 +567,7 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
     const PassCounts pc = classify_pass(mp, DV, T);
     if (pc.all_careful) return launch_careful2(mp, T, lossy, pc.n_careful, 1, st);
     auto launch_interior = [&]() -> int {
+        if (g_tune.variant >= 10 && chain_supported(T, lossy)) return launch_march_chain(mp, T, g_tune.variant - 10, pc.n_fast, st);
         if (T == 12) return launch_deep_interior<12, false, 2, 8, 0>(mp, pc.n_fast, st);
         switch (g_tune.variant) {       // experiments (fdtd2d_tune2 FDTD_TUNE_VARIANT); 0 = the shipped shape
             case 1: return launch_deep_interior<8, false, 3, 8, 0>(mp, pc.n_fast, st);
@@ -598,6 +599,7 @@ void preload_deep(bool lossy) {
     cudaFuncGetAttributes(&a, k_march_deep<12, false, 2, 8, 0>);
     cudaFuncGetAttributes(&a, k_march_deep<8, false, 3, 8, KEEP_IHX>);
     cudaFuncGetAttributes(&a, k_careful2<float, DV, 0>);
+    preload_chain();
     if (lossy) cudaFuncGetAttributes(&a, k_careful2<float, DV, 1>);
 }
 

@@ -596,5 +596,9 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
 // the shared-memory-resident careful kernel (any depth <= TMAX), used by the deep passes
 int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int all_careful, cudaStream_t st);
 void preload_deep(bool lossy);
+// warp-chain passes (fd2d_chain.cu): the interior items of a depth-8 / depth-12 pass as a TMA-fed pipeline of warps
+bool chain_supported(int T, bool lossy);
+int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items, cudaStream_t st);
+void preload_chain();
 
 }  // namespace fdtd_march

@@ -233,21 +233,40 @@ class SlabFdtd2D:
                 dist.barrier(group=self.group)
             self._ghost_dirty = False
         while left > 0:
-            n = min(left, self.ghost) if self.world > 1 else left
-            left -= n
+            if self.world == 1:
+                self.engine.advance(left, tblock=tblock)
+                return
+            # The library splits a run into passes of least total cost (e.g. 20 steps = 8 + 6 + 6, not 8 + 8 + 4): the
+            # blocks between exchanges follow THAT split of everything still to come, not a split of ghost-sized blocks.
+            depths = self._depths_left(left, tblock)
             if self.halo_mode == "p2p":
                 # the pass pushes its edge rows into the neighbours' ghost rows and waits on their flags itself.
                 # ONE pass per call: the push lands in the set the neighbour's earlier passes of a multi-pass call
                 # would still be reading (the per-call handshake only orders whole calls)
-                n_one = self.engine.pass_depths(n, tblock)[0]
-                left += n - n_one
-                n = n_one
+                n = depths[0]
+                left -= n
                 self._epoch += 1
                 self.engine.advance(n, tblock=tblock, lazy_ez=left > 0, epoch=self._epoch)
                 self.exchanges += 1
             else:
+                n = 0
+                for d in depths:                   # as many whole passes as the ghost band covers
+                    if n + d > self.ghost:
+                        break
+                    n += d
+                left -= n
                 self.engine.advance(n, tblock=tblock, lazy_ez=left > 0)    # ez is stored by the last block only
                 self.exchange_ghosts()
+
+    def _depths_left(self, left: int, tblock) -> list:
+        """Pass depths of the next steps: the engine's split of all ``left`` steps when its first pass fits the ghost
+        band, else its split of one ghost-sized block."""
+        if not hasattr(self.engine, "pass_depths"):         # a stand-in stepper (tests): ghost-sized blocks
+            return [min(left, self.ghost)]
+        depths = self.engine.pass_depths(left, tblock)
+        if depths[0] > self.ghost:
+            depths = self.engine.pass_depths(min(left, self.ghost), tblock)
+        return depths
 
     def run_streamed(self, nsteps: int, naz_host: torch.Tensor, ez_host: torch.Tensor, **kw) -> None:
         """Host medium in, ``nsteps <= ghost`` steps, host Ez out, with the transfers hidden behind the kernels and NO

@@ -43,6 +43,16 @@ int fdtd_ipc_close(void *) { return FDTD_OK; }
 '''
 
 
+CHAIN_STUBS = r'''
+#include "fd2d_march.cuh"
+namespace fdtd_march {
+bool chain_supported(int, bool) { return false; }
+int launch_march_chain(const MarchParams<float> &, int, int, int, cudaStream_t) { fdtd::set_error("the warp-chain passes are not part of the emulated build"); return FDTD_EUNSUPPORTED; }
+void preload_chain() {}
+}
+'''
+
+
 def _match(text, i, open_ch, close_ch):
     """index just past the bracket that closes text[i] (== open_ch)"""
     depth = 0
@@ -152,6 +162,8 @@ def build(*source_names: str) -> str:
     for n, text in cuh.items():
         with open(os.path.join(inc, n), "w") as f:
             f.write(rewrite_device_code(text).replace('"../../include/fdtd_b200.h"', '"fdtd_b200.h"'))
+    if "fd2d_deep.cu" in srcs:       # fd2d_chain.cu (TMA + mbarrier pipeline) has no emulation: the deep passes keep their own interior kernel
+        stubs += CHAIN_STUBS
     units = {"stubs": '#include "common.cuh"\n' + stubs}
     for n, src in srcs.items():
         units[os.path.splitext(n)[0]] = f'#line 1 "{n}"\n' + rewrite_launches(rewrite_device_code(src))

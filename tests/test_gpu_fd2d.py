@@ -447,6 +447,54 @@ def test_deep_passes_and_ring_careful_kernel(prog, nx, ny, npml, chunk_rows, tbl
     _assert_same(sim, g, prog)
 
 
+@pytest.mark.parametrize("variant", [10, 11, 12])
+@pytest.mark.parametrize("chunk_rows,tblock", [(40, 12), (24, 8), (0, 12), (0, 8), (7, 8)])
+@pytest.mark.parametrize("prog,nx,ny,npml", [("3_2", 420, 1100, 8), ("3_3", 400, 1000, 12)])
+def test_warp_chain_passes(prog, nx, ny, npml, chunk_rows, tblock, variant):
+    """The warp-chain interior kernel (fd2d_chain.cu: TMA-fed staging ring, G warps of K stages each, mbarrier hand-off)
+    in every instantiated shape, with the ring careful kernel around it, on grids with a true interior: bit-for-bit vs
+    the oracle, ragged chunk heights and several advance() calls included."""
+    from simulation_b200 import _lib
+    ns = 2 * tblock + 5
+    _lib.lib().fdtd2d_tune(4, chunk_rows, 0, 0, 0)
+    _lib.lib().fdtd2d_tune2(_lib.TUNE_VARIANT, variant)
+    try:
+        sim = _sim_for(prog, nx, ny, np.float32, npml=npml, radius=0.3)
+        sim.advance(tblock, tblock=tblock)
+        sim.advance(ns - tblock, tblock=tblock)
+        sim.synchronize()
+    finally:
+        _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
+        _lib.lib().fdtd2d_tune2(_lib.TUNE_VARIANT, 0)
+    g, src = cases.grid_program(prog, nx, ny, ns, np.float32, npml=npml, radius=0.3, dft=False)
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, prog)
+
+
+@pytest.mark.parametrize("variant", [10, 11])
+def test_warp_chain_bench_plan_vs_oracle(variant):
+    """The warp-chain passes on the bench's launch plan (4-wide vectors, 256-row chunks, depth 8 and 12) forced onto
+    2304 x 4096 with a random medium: every array bit-for-bit against the numpy oracle."""
+    from simulation_b200 import _lib
+    nx, ny, npml, ns = 2304, 4096, 80, 45
+    rng = np.random.default_rng(6)
+    naz = rng.uniform(0.25, 1.0, size=(nx, ny)).astype(np.float32)
+    _lib.lib().fdtd2d_tune(4, 0, 0, 0, 0)
+    _lib.lib().fdtd2d_tune2(_lib.TUNE_VARIANT, variant)
+    try:
+        sim = _sim_for("3_2", nx, ny, np.float32, npml=npml, naz=naz)
+        sim.advance(24, tblock=8)
+        sim.advance(ns - 24, tblock=12)
+        sim.synchronize()
+    finally:
+        _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
+        _lib.lib().fdtd2d_tune2(_lib.TUNE_VARIANT, 0)
+    g, src = cases.grid_program("3_2", nx, ny, ns, np.float32, npml=npml, naz=naz.copy())
+    orc.advance_2d(g, src)
+    _assert_same(sim, g, "3_2")
+    assert float(np.abs(g.ez).max()) > 0.1
+
+
 @pytest.mark.parametrize("tblock,chunk", [(0, 0), (6, 128), (8, 0)])
 def test_bench_launch_plan_vs_oracle(tblock, chunk):
     """The launch plan bench.py runs at 32768^2 -- 4-wide vectors; depth-8 deep passes on 256-row chunks mixed with depth
