@@ -47,10 +47,16 @@ constexpr int NARR = 6;               // arrays that travel with a row: dz hx hy
 
 struct ChainMaps { CUtensorMap m[NARR]; };   // in_dz in_hx in_hy in_ihx in_ihy naz: (rows, ny) float, box R x 128
 
-template <int G_, int K_, int R_, int NSTAGE_, int QD_, int GROUPS_>
+template <int G_, int K_, int GROUPS_>
 struct ChainShape {
-    static constexpr int G = G_, K = K_, R = R_, NSTAGE = NSTAGE_, QD = QD_, GROUPS = GROUPS_;
+    static constexpr int G = G_, K = K_, GROUPS = GROUPS_;
     static constexpr int T = G * K, NS = K + 1;
+    // Ring geometry tied to the register rotation: a TMA box is NS rows x 128 columns of one array (one trip of the
+    // unrolled row loop), the staging ring has two boxes per array, a queue has NS one-row slots -- so every slot index
+    // is a compile-time constant of the unrolled loop and a barrier's parity is a bit of the trip counter.  (One-row
+    // boxes in an NS-slot ring halve the staging memory but measured 23 % slower: 685 against 890 Gcell/s at
+    // G = 2, K = 4 -- six 512-byte TMA operations and an elected issue per row instead of per trip.)
+    static constexpr int R = NS, NSTAGE = 2, QD = NS;
     static constexpr int HALO = ((T + CV - 1) / CV) * CV, W = 32 * CV, USE = W - 2 * HALO;
     static constexpr int BOX_B = R * CROWB;                   // one array of one box
     static constexpr int STAGE_B = NARR * BOX_B;              // one staging slot
@@ -61,18 +67,21 @@ struct ChainShape {
     static constexpr int GROUP_SMEM = ((OFF_BAR + NBAR * 8 + 127) / 128) * 128;
     static constexpr int THREADS = GROUPS * G * 32;
     static constexpr int SMEM = GROUPS * GROUP_SMEM;
+    static_assert(SMEM <= 227 * 1024, "the groups of a CTA must fit the shared memory of an SM");
 };
 
-// ---- mbarrier and TMA in PTX (sm_90+)
+// ---- mbarrier and TMA in PTX (sm_90+).  `leader`: the instruction is predicated on it (one lane), not branched around.
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(const unsigned bar, const unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(const unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(const unsigned bar, const unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive(const unsigned bar, const int leader) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.s32 p, %1, 0;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(bar), "r"(leader) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(const unsigned bar, const unsigned parity) {
     asm volatile(
@@ -80,43 +89,64 @@ __device__ __forceinline__ void mbar_wait(const unsigned bar, const unsigned par
         ".reg .pred p;\n"
         "CHAIN_WAIT:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra CHAIN_DONE;\n"
-        "bra CHAIN_WAIT;\n"
-        "CHAIN_DONE:\n"
+        "@!p bra CHAIN_WAIT;\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// one box (R rows x 128 columns of one array) global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void tma_load_2d(const unsigned dst, const CUtensorMap *map, const unsigned bar, const int col,
-                                            const int row) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(col), "r"(row) : "memory");
+// one staging slot: arm its barrier with the bytes of the six boxes, then one box (R rows x 128 columns) per array
+// global -> shared, completion counted in bytes on the barrier
+__device__ __forceinline__ void tma_issue_boxes(const unsigned dst, const int box_bytes, const ChainMaps &maps, const unsigned bar,
+                                                const int col, const int row, const int leader) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.s32 p, %10, 0;\n"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %9;\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%2, {%8, %11}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%12], [%3, {%8, %11}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%13], [%4, {%8, %11}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%14], [%5, {%8, %11}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%15], [%6, {%8, %11}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%16], [%7, {%8, %11}], [%1];\n"
+        "}\n"
+        ::"r"(dst), "r"(bar), "l"(&maps.m[0]), "l"(&maps.m[1]), "l"(&maps.m[2]), "l"(&maps.m[3]), "l"(&maps.m[4]), "l"(&maps.m[5]),
+          "r"(col), "r"(NARR * box_bytes), "r"(leader), "r"(row), "r"(dst + box_bytes), "r"(dst + 2 * box_bytes),
+          "r"(dst + 3 * box_bytes), "r"(dst + 4 * box_bytes), "r"(dst + 5 * box_bytes)
+        : "memory");
 }
 
-__device__ __forceinline__ void sts4(void *dst, const float (&d)[CV]) {
-    *reinterpret_cast<float4 *>(dst) = make_float4(d[0], d[1], d[2], d[3]);
+// values computed in register PAIRS leave as two 64-bit halves: assembling an aligned quad for a 128-bit store costs
+// four moves (same bytes, same banks)
+__device__ __forceinline__ void sts22(void *dst, const float (&d)[CV]) {
+    *reinterpret_cast<float2 *>(dst) = make_float2(d[0], d[1]);
+    *reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(dst) + 8) = make_float2(d[2], d[3]);
 }
 
-template <typename Shape>
+// One warp of the chain.  FIRST: input from the TMA staging ring; else from the queue behind it.  LAST: output to global
+// memory; else into the queue ahead.  Every warp runs the same number of trips: a warp hands on EVERY row that leaves
+// its last stage, the all-zero sets of the first K sub-iterations included (zero rows stay zero through a stage), so
+// the x-th input of warp g is global row r_begin + x - g*K and nothing in the loop depends on the warp's position.
+template <typename Shape, bool FIRST, bool LAST>
 __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const ChainMaps &maps, const int strip, const int i0,
                                            const int i1, const int lane, const int wg, unsigned char *const gsm) {
-    constexpr int G = Shape::G, K = Shape::K, R = Shape::R, NSTAGE = Shape::NSTAGE, QD = Shape::QD;
+    constexpr int K = Shape::K, NSTAGE = Shape::NSTAGE;
     constexpr int T = Shape::T, NS = Shape::NS, HALO = Shape::HALO, W = Shape::W, USE = Shape::USE;
-    const bool first = wg == 0, last = wg == G - 1;
+    static_assert(Shape::R == NS && Shape::QD == NS && NSTAGE == 2, "slot indices follow the register rotation");
 
     const int c0 = strip * USE - HALO;               // first column of the strip (halo included)
     const int jb = c0 + lane * CV;                   // first column of this lane
     const bool col_store = (lane * CV >= HALO) && (lane * CV + CV <= W - HALO);
     const int r_begin = i0 - T, r_end = i1 + T;      // rows fed to stage 0: [r_begin, r_end)
-    const int n_in = (r_end - r_begin) - wg * K;     // rows this warp receives
+    const int n_trip = (r_end - r_begin + NS - 1) / NS;   // trips of NS rows (the last one may run past r_end: never stored)
+    const int leader = lane == 0;
 
-    // shared memory of the group
-    unsigned char *const stage = gsm;                                    // [NSTAGE][NARR][R][CROWB]
-    unsigned char *const queue = gsm + Shape::OFF_Q;                     // [G-1][QD][NARR][CROWB]
+    // shared memory of the group: staging ring, queues, barriers
     const unsigned bars = smem_u32(gsm + Shape::OFF_BAR);
-    // barrier ids: stage full s -> s; queue q slot d: full -> NSTAGE + (q*QD + d)*2, empty -> ... + 1
-    auto bar_stage = [&](const int s) { return bars + 8u * s; };
-    auto bar_qfull = [&](const int q, const int d) { return bars + 8u * (NSTAGE + (q * QD + d) * 2); };
-    auto bar_qempty = [&](const int q, const int d) { return bars + 8u * (NSTAGE + (q * QD + d) * 2 + 1); };
+    // barriers: staging slot s -> bars + 8 s; queue q slot d: full -> bars + 8 (NSTAGE + (q NS + d) 2), empty -> + 8
+    const unsigned char *const in_data = FIRST ? gsm + lane * CLB
+                                               : gsm + Shape::OFF_Q + (wg - 1) * NS * Shape::QSLOT_B + lane * CLB;
+    const unsigned in_bar = bars + 8u * (NSTAGE + (wg - 1) * NS * 2);     // (queue behind; unused by the first warp)
+    unsigned char *const out_data = gsm + Shape::OFF_Q + wg * NS * Shape::QSLOT_B + lane * CLB;   // (queue ahead)
+    const unsigned out_bar = bars + 8u * (NSTAGE + wg * NS * 2);
 
     RowSet<float, CV> S[NS];
 #pragma unroll
@@ -129,107 +159,78 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
         const unsigned long long z = p.negzero2;
         negzero = make_float2(__uint_as_float((unsigned)z), __uint_as_float((unsigned)(z >> 32)));
     }
-
-    // ---- first warp: the TMA side.  Box b holds the rows r_begin + b*R .. + R - 1 of the six arrays.
-    const int n_box = (n_in + R - 1) / R;            // (meaningful for the first warp)
-    auto issue_box = [&](const int b, const int slot) {       // one lane
-        const unsigned bar = bar_stage(slot);
-        mbar_arrive_expect_tx(bar, (unsigned)Shape::STAGE_B);
-        const unsigned dst = smem_u32(stage + slot * Shape::STAGE_B);
-        const int row = r_begin + b * R - p.row_base;
-#pragma unroll
-        for (int a = 0; a < NARR; ++a) tma_load_2d(dst + a * Shape::BOX_B, &maps.m[a], bar, c0, row);
-    };
-    if (first && lane == 0) {
-#pragma unroll
-        for (int b = 0; b < NSTAGE; ++b)
-            if (b < n_box) issue_box(b, b);
+    const unsigned stage0 = smem_u32(gsm);
+    const int row0 = r_begin - p.row_base;           // array row of the first box
+    if (FIRST) {                                     // prime the staging ring: boxes 0 and 1
+        tma_issue_boxes(stage0, Shape::BOX_B, maps, bars, c0, row0, leader);
+        tma_issue_boxes(stage0 + Shape::STAGE_B, Shape::BOX_B, maps, bars + 8u, c0, row0 + NS, leader && n_trip > 1);
     }
-
-    int in_slot = 0, in_row = 0, box = 0;            // input ring position (first warp: staging slot / row in box / box id)
-    unsigned in_phase = 0;
-    int out_slot = 0;
-    unsigned out_phase = 0;
-    long long off_s = (long long)(r_begin - K - p.row_base) * p.ny + jb;   // last warp: element offset of the row stored next
-
+    // last warp: element offset of the row stored next (its x-th input is row r_begin + x - (G-1)K, released K rows later)
+    long long off_s = (long long)(r_begin - T - p.row_base) * p.ny + jb;
+    int ro = r_begin - T;
     auto st2 = [&](float *dst, const float (&d)[CV]) {      // register pairs leave as two 64-bit halves (no quad assembly)
         *reinterpret_cast<float2 *>(dst) = make_float2(d[0], d[1]);
         *reinterpret_cast<float2 *>(dst + 2) = make_float2(d[2], d[3]);
     };
 
 #pragma unroll 1
-    for (int x0 = 0; x0 < n_in; x0 += NS) {
+    for (int trip = 0; trip < n_trip; ++trip) {
+        const unsigned par = (unsigned)trip & 1u;    // queue barriers complete one phase per trip
+        const int sslot = trip & 1;                  // staging slot of this trip's box; its barrier's parity is (trip >> 1) & 1
+        const unsigned char *const src_base = FIRST ? in_data + sslot * Shape::STAGE_B : in_data;
+        if (FIRST) mbar_wait(bars + 8u * sslot, ((unsigned)trip >> 1) & 1u);
 #pragma unroll
         for (int u = 0; u < NS; ++u) {
-            const int x = x0 + u;                     // this warp's x-th input: global row r_begin + x
-            if (x >= n_in) break;
             // ---- take the row into register set u
             {
-                const unsigned char *src;
-                int astride;
-                if (first) {
-                    if (in_row == 0) mbar_wait(bar_stage(in_slot), in_phase);
-                    src = stage + in_slot * Shape::STAGE_B + in_row * CROWB + lane * CLB;
-                    astride = Shape::BOX_B;
-                } else {
-                    mbar_wait(bar_qfull(wg - 1, in_slot), in_phase);
-                    src = queue + ((wg - 1) * QD + in_slot) * Shape::QSLOT_B + lane * CLB;
-                    astride = CROWB;
-                }
-                lds_vec<float, CV>(src + 0 * astride, S[u].dz);
-                lds_vec<float, CV>(src + 1 * astride, S[u].hx);
-                lds_vec<float, CV>(src + 2 * astride, S[u].hy);
-                lds_vec<float, CV>(src + 3 * astride, S[u].ihx);
-                lds_vec<float, CV>(src + 4 * astride, S[u].ihy);
-                lds_vec<float, CV>(src + 5 * astride, S[u].naz);
+                constexpr int ASTRIDE = FIRST ? Shape::BOX_B : CROWB;
+                const unsigned char *const src = src_base + u * (FIRST ? CROWB : Shape::QSLOT_B);
+                if (!FIRST) mbar_wait(in_bar + 16u * u, par);
+                lds_vec<float, CV>(src + 0 * ASTRIDE, S[u].dz);
+                lds_vec<float, CV>(src + 1 * ASTRIDE, S[u].hx);
+                lds_vec<float, CV>(src + 2 * ASTRIDE, S[u].hy);
+                lds_vec<float, CV>(src + 3 * ASTRIDE, S[u].ihx);
+                lds_vec<float, CV>(src + 4 * ASTRIDE, S[u].ihy);
+                lds_vec<float, CV>(src + 5 * ASTRIDE, S[u].naz);
             }
-            // ---- this warp's K stages: stage s has row x-s arriving and holds row x-s-1
+            // ---- this warp's K stages: stage s has the (x-s)-th input arriving and holds the (x-s-1)-th
 #pragma unroll
             for (int s = 0; s < K; ++s) {
                 const int sa = (u - s + 2 * NS) % NS, sh = (u - s - 1 + 2 * NS) % NS;
                 march_stage_pk<CV, false, false>(S[sa], S[sh], negzero, nullptr, nullptr);
             }
-            // ---- give the input slot back (every value read from it has been used by now)
-            __syncwarp();
-            if (first) {
-                if (++in_row == R || x + 1 == n_in) {
-                    in_row = 0;
-                    if (lane == 0 && box + NSTAGE < n_box) issue_box(box + NSTAGE, in_slot);
-                    ++box;
-                    if (++in_slot == NSTAGE) { in_slot = 0; in_phase ^= 1u; }
+            // ---- give the input slot back: every value read from it has been used by the stages above
+            if (!FIRST) mbar_arrive(in_bar + 16u * u + 8u, leader);
+            // ---- the row leaving the last stage: register set (u+1) % NS
+            const RowSet<float, CV> &O = S[(u + 1) % NS];
+            if (LAST) {
+                if (ro >= i0 && ro < i1 && col_store) {
+                    st2(p.out_dz + off_s, O.dz);
+                    st2(p.out_hx + off_s, O.hx);
+                    st2(p.out_hy + off_s, O.hy);
+                    st2(p.out_ihx + off_s, O.ihx);
+                    st2(p.out_ihy + off_s, O.ihy);
+                    if (p.write_ez) st2(p.out_ez + off_s, O.ez);
                 }
+                off_s += p.ny;
+                ++ro;
             } else {
-                if (lane == 0) mbar_arrive(bar_qempty(wg - 1, in_slot));
-                if (++in_slot == QD) { in_slot = 0; in_phase ^= 1u; }
+                mbar_wait(out_bar + 16u * u + 8u, par ^ 1u);           // the consumer has released the slot's previous row
+                unsigned char *const dst = out_data + u * Shape::QSLOT_B;
+                sts22(dst + 0 * CROWB, O.dz);
+                sts22(dst + 1 * CROWB, O.hx);
+                sts22(dst + 2 * CROWB, O.hy);
+                sts22(dst + 3 * CROWB, O.ihx);
+                sts22(dst + 4 * CROWB, O.ihy);
+                sts22(dst + 5 * CROWB, O.naz);
+                __syncwarp();
+                mbar_arrive(out_bar + 16u * u, leader);
             }
-            // ---- the row leaving the last stage: set (u+1) % NS = this warp's input x-K, now K levels later
-            if (x >= K) {
-                const RowSet<float, CV> &O = S[(u + 1) % NS];
-                if (last) {
-                    const int ro = r_begin + x - K;
-                    if (ro >= i0 && ro < i1 && col_store) {
-                        st2(p.out_dz + off_s, O.dz);
-                        st2(p.out_hx + off_s, O.hx);
-                        st2(p.out_hy + off_s, O.hy);
-                        st2(p.out_ihx + off_s, O.ihx);
-                        st2(p.out_ihy + off_s, O.ihy);
-                        if (p.write_ez) st2(p.out_ez + off_s, O.ez);
-                    }
-                } else {
-                    mbar_wait(bar_qempty(wg, out_slot), out_phase ^ 1u);
-                    unsigned char *dst = queue + (wg * QD + out_slot) * Shape::QSLOT_B + lane * CLB;
-                    sts4(dst + 0 * CROWB, O.dz);
-                    sts4(dst + 1 * CROWB, O.hx);
-                    sts4(dst + 2 * CROWB, O.hy);
-                    sts4(dst + 3 * CROWB, O.ihx);
-                    sts4(dst + 4 * CROWB, O.ihy);
-                    sts4(dst + 5 * CROWB, O.naz);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_qfull(wg, out_slot));
-                    if (++out_slot == QD) { out_slot = 0; out_phase ^= 1u; }
-                }
-            }
-            off_s += p.ny;
+        }
+        if (FIRST) {     // the box of this trip is consumed: refill its slot with the box two trips ahead
+            __syncwarp();
+            tma_issue_boxes(stage0 + sslot * Shape::STAGE_B, Shape::BOX_B, maps, bars + 8u * sslot, c0, row0 + (trip + 2) * NS,
+                            leader && trip + 2 < n_trip);
         }
     }
 }
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(Shape::THREADS, 1)
 k_march_chain(const __grid_constant__ MarchParams<float> p, const __grid_constant__ ChainMaps maps) {
     extern __shared__ __align__(1024) unsigned char chain_smem[];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // (tells the compiler the value is warp-uniform)
     const int grp = warp / Shape::G, wg = warp % Shape::G;
     unsigned char *const gsm = chain_smem + (size_t)grp * Shape::GROUP_SMEM;
     if (wg == 0 && lane == 0) {
@@ -250,7 +251,9 @@ k_march_chain(const __grid_constant__ MarchParams<float> p, const __grid_constan
     __syncthreads();
     int strip, i0, i1;
     if (!decode_item<true>(p, blockIdx.x * Shape::GROUPS + grp, 0, CV, Shape::T, false, strip, i0, i1)) return;   // the whole group
-    chain_body<Shape>(p, maps, strip, i0, i1, lane, wg, gsm);
+    if (wg == 0) chain_body<Shape, true, false>(p, maps, strip, i0, i1, lane, wg, gsm);
+    else if (wg == Shape::G - 1) chain_body<Shape, false, true>(p, maps, strip, i0, i1, lane, wg, gsm);
+    else chain_body<Shape, false, false>(p, maps, strip, i0, i1, lane, wg, gsm);
 }
 
 // ---- host: tensor maps
@@ -312,12 +315,13 @@ int launch_chain(const MarchParams<float> &mp, int items, cudaStream_t st) {
     return FDTD_OK;
 }
 
-//                        G  K  R  NSTAGE QD GROUPS
-using Chain8 = ChainShape<4, 2, 2, 3, 2, 4>;          // depth 8: sixteen warps per SM
-using Chain8b = ChainShape<4, 2, 4, 2, 3, 4>;         // ... bigger boxes, deeper queues
-using Chain8c = ChainShape<2, 4, 2, 3, 2, 4>;         // ... two warps of four stages (eight warps per SM)
-using Chain12 = ChainShape<4, 3, 2, 3, 2, 3>;         // depth 12: twelve warps per SM
-using Chain12b = ChainShape<6, 2, 2, 3, 2, 2>;        // ... six warps of two stages
+//                        G  K  GROUPS
+using Chain8 = ChainShape<2, 4, 4>;          // depth 8: two warps of four stages, eight warps per SM
+using Chain8b = ChainShape<2, 4, 5>;         // ... ten warps per SM (168 registers; 226 KB of shared memory)
+using Chain8c = ChainShape<4, 2, 4>;         // ... four warps of two stages, sixteen warps per SM
+using Chain12 = ChainShape<4, 3, 3>;         // depth 12: four warps of three stages, twelve warps per SM
+using Chain12b = ChainShape<2, 6, 3>;        // ... two warps of six stages, six warps per SM
+using Chain12c = ChainShape<3, 4, 3>;        // ... three warps of four stages, nine warps per SM
 
 }  // namespace
 
@@ -339,6 +343,7 @@ int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items
     }
     if (T == 12) {
         if (shape == 1) return launch_chain<Chain12b>(mp, items, st);
+        if (shape == 2) return launch_chain<Chain12c>(mp, items, st);
         return launch_chain<Chain12>(mp, items, st);
     }
     fdtd::set_error("no warp-chain pass of depth %d", T);
