@@ -270,14 +270,16 @@ int fdtd2d_halo_status(const fdtd2d_problem *p, unsigned long long *word);
  * ignores the lossless-outside promise.  Results are bit-identical under every setting (that is what the tests use
  * it for). */
 int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, int force_careful);
-/* More process-wide knobs, by key.  FDTD_TUNE_DEEP: 1 (default) = passes of depth 8 and 12 use the kernels with
- * shared-memory-resident accumulators where they apply (float, 4-wide vectors, no fused DFT), 0 = never (depth <= 8,
- * register-pipeline kernels only), 2 = additionally run the shared-memory-resident careful (edge) kernel at every
- * depth.  FDTD_TUNE_HALO_WAIT_MS: bound of the fused halo exchange's wait for a neighbour in milliseconds (0 = the
- * default of 20 s).  Results are bit-identical under every setting. */
+/* More process-wide knobs, by key.  FDTD_TUNE_DEEP: 1 (default) = passes of depth 8 and 12 use the deep kernels where
+ * they apply (float, 4-wide vectors, no fused DFT), 0 = never (depth <= 8, register-pipeline kernels only), 2 =
+ * additionally run the shared-memory-resident careful (edge) kernel at every depth.  FDTD_TUNE_HALO_WAIT_MS: bound of
+ * the fused halo exchange's wait for a neighbour in milliseconds (0 = the default of 20 s).  FDTD_TUNE_VARIANT: interior
+ * kernel of the deep passes -- 0 (default) = the warp-chain kernel (TMA-fed pipeline of warps; shipped shape), 1..3 =
+ * the shared-memory-accumulator kernels, >= 10 = other warp-chain shapes.  Results are bit-identical under every
+ * setting. */
 #define FDTD_TUNE_DEEP 0
 #define FDTD_TUNE_HALO_WAIT_MS 1
-#define FDTD_TUNE_VARIANT 2          /* kernel-shape experiments of the deep passes (0 = the shipped shape) */
+#define FDTD_TUNE_VARIANT 2
 int fdtd2d_tune2(int key, long long value);
 
 #ifdef __cplusplus

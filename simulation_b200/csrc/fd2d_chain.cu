@@ -47,16 +47,21 @@ constexpr int NARR = 6;               // arrays that travel with a row: dz hx hy
 
 struct ChainMaps { CUtensorMap m[NARR]; };   // in_dz in_hx in_hy in_ihx in_ihy naz: (rows, ny) float, box R x 128
 
-template <int G_, int K_, int GROUPS_>
+template <int G_, int K_, int GROUPS_, int R_ = K_ + 1, int NSTAGE_ = 2, bool STS_PTX_ = false>
 struct ChainShape {
+    static constexpr bool STS_PTX = STS_PTX_;
     static constexpr int G = G_, K = K_, GROUPS = GROUPS_;
     static constexpr int T = G * K, NS = K + 1;
+    static_assert(T == 8 || T == 12, "depths the host plans");
     // Ring geometry tied to the register rotation: a TMA box is NS rows x 128 columns of one array (one trip of the
     // unrolled row loop), the staging ring has two boxes per array, a queue has NS one-row slots -- so every slot index
     // is a compile-time constant of the unrolled loop and a barrier's parity is a bit of the trip counter.  (One-row
     // boxes in an NS-slot ring halve the staging memory but measured 23 % slower: 685 against 890 Gcell/s at
     // G = 2, K = 4 -- six 512-byte TMA operations and an elected issue per row instead of per trip.)
-    static constexpr int R = NS, NSTAGE = 2, QD = NS;
+    // Smaller boxes (R_ < NS rows, NSTAGE_ of them) walk the staging ring with run-time counters instead: a few uniform
+    // instructions per row buy back staging memory, i.e. room for more groups per SM.
+    static constexpr int R = R_, NSTAGE = NSTAGE_, QD = NS;
+    static constexpr bool STATIC_RING = (R == NS && NSTAGE == 2);
     static constexpr int HALO = ((T + CV - 1) / CV) * CV, W = 32 * CV, USE = W - 2 * HALO;
     static constexpr int BOX_B = R * CROWB;                   // one array of one box
     static constexpr int STAGE_B = NARR * BOX_B;              // one staging slot
@@ -93,32 +98,44 @@ __device__ __forceinline__ void mbar_wait(const unsigned bar, const unsigned par
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 // one staging slot: arm its barrier with the bytes of the six boxes, then one box (R rows x 128 columns) per array
-// global -> shared, completion counted in bytes on the barrier
+// global -> shared, completion counted in bytes on the barrier.  Called by the whole (converged) warp under a
+// warp-uniform condition; elect.sync picks the one lane that issues, which lets the assembler keep every operand in
+// uniform registers (a predicate derived from the lane id costs a waterfall loop per instruction).
 __device__ __forceinline__ void tma_issue_boxes(const unsigned dst, const int box_bytes, const ChainMaps &maps, const unsigned bar,
-                                                const int col, const int row, const int leader) {
+                                                const int col, const int row) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "setp.ne.s32 p, %10, 0;\n"
+        "elect.sync _|p, 0xffffffff;\n"
         "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %9;\n"
-        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%2, {%8, %11}], [%1];\n"
-        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%12], [%3, {%8, %11}], [%1];\n"
-        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%13], [%4, {%8, %11}], [%1];\n"
-        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%14], [%5, {%8, %11}], [%1];\n"
-        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%15], [%6, {%8, %11}], [%1];\n"
-        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%16], [%7, {%8, %11}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%2, {%8, %10}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%11], [%3, {%8, %10}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%12], [%4, {%8, %10}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%13], [%5, {%8, %10}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%14], [%6, {%8, %10}], [%1];\n"
+        "@p cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%15], [%7, {%8, %10}], [%1];\n"
         "}\n"
         ::"r"(dst), "r"(bar), "l"(&maps.m[0]), "l"(&maps.m[1]), "l"(&maps.m[2]), "l"(&maps.m[3]), "l"(&maps.m[4]), "l"(&maps.m[5]),
-          "r"(col), "r"(NARR * box_bytes), "r"(leader), "r"(row), "r"(dst + box_bytes), "r"(dst + 2 * box_bytes),
+          "r"(col), "r"(NARR * box_bytes), "r"(row), "r"(dst + box_bytes), "r"(dst + 2 * box_bytes),
           "r"(dst + 3 * box_bytes), "r"(dst + 4 * box_bytes), "r"(dst + 5 * box_bytes)
         : "memory");
 }
 
-// values computed in register PAIRS leave as two 64-bit halves: assembling an aligned quad for a 128-bit store costs
-// four moves (same bytes, same banks)
+// Queue stores.  Values computed in register PAIRS are not aligned quads: the compiler fuses two adjacent 64-bit
+// stores into one 128-bit store plus four moves.  PTX = true spells the 64-bit stores out (no moves, twice the store
+// instructions, and volatile statements the scheduler cannot move the stage arithmetic across; no memory clobber: the
+// stores only have to stay ordered with the barrier operations, which volatile gives).  Measured: the compiler's form wins
+// at eight warps per SM (889 against 845 Gcell/s), the PTX form at twelve (885 against 848).
+template <bool PTX>
 __device__ __forceinline__ void sts22(void *dst, const float (&d)[CV]) {
-    *reinterpret_cast<float2 *>(dst) = make_float2(d[0], d[1]);
-    *reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(dst) + 8) = make_float2(d[2], d[3]);
+    if constexpr (PTX) {
+        const unsigned a = smem_u32(dst);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(d[0]), "f"(d[1]));
+        asm volatile("st.shared.v2.f32 [%0+8], {%1, %2};" ::"r"(a), "f"(d[2]), "f"(d[3]));
+    } else {
+        *reinterpret_cast<float2 *>(dst) = make_float2(d[0], d[1]);
+        *reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(dst) + 8) = make_float2(d[2], d[3]);
+    }
 }
 
 // One warp of the chain.  FIRST: input from the TMA staging ring; else from the queue behind it.  LAST: output to global
@@ -130,7 +147,9 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
                                            const int i1, const int lane, const int wg, unsigned char *const gsm) {
     constexpr int K = Shape::K, NSTAGE = Shape::NSTAGE;
     constexpr int T = Shape::T, NS = Shape::NS, HALO = Shape::HALO, W = Shape::W, USE = Shape::USE;
-    static_assert(Shape::R == NS && Shape::QD == NS && NSTAGE == 2, "slot indices follow the register rotation");
+    static_assert(Shape::QD == NS, "queue slot indices follow the register rotation");
+    constexpr bool SRING = Shape::STATIC_RING;
+    constexpr int R = Shape::R;
 
     const int c0 = strip * USE - HALO;               // first column of the strip (halo included)
     const int jb = c0 + lane * CV;                   // first column of this lane
@@ -161,10 +180,15 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
     }
     const unsigned stage0 = smem_u32(gsm);
     const int row0 = r_begin - p.row_base;           // array row of the first box
-    if (FIRST) {                                     // prime the staging ring: boxes 0 and 1
-        tma_issue_boxes(stage0, Shape::BOX_B, maps, bars, c0, row0, leader);
-        tma_issue_boxes(stage0 + Shape::STAGE_B, Shape::BOX_B, maps, bars + 8u, c0, row0 + NS, leader && n_trip > 1);
+    const int n_box = (n_trip * NS + R - 1) / R;     // boxes of R rows that cover every row the trips take
+    if (FIRST) {                                     // prime the staging ring
+#pragma unroll
+        for (int b = 0; b < NSTAGE; ++b)
+            if (b < n_box) tma_issue_boxes(stage0 + b * Shape::STAGE_B, Shape::BOX_B, maps, bars + 8u * b, c0, row0 + b * R);
     }
+    // run-time walk of the staging ring (first warp, !SRING): slot / row in the box / box id / parity of the slot's barrier
+    int rs_slot = 0, rs_row = 0, rs_box = 0;
+    unsigned rs_par = 0;
     // last warp: element offset of the row stored next (its x-th input is row r_begin + x - (G-1)K, released K rows later)
     long long off_s = (long long)(r_begin - T - p.row_base) * p.ny + jb;
     int ro = r_begin - T;
@@ -177,14 +201,18 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
     for (int trip = 0; trip < n_trip; ++trip) {
         const unsigned par = (unsigned)trip & 1u;    // queue barriers complete one phase per trip
         const int sslot = trip & 1;                  // staging slot of this trip's box; its barrier's parity is (trip >> 1) & 1
-        const unsigned char *const src_base = FIRST ? in_data + sslot * Shape::STAGE_B : in_data;
-        if (FIRST) mbar_wait(bars + 8u * sslot, ((unsigned)trip >> 1) & 1u);
+        const unsigned char *const src_base = (FIRST && SRING) ? in_data + sslot * Shape::STAGE_B : in_data;
+        if (FIRST && SRING) mbar_wait(bars + 8u * sslot, ((unsigned)trip >> 1) & 1u);
 #pragma unroll
         for (int u = 0; u < NS; ++u) {
             // ---- take the row into register set u
             {
                 constexpr int ASTRIDE = FIRST ? Shape::BOX_B : CROWB;
-                const unsigned char *const src = src_base + u * (FIRST ? CROWB : Shape::QSLOT_B);
+                const unsigned char *src = src_base + u * (FIRST ? CROWB : Shape::QSLOT_B);
+                if (FIRST && !SRING) {
+                    if (rs_row == 0) mbar_wait(bars + 8u * rs_slot, rs_par);
+                    src = in_data + rs_slot * Shape::STAGE_B + rs_row * CROWB;
+                }
                 if (!FIRST) mbar_wait(in_bar + 16u * u, par);
                 lds_vec<float, CV>(src + 0 * ASTRIDE, S[u].dz);
                 lds_vec<float, CV>(src + 1 * ASTRIDE, S[u].hx);
@@ -201,6 +229,17 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
             }
             // ---- give the input slot back: every value read from it has been used by the stages above
             if (!FIRST) mbar_arrive(in_bar + 16u * u + 8u, leader);
+            if (FIRST && !SRING) {
+                if (++rs_row == R) {                 // the box is consumed: refill its slot with the box NSTAGE ahead
+                    rs_row = 0;
+                    __syncwarp();
+                    if (rs_box + NSTAGE < n_box)
+                        tma_issue_boxes(stage0 + rs_slot * Shape::STAGE_B, Shape::BOX_B, maps, bars + 8u * rs_slot, c0,
+                                        row0 + (rs_box + NSTAGE) * R);
+                    ++rs_box;
+                    if (++rs_slot == NSTAGE) { rs_slot = 0; rs_par ^= 1u; }
+                }
+            }
             // ---- the row leaving the last stage: register set (u+1) % NS
             const RowSet<float, CV> &O = S[(u + 1) % NS];
             if (LAST) {
@@ -217,20 +256,20 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
             } else {
                 mbar_wait(out_bar + 16u * u + 8u, par ^ 1u);           // the consumer has released the slot's previous row
                 unsigned char *const dst = out_data + u * Shape::QSLOT_B;
-                sts22(dst + 0 * CROWB, O.dz);
-                sts22(dst + 1 * CROWB, O.hx);
-                sts22(dst + 2 * CROWB, O.hy);
-                sts22(dst + 3 * CROWB, O.ihx);
-                sts22(dst + 4 * CROWB, O.ihy);
-                sts22(dst + 5 * CROWB, O.naz);
+                sts22<Shape::STS_PTX>(dst + 0 * CROWB, O.dz);
+                sts22<Shape::STS_PTX>(dst + 1 * CROWB, O.hx);
+                sts22<Shape::STS_PTX>(dst + 2 * CROWB, O.hy);
+                sts22<Shape::STS_PTX>(dst + 3 * CROWB, O.ihx);
+                sts22<Shape::STS_PTX>(dst + 4 * CROWB, O.ihy);
+                sts22<Shape::STS_PTX>(dst + 5 * CROWB, O.naz);
                 __syncwarp();
                 mbar_arrive(out_bar + 16u * u, leader);
             }
         }
-        if (FIRST) {     // the box of this trip is consumed: refill its slot with the box two trips ahead
+        if (FIRST && SRING) {     // the box of this trip is consumed: refill its slot with the box two trips ahead
             __syncwarp();
-            tma_issue_boxes(stage0 + sslot * Shape::STAGE_B, Shape::BOX_B, maps, bars + 8u * sslot, c0, row0 + (trip + 2) * NS,
-                            leader && trip + 2 < n_trip);
+            if (trip + 2 < n_trip)
+                tma_issue_boxes(stage0 + sslot * Shape::STAGE_B, Shape::BOX_B, maps, bars + 8u * sslot, c0, row0 + (trip + 2) * NS);
         }
     }
 }
@@ -315,13 +354,14 @@ int launch_chain(const MarchParams<float> &mp, int items, cudaStream_t st) {
     return FDTD_OK;
 }
 
-//                        G  K  GROUPS
-using Chain8 = ChainShape<2, 4, 4>;          // depth 8: two warps of four stages, eight warps per SM
-using Chain8b = ChainShape<2, 4, 5>;         // ... ten warps per SM (168 registers; 226 KB of shared memory)
-using Chain8c = ChainShape<4, 2, 4>;         // ... four warps of two stages, sixteen warps per SM
-using Chain12 = ChainShape<4, 3, 3>;         // depth 12: four warps of three stages, twelve warps per SM
-using Chain12b = ChainShape<2, 6, 3>;        // ... two warps of six stages, six warps per SM
-using Chain12c = ChainShape<3, 4, 3>;        // ... three warps of four stages, nine warps per SM
+//                        G  K  GROUPS [R NSTAGE STS_PTX]      measured at 32768^2 (profiles/r2_chain_shapes.txt)
+using Chain8 = ChainShape<2, 4, 4>;                    // depth 8, shipped: two warps of four stages, eight warps per SM -- 889 Gcell/s
+using Chain8b = ChainShape<2, 4, 6, 2, 3, true>;       // twelve warps per SM: three boxes of two rows, run-time staging ring -- 885
+using Chain8c = ChainShape<2, 4, 6, 3, 2, true>;       // twelve warps per SM: two boxes of three rows -- 814
+using Chain8d = ChainShape<4, 2, 4>;                   // four warps of two stages, sixteen warps per SM -- 711 (twice the hand-offs per stage)
+using Chain12 = ChainShape<4, 3, 3>;                   // depth 12, shipped: four warps of three stages, twelve warps per SM -- 765
+using Chain12b = ChainShape<4, 3, 3, 2, 3>;            // run-time staging ring, boxes of two rows -- 718
+using Chain12c = ChainShape<3, 4, 3>;                  // three warps of four stages, nine warps per SM -- 524
 
 }  // namespace
 
@@ -339,6 +379,7 @@ int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items
     if (T == 8) {
         if (shape == 1) return launch_chain<Chain8b>(mp, items, st);
         if (shape == 2) return launch_chain<Chain8c>(mp, items, st);
+        if (shape == 3) return launch_chain<Chain8d>(mp, items, st);
         return launch_chain<Chain8>(mp, items, st);
     }
     if (T == 12) {

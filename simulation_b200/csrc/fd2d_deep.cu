@@ -567,9 +567,13 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
     const PassCounts pc = classify_pass(mp, DV, T);
     if (pc.all_careful) return launch_careful2(mp, T, lossy, pc.n_careful, 1, st);
     auto launch_interior = [&]() -> int {
-        if (g_tune.variant >= 10 && chain_supported(T, lossy)) return launch_march_chain(mp, T, g_tune.variant - 10, pc.n_fast, st);
+        // the warp-chain kernel of fd2d_chain.cu (TMA-fed pipeline of warps) is the shipped interior kernel of both
+        // depths; variants 1..3 select the shared-memory-accumulator kernels of this file (also the fallback when the
+        // driver has no tensor-map encoder), variants >= 10 the other chain shapes
+        const int v = g_tune.variant;
+        if ((v == 0 || v >= 10) && chain_supported(T, lossy)) return launch_march_chain(mp, T, v >= 10 ? v - 10 : 0, pc.n_fast, st);
         if (T == 12) return launch_deep_interior<12, false, 2, 8, 0>(mp, pc.n_fast, st);
-        switch (g_tune.variant) {       // experiments (fdtd2d_tune2 FDTD_TUNE_VARIANT); 0 = the shipped shape
+        switch (v) {
             case 1: return launch_deep_interior<8, false, 3, 8, 0>(mp, pc.n_fast, st);
             case 2: return launch_deep_interior<8, false, 2, 8, KEEP_IHX>(mp, pc.n_fast, st);
             default: return launch_deep_interior<8, false, 3, 8, KEEP_IHX>(mp, pc.n_fast, st);

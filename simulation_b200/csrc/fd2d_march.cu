@@ -578,13 +578,13 @@ Plan choose_plan(const fdtd2d_problem *q) {
 // (+ 12 on explicit request where the deep passes apply).  tblock = 0: the library's choice.  Where the deep passes
 // apply that is the split of the remaining steps into passes of depth 8, 6 and <= 4 with the least total cost: every
 // pass moves the state through HBM once, so a shallow pass costs about as much as a depth-6 one (HBM-bound: 8.3 ms at
-// 32768^2), while a depth-8 pass (shared-memory-bound) costs 10.9 ms -- e.g. 20 steps = 8 + 6 + 6, 96 steps = 12 x 8
-// (profiles/r2_deep_variants.txt).
+// 32768^2), while a depth-8 pass (the warp-chain kernel, issue-bound) costs 9.7 ms -- e.g. 20 steps = 8 + 6 + 6,
+// 96 steps = 12 x 8 (profiles/r2_chain_shapes.txt; 10.9 ms with the shared-memory-accumulator kernel).
 inline int next_depth(const Plan &plan, int tblock, int left, int nf) {
     if (tblock <= 0 && plan.deep && nf == 0) {
         // cost of a pass by depth, in units of a depth-6 pass; least-cost split by dynamic programming over `left`
         static const int depths[] = {8, 6, 4, 3, 2, 1};
-        static const double cost[] = {1.31, 1.00, 0.97, 0.96, 0.95, 0.94};
+        static const double cost[] = {1.17, 1.00, 0.97, 0.96, 0.95, 0.94};
         constexpr int HORIZON = 48;                     // beyond this many steps the split starts with a depth-8 pass anyway
         if (left > HORIZON) return 8;
         double best[HORIZON + 1];

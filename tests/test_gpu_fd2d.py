@@ -423,18 +423,20 @@ def test_full_size_linearity_32768():
 
 
 # ------------------------------------------------------------------ deep passes (fd2d_deep.cu) and the bench's own launch plan
-@pytest.mark.parametrize("deep", [1, 2])
+@pytest.mark.parametrize("deep,variant", [(1, 0), (2, 0), (1, 3), (1, 1), (1, 2)])
 @pytest.mark.parametrize("chunk_rows,tblock", [(40, 12), (24, 8), (0, 12), (64, 6)])
 @pytest.mark.parametrize("prog,nx,ny,npml", [("3_2", 420, 1100, 8), ("3_3", 400, 1000, 12), ("3_4", 380, 1040, 10)])
-def test_deep_passes_and_ring_careful_kernel(prog, nx, ny, npml, chunk_rows, tblock, deep):
-    """Depth 8 / 12 passes (shared-memory-resident accumulators + the shared-memory-ring careful kernel) and, with
-    deep = 2, the ring careful kernel at every depth, on grids with a true interior; bit-for-bit vs the oracle.  The
-    lossy program has no deep interior kernel: it exercises the fallback (register pipeline) and the lossy ring
-    careful kernel."""
+def test_deep_passes_and_ring_careful_kernel(prog, nx, ny, npml, chunk_rows, tblock, deep, variant):
+    """Depth 8 / 12 passes -- the shipped warp-chain interior kernel (variant 0) and the shared-memory-accumulator
+    kernels it replaced (variants 1..3, still the fallback without a tensor-map encoder) + the shared-memory-ring
+    careful kernel -- and, with deep = 2, the ring careful kernel at every depth, on grids with a true interior;
+    bit-for-bit vs the oracle.  The lossy program has no deep interior kernel: it exercises the fallback (register
+    pipeline) and the lossy ring careful kernel."""
     from simulation_b200 import _lib
     ns = 2 * tblock + 5
     _lib.lib().fdtd2d_tune(4, chunk_rows, 0, 0, 0)
     _lib.lib().fdtd2d_tune2(_lib.TUNE_DEEP, deep)
+    _lib.lib().fdtd2d_tune2(_lib.TUNE_VARIANT, variant)
     try:
         sim = _sim_for(prog, nx, ny, np.float32, npml=npml, radius=0.3)
         sim.advance(ns, tblock=tblock)
@@ -442,12 +444,13 @@ def test_deep_passes_and_ring_careful_kernel(prog, nx, ny, npml, chunk_rows, tbl
     finally:
         _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
         _lib.lib().fdtd2d_tune2(_lib.TUNE_DEEP, 1)
+        _lib.lib().fdtd2d_tune2(_lib.TUNE_VARIANT, 0)
     g, src = cases.grid_program(prog, nx, ny, ns, np.float32, npml=npml, radius=0.3, dft=False)
     orc.advance_2d(g, src)
     _assert_same(sim, g, prog)
 
 
-@pytest.mark.parametrize("variant", [10, 11, 12])
+@pytest.mark.parametrize("variant", [0, 11, 12, 13])
 @pytest.mark.parametrize("chunk_rows,tblock", [(40, 12), (24, 8), (0, 12), (0, 8), (7, 8)])
 @pytest.mark.parametrize("prog,nx,ny,npml", [("3_2", 420, 1100, 8), ("3_3", 400, 1000, 12)])
 def test_warp_chain_passes(prog, nx, ny, npml, chunk_rows, tblock, variant):

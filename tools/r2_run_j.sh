@@ -16,14 +16,9 @@ except Exception as e:
     print("$name failed", e); print(open("$out/bench_$name.err").read()[-1500:])
 PY
 }
-ARGS="--steps 96 --tblock 8";  run t8_deep FDTD_VARIANT=0
-ARGS="--steps 96 --tblock 8";  run t8_chain_g2k4_w8 FDTD_VARIANT=10
-ARGS="--steps 96 --tblock 8";  run t8_chain_g2k4_w10 FDTD_VARIANT=11
-ARGS="--steps 96 --tblock 8";  run t8_chain_g4k2_w16 FDTD_VARIANT=12
+ARGS="--steps 96 --tblock 8";  run t8_chain_g2k4_w8_ptxsts FDTD_VARIANT=10
+ARGS="--steps 96 --tblock 8";  run t8_chain_g2k4_w8_csts FDTD_VARIANT=14
+ARGS="--steps 96 --tblock 8";  run t8_chain_g2k4_w12_box2x3_ptxsts FDTD_VARIANT=11
+ARGS="--steps 96 --tblock 8";  run t8_chain_g2k4_w12_box2x3_csts FDTD_VARIANT=15
+ARGS="--steps 96 --tblock 8";  run t8_chain_g2k4_w12_box3x2 FDTD_VARIANT=12
 ARGS="--steps 96 --tblock 12"; run t12_chain_g4k3_w12 FDTD_VARIANT=10
-ARGS="--steps 96 --tblock 12"; run t12_chain_g2k6_w6 FDTD_VARIANT=11
-ARGS="--steps 96 --tblock 12"; run t12_chain_g3k4_w9 FDTD_VARIANT=12
-ARGS="--steps 96 --tblock 8";  run t8_chain_g2k4_w10_c512 FDTD_VARIANT=11 FDTD_CHUNK_ROWS=512
-ARGS="--steps 96 --tblock 8";  run t8_chain_g2k4_w10_c128 FDTD_VARIANT=11 FDTD_CHUNK_ROWS=128
-ARGS="--steps 96 --tblock 12"; run t12_chain_g4k3_c512 FDTD_VARIANT=10 FDTD_CHUNK_ROWS=512
-ARGS="--steps 96 --tblock 12"; run t12_chain_g2k6_c512 FDTD_VARIANT=11 FDTD_CHUNK_ROWS=512
