@@ -518,19 +518,19 @@ int opt_in_smem(K kernel, size_t smem, size_t (&configured)[64], std::mutex &gua
     return FDTD_OK;
 }
 
-template <int MODE>
+template <int V, int MODE>
 int launch_careful2_k(const MarchParams<float> &mp, int T, int items, int all_careful, cudaStream_t st) {
     if (items <= 0) return FDTD_OK;
-    const size_t per_warp = (size_t)CarefulShape<float, DV, MODE>::warp_smem(T);
+    const size_t per_warp = (size_t)CarefulShape<float, V, MODE>::warp_smem(T);
     int warps = CAREFUL2_WARPS;
     while (warps > 1 && (size_t)warps * per_warp > 220 * 1024) --warps;
     const size_t smem = (size_t)warps * per_warp;
     static size_t configured[64] = {0};
     static std::mutex guard;
-    const int rc = opt_in_smem(k_careful2<float, DV, MODE>, smem, configured, guard);
+    const int rc = opt_in_smem(k_careful2<float, V, MODE>, smem, configured, guard);
     if (rc != FDTD_OK) return rc;
     const int grid = (items + warps - 1) / warps;
-    k_careful2<float, DV, MODE><<<grid, warps * 32, smem, st>>>(mp, all_careful, T);
+    k_careful2<float, V, MODE><<<grid, warps * 32, smem, st>>>(mp, all_careful, T);
     FDTD_LAUNCH_CHECK("k_careful2");
     return FDTD_OK;
 }
@@ -557,9 +557,11 @@ namespace fdtd_march {
 
 bool deep_supported(int T, bool lossy) { return (T == 8 || T == 12) && !lossy; }
 
-int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int all_careful, cudaStream_t st) {
+int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int all_careful, cudaStream_t st, int V) {
     if (T < 1 || T > TMAX) { fdtd::set_error("careful kernel: depth %d outside [1, %d]", T, TMAX); return FDTD_EINVAL; }
-    return lossy ? launch_careful2_k<1>(mp, T, items, all_careful, st) : launch_careful2_k<0>(mp, T, items, all_careful, st);
+    if (V == 2) return lossy ? launch_careful2_k<2, 1>(mp, T, items, all_careful, st) : launch_careful2_k<2, 0>(mp, T, items, all_careful, st);
+    if (V != DV) { fdtd::set_error("ring careful kernel: vector width %d (2 or 4)", V); return FDTD_EUNSUPPORTED; }
+    return lossy ? launch_careful2_k<DV, 1>(mp, T, items, all_careful, st) : launch_careful2_k<DV, 0>(mp, T, items, all_careful, st);
 }
 
 int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st) {
@@ -603,8 +605,12 @@ void preload_deep(bool lossy) {
     cudaFuncGetAttributes(&a, k_march_deep<12, false, 2, 8, 0>);
     cudaFuncGetAttributes(&a, k_march_deep<8, false, 3, 8, KEEP_IHX>);
     cudaFuncGetAttributes(&a, k_careful2<float, DV, 0>);
+    cudaFuncGetAttributes(&a, k_careful2<float, 2, 0>);
     preload_chain();
-    if (lossy) cudaFuncGetAttributes(&a, k_careful2<float, DV, 1>);
+    if (lossy) {
+        cudaFuncGetAttributes(&a, k_careful2<float, DV, 1>);
+        cudaFuncGetAttributes(&a, k_careful2<float, 2, 1>);
+    }
 }
 
 }  // namespace fdtd_march

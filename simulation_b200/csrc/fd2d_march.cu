@@ -427,8 +427,8 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     // the careful (edge) warps: the register-shifting kernel of this file or, on request (fdtd2d_tune2 deep = 2), the
     // shared-memory-resident one of fd2d_deep.cu
     auto launch_careful = [&](int items, int all, cudaStream_t where) -> int {
-        if constexpr (sizeof(real) == 4 && V == 4 && (MODE & 2) == 0) {
-            if (g_tune.deep == 2) return launch_careful2(mp, T, (MODE & 1) != 0, items, all, where);
+        if constexpr (sizeof(real) == 4 && (V == 4 || V == 2) && (MODE & 2) == 0) {
+            if (g_tune.deep == 2) return launch_careful2(mp, T, (MODE & 1) != 0, items, all, where, V);
         }
         return launch_one<real, V, T, MODE, false>(mp, items, all, where);
     };

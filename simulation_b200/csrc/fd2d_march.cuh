@@ -594,7 +594,7 @@ PassCounts classify_pass(MarchParams<real> &mp, const int V, const int T) {
 bool deep_supported(int T, bool lossy);
 int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st);
 // the shared-memory-resident careful kernel (any depth <= TMAX), used by the deep passes
-int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int all_careful, cudaStream_t st);
+int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int all_careful, cudaStream_t st, int V = 4);
 void preload_deep(bool lossy);
 // warp-chain passes (fd2d_chain.cu): the interior items of a depth-8 / depth-12 pass as a TMA-fed pipeline of warps
 bool chain_supported(int T, bool lossy);
