@@ -705,6 +705,27 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         chunk = max(1, min(chunk, rows));
         mp.chunk_rows = chunk;
         mp.nchunks = (rows + chunk - 1) / chunk;
+        mp.first_rows = mp.last_rows = 0;
+        if (g_tune.edge_chunks && rows >= 3 * chunk) {
+            // Short edge chunks: F = the fewest rows (a multiple of 8) after which a chunk starts clear of everything
+            // that makes the rows above it special -- the same conditions classify_pass applies to lo = i0 - T - 1 --
+            // and L likewise for hi = i1 + 2T + RING + 2 below.  No edge condition on a side: that chunk stays whole.
+            const int margin_lo = T + 1, margin_hi = 2 * T + RING + 2;
+            int top = max(max(1, mp.in_lo), mp.ident_row_lo);          // lo must not fall below this row
+            int bot = min(min(mp.nx - 1, mp.in_hi), mp.ident_row_hi);  // hi must not exceed this row
+            int f_req = top + margin_lo - mp.out_lo, l_req = mp.out_hi + margin_hi - bot;
+            if (q->halo > 0) {
+                f_req = max(f_req, max(q->row_lo + margin_lo, q->row_lo + q->halo) - mp.out_lo);
+                l_req = max(l_req, mp.out_hi - min(q->row_hi - margin_hi, q->row_hi - q->halo));
+            }
+            int F = f_req <= 0 ? chunk : min(chunk, (f_req + 7) / 8 * 8);
+            int L = l_req <= 0 ? chunk : min(chunk, (l_req + 7) / 8 * 8);
+            if ((F < chunk || L < chunk) && rows - F - L >= 1) {
+                mp.first_rows = F;
+                mp.last_rows = L;
+                mp.nchunks = 2 + (rows - F - L + chunk - 1) / chunk;
+            }
+        }
 
         if (tfsf && !(q->flags & FDTD_INCIDENT_READY)) {
             SrcTable tab;
@@ -849,6 +870,9 @@ int fdtd2d_tune2(int key, long long value) {
             return FDTD_OK;
         case FDTD_TUNE_VARIANT:
             g_tune.variant = (int)value;
+            return FDTD_OK;
+        case FDTD_TUNE_EDGE_CHUNKS:
+            g_tune.edge_chunks = value != 0;
             return FDTD_OK;
         default:
             fdtd::set_error("fdtd2d_tune2: unknown key %d", key);

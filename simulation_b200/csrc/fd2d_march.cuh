@@ -25,6 +25,11 @@ struct MarchParams {
     int in_lo, in_hi;                          // global rows readable in the input set
     int out_lo, out_hi;                        // global rows this pass must produce
     int chunk_rows, nstrips, nchunks;
+    // Edge chunks: the rows that need the careful kernel because of what lies ABOVE or BELOW them (PML rows, the grid's
+    // first / last row, TFSF box rows, ghost rows and pushed rows of a slab) are a thin band, so the first and the last
+    // chunk are cut just tall enough to hold it (first_rows / last_rows; 0 = uniform chunks) and everything between
+    // is ordinary chunks of chunk_rows -- see chunk_span.
+    int first_rows, last_rows;
     int cchunk_rows, ncchunks;                 // row partition of the SPECIAL strips (careful kernel): finer on small launches
     int tfsf, npml;
     const real *ezi_hist, *hxi_hist;           // [T][ny], [T][2]
@@ -371,6 +376,25 @@ __device__ __forceinline__ int kth_not_in(int k, const int *skip, int n) {
 }
 
 
+// rows [i0, i1) of chunk k of the pass (uniform chunks, or a short first and last chunk around uniform ones)
+template <typename real>
+__host__ __device__ __forceinline__ void chunk_span(const MarchParams<real> &p, const int k, int &i0, int &i1) {
+    if (p.first_rows == 0) {
+        i0 = p.out_lo + k * p.chunk_rows;
+        i1 = i0 + p.chunk_rows < p.out_hi ? i0 + p.chunk_rows : p.out_hi;
+    } else if (k == 0) {
+        i0 = p.out_lo;
+        i1 = p.out_lo + p.first_rows;
+    } else if (k == p.nchunks - 1) {
+        i0 = p.out_hi - p.last_rows;
+        i1 = p.out_hi;
+    } else {
+        const int end = p.out_hi - p.last_rows;
+        i0 = p.out_lo + p.first_rows + (k - 1) * p.chunk_rows;
+        i1 = i0 + p.chunk_rows < end ? i0 + p.chunk_rows : end;
+    }
+}
+
 // ---- which (strip, rows) a warp owns.  Two kinds of launch share one index space per pass:
 //   FAST    : interior warps -- (ordinary strips) x (ordinary chunks): every column (halo included) is an ordinary
 //             cell and every row touched (warm-up, drain and unroll overrun included) is an ordinary stored row;
@@ -383,7 +407,8 @@ template <bool FAST, typename real>
 __device__ __forceinline__ bool decode_item(const MarchParams<real> &p, const int w, const int all_careful, const int V,
                                             const int T, const bool lossy_kernel, int &strip, int &i0, int &i1) {
     const int nsf = p.nstrips - p.n_sstrips, ncf = p.nchunks - p.n_schunks;   // ordinary strips / chunks
-    int chunk, crows = p.chunk_rows;            // rows [out_lo + chunk*crows, ...) of the strip
+    int chunk;
+    bool own_partition = false;                 // special strips: their own (finer, uniform) row partition
     if (FAST) {
         if (w >= nsf * ncf) return false;
         strip = kth_not_in(w % nsf, p.sstrips, p.n_sstrips);
@@ -394,7 +419,8 @@ __device__ __forceinline__ bool decode_item(const MarchParams<real> &p, const in
             // rows and columns this warp touches (warm-up, drain and fetch run-ahead included), as the host classifies them
             const int W = 32 * V, HALO = ((T + V - 1) / V) * V, USE = W - 2 * HALO;
             const int c0 = strip * USE - HALO, c1 = c0 + W;
-            const int r0 = p.out_lo + chunk * crows, r1 = min(r0 + crows, p.out_hi);
+            int r0, r1;
+            chunk_span(p, chunk, r0, r1);
             const int lo = r0 - T - 1, hi = r1 + 2 * T + RING + 2;
             const bool in_box = c0 < p.lz_col_hi && c1 > p.lz_col_lo && lo < p.lz_row_hi && hi > p.lz_row_lo;
             if (in_box != lossy_kernel) return false;    // lossy kernel: warps meeting the box; lossless kernel: the others
@@ -408,7 +434,7 @@ __device__ __forceinline__ bool decode_item(const MarchParams<real> &p, const in
         if (w < na) {
             strip = p.sstrips[w % p.n_sstrips];
             chunk = w / p.n_sstrips;
-            crows = p.cchunk_rows;
+            own_partition = true;
         } else {
             const int x = w - na, nb = nsf * p.n_schunks;
             if (x < nb) {
@@ -421,8 +447,12 @@ __device__ __forceinline__ bool decode_item(const MarchParams<real> &p, const in
             }
         }
     }
-    i0 = p.out_lo + chunk * crows;
-    i1 = min(i0 + crows, p.out_hi);
+    if (own_partition) {
+        i0 = p.out_lo + chunk * p.cchunk_rows;
+        i1 = min(i0 + p.cchunk_rows, p.out_hi);
+    } else {
+        chunk_span(p, chunk, i0, i1);
+    }
     return true;
 }
 
@@ -510,6 +540,7 @@ struct Tuning {
     int serial = 2;              // 2 = fork the edge kernel onto a side stream (measured +2 %); 1 = edge then interior in order
     int variant = 0;             // kernel-shape experiments of the deep passes (0 = the shipped shape)
     int deep = 1;                // 0 = never use the deep passes of fd2d_deep.cu; 2 = the smem-resident careful kernel at every depth
+    int edge_chunks = 1;         // 1 = short first / last chunk around the rows that need the careful kernel; 0 = uniform chunks
     unsigned long long spin_ns = HALO_SPIN_NS;
 };
 extern Tuning g_tune;
@@ -538,7 +569,8 @@ PassCounts classify_pass(MarchParams<real> &mp, const int V, const int T) {
         }
     }
     for (int k = 0; k < mp.nchunks && !overflow; ++k) {
-        const int i0 = mp.out_lo + k * mp.chunk_rows, i1 = min(i0 + mp.chunk_rows, mp.out_hi);
+        int i0, i1;
+        chunk_span(mp, k, i0, i1);
         const int lo = i0 - T - 1, hi = i1 + 2 * T + RING + 2; // rows touched (fetch run-ahead included): [lo, hi)
         bool special = (lo < max(max(1, mp.in_lo), mp.ident_row_lo)) || (hi > min(min(mp.nx - 1, mp.in_hi), mp.ident_row_hi));
         if (mp.tfsf) special = special || (ia - 1 >= lo && ia - 1 < hi) || (iz_ >= lo && iz_ < hi);
@@ -558,7 +590,8 @@ PassCounts classify_pass(MarchParams<real> &mp, const int V, const int T) {
             const int c0 = k * USE - HALO, c1 = c0 + W;
             if (!(mp.src_j >= c0 && mp.src_j < c1) || listed(mp.sstrips, ns, k)) continue;
             for (int c = 0; c < mp.nchunks && !overflow; ++c) {
-                const int i0 = mp.out_lo + c * mp.chunk_rows, i1 = min(i0 + mp.chunk_rows, mp.out_hi);
+                int i0, i1;
+                chunk_span(mp, c, i0, i1);
                 const int lo = i0 - T - 1, hi = i1 + 2 * T + RING + 2;
                 if (!(mp.src_i >= lo && mp.src_i < hi) || listed(mp.schunks, nc, c)) continue;
                 if (np == MAX_PAIRS) overflow = true;

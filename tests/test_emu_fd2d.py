@@ -25,10 +25,11 @@ def emu(monkeypatch):
     return device.install(monkeypatch)
 
 
-def _run(emu, prog, nx, ny, npml, ns, dtype, tblock=None, radius=0.12, tune=(0, 0, 0, 0, 0), parts=None, deep=1):
+def _run(emu, prog, nx, ny, npml, ns, dtype, tblock=None, radius=0.12, tune=(0, 0, 0, 0, 0), parts=None, deep=1, edge=1):
     before = emu.emu_launches()
     emu.fdtd2d_tune(*tune)
     emu.fdtd2d_tune2(0, deep)
+    emu.fdtd2d_tune2(3, edge)
     try:
         sim = _sim_for(prog, nx, ny, dtype, npml=npml, radius=radius, device="cpu")
         for part in (parts or (ns,)):
@@ -36,6 +37,7 @@ def _run(emu, prog, nx, ny, npml, ns, dtype, tblock=None, radius=0.12, tune=(0, 
     finally:
         emu.fdtd2d_tune(0, 0, 0, 0, 0)
         emu.fdtd2d_tune2(0, 1)
+        emu.fdtd2d_tune2(3, 1)
     assert sim.t == ns and emu.emu_launches() > before
     g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=radius, dft=False)
     orc.advance_2d(g, src)
@@ -301,6 +303,19 @@ def test_emulated_deep_passes(emu, prog, nx, ny, npml, tblock, chunk_rows):
         assert emu.emu_launches() - before == 3 * (3 if prog == "3_3" else 2) + 2, "an interior kernel did not run in every pass"
 
 
+@pytest.mark.parametrize("prog,nx,ny,npml,vec,chunk,tblock", [("3_2", 420, 600, 8, 4, 64, 6), ("3_3", 400, 560, 12, 4, 96, 8),
+                                                             ("3_4", 380, 520, 10, 2, 64, 6), ("3_3", 500, 300, 20, 2, 48, 4)])
+def test_emulated_short_edge_chunks(emu, prog, nx, ny, npml, vec, chunk, tblock):
+    """The first and the last row chunk are cut just tall enough to hold the rows that need the careful kernel (PML,
+    grid edge, TFSF box rows); ordinary chunks lie between.  With and without the short edge chunks: the oracle's bits,
+    and FEWER careful warps with them (the launch count is the same, so compare the two runs' arrays only)."""
+    ns = 2 * tblock + 3
+    a = _run(emu, prog, nx, ny, npml, ns, np.float32, tblock, radius=0.3, tune=(vec, chunk, 0, 0, 0), edge=1)
+    b = _run(emu, prog, nx, ny, npml, ns, np.float32, tblock, radius=0.3, tune=(vec, chunk, 0, 0, 0), edge=0)
+    for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
+        assert a.get(name).tobytes() == b.get(name).tobytes(), name
+
+
 def test_emulated_deep_equals_register_pipeline(emu):
     """Same problem through the deep passes (8 + 8 + 8), the register-pipeline kernels alone (deep off: 8 + 8 + 8 with
     the naz ring) and depth 6: all arrays byte-identical."""
@@ -312,14 +327,15 @@ def test_emulated_deep_equals_register_pipeline(emu):
         assert a.get(name).tobytes() == b.get(name).tobytes() == c.get(name).tobytes(), name
 
 
-@pytest.mark.parametrize("prog,tblock", [("3_2", 6), ("3_3", 4), ("3_4", 6), ("3_4", 3), ("3_1", 8), ("3_3", 12)])
-def test_emulated_ring_careful_kernel_at_every_depth(emu, prog, tblock):
+@pytest.mark.parametrize("prog,tblock,vec", [("3_2", 6, 4), ("3_3", 4, 4), ("3_4", 6, 4), ("3_4", 3, 4), ("3_1", 8, 4), ("3_3", 12, 4),
+                                              ("3_4", 6, 2), ("3_3", 4, 2), ("3_2", 8, 2)])
+def test_emulated_ring_careful_kernel_at_every_depth(emu, prog, tblock, vec):
     """fdtd2d_tune2(deep = 2): the shared-memory-ring careful kernel (run-time depth, rolled stages) replaces the
-    register-shifting one in every float / 4-wide pass -- lossless and lossy, TFSF, point source; once for the whole
-    grid (force_careful) and once beside the interior kernels."""
+    register-shifting one in every float pass of 4- or 2-wide vectors -- lossless and lossy, TFSF, point source; once
+    for the whole grid (force_careful) and once beside the interior kernels."""
     for force in (1, 0):
         _run(emu, prog, 150, 560, 0 if prog == "3_1" else 9, 2 * tblock + 1, np.float32, tblock, radius=0.3,
-             tune=(4, 24, 0, 0, force), deep=2)
+             tune=(vec, 24, 0, 0, force), deep=2)
 
 
 def test_emulated_plan_query(emu):
