@@ -543,7 +543,18 @@ template <> int pick_v<double>(int ny) { return ny % 2 == 0 ? 2 : 1; }
 struct Plan {
     int V, T, chunk;
     bool deep;       // the deep passes of fd2d_deep.cu (depth 8 and 12: float, 4-wide vectors, no fused DFT) are available
+    long cells;      // cells the call produces
 };
+
+// rows per chunk of a pass.  The deep (warp-chain) passes recompute 2T rows per chunk and, with the short edge chunks,
+// pay nothing extra at the edges for tall chunks: 384 rows at 32768^2 (965 Gcell/s; 256: 947, 128: 891), 256 at
+// 16384^2 (832; 128: 798), 128 at 8192^2 (640; 64: 604, 256: 605) -- profiles/r2_chunk_rows_by_grid.txt.  The
+// register-pipeline passes keep their round-1 heights (depth 6 at 32768^2: 128 rows 781, 192: 763, 256: 751).
+inline int pass_chunk_rows(const Plan &plan, int T, bool deep_pass) {
+    if (g_tune.chunk_rows > 0) return g_tune.chunk_rows;
+    if (deep_pass) return plan.cells >= 500000000L ? 384 : (plan.cells >= 100000000L ? 256 : 128);
+    return max(plan.chunk, 4 * T);                  // at most ~50 % warm-up/drain recompute on shallow grids
+}
 
 template <typename real>
 Plan choose_plan(const fdtd2d_problem *q) {
@@ -553,15 +564,15 @@ Plan choose_plan(const fdtd2d_problem *q) {
     const int ny = q->ny;
     Plan p;
     if (sizeof(real) == 4) {                            // profiles/r1_v18_sweep_grid_sizes.txt
-        if (cells < 6000000L)        p = {2, 4, 16, false};
-        else if (cells < 24000000L)  p = {2, 6, 64, false};
-        else if (cells < 100000000L) p = {lossy ? 2 : 4, 6, 64, false};
-        else                         p = {lossy ? 2 : 4, 6, 128, false};   // 7 row sets x 4 columns x 9 lossy fields spill
+        if (cells < 6000000L)        p = {2, 4, 16, false, cells};
+        else if (cells < 24000000L)  p = {2, 6, 64, false, cells};
+        else if (cells < 100000000L) p = {lossy ? 2 : 4, 6, 64, false, cells};
+        else                         p = {lossy ? 2 : 4, 6, 128, false, cells};   // 7 row sets x 4 columns x 9 lossy fields spill
     } else {
-        if (cells < 1500000L)        p = {1, 4, 16, false};           // profiles/r1_sweep_fp64.txt
-        else if (cells < 12000000L)  p = {2, 4, 16, false};
-        else if (cells < 150000000L) p = {2, 6, 64, false};
-        else                         p = {2, 6, 128, false};
+        if (cells < 1500000L)        p = {1, 4, 16, false, cells};           // profiles/r1_sweep_fp64.txt
+        else if (cells < 12000000L)  p = {2, 4, 16, false, cells};
+        else if (cells < 150000000L) p = {2, 6, 64, false, cells};
+        else                         p = {2, 6, 128, false, cells};
     }
     while (p.V > 1 && ny % p.V != 0) p.V >>= 1;
     // vector width of the call (the depth-dependent float64 exception is applied per pass)
@@ -574,17 +585,19 @@ Plan choose_plan(const fdtd2d_problem *q) {
     return p;
 }
 
-// Depth of the next pass: at most `left` steps and `tblock`, rounded down to an instantiated depth: 1, 2, 3, 4, 6, 8
-// (+ 12 on explicit request where the deep passes apply).  tblock = 0: the library's choice.  Where the deep passes
-// apply that is the split of the remaining steps into passes of depth 8, 6 and <= 4 with the least total cost: every
-// pass moves the state through HBM once, so a shallow pass costs about as much as a depth-6 one (HBM-bound: 8.3 ms at
-// 32768^2), while a depth-8 pass (the warp-chain kernel, issue-bound) costs 9.7 ms -- e.g. 20 steps = 8 + 6 + 6,
-// 96 steps = 12 x 8 (profiles/r2_chain_shapes.txt; 10.9 ms with the shared-memory-accumulator kernel).
+// Depth of the next pass: at most `left` steps and `tblock`, rounded down to an instantiated depth: 1, 2, 3, 4, 6, 8, 12
+// (8 and 12 where the deep passes apply).  tblock = 0: the library's choice.  Where the deep passes apply that is the
+// split of the remaining steps into passes of least total cost: every pass moves the state through HBM once, so a
+// shallow pass costs about as much as a depth-6 one (HBM-bound: 8.25 ms at 32768^2), a depth-8 pass of the warp-chain
+// kernel 8.9 ms and a depth-12 pass 14.9 ms (profiles/r2_chunk_rows_by_grid.txt) -- e.g. 20 steps = 12 + 8 (23.8 ms;
+// 8 + 6 + 6 = 25.4, round 1's 6 + 6 + 6 + 2 = 34.2), 96 steps = 12 x 8.  Depth 12 is measured at 32768^2 only and is
+// offered to the split from 500 M cells up.
 inline int next_depth(const Plan &plan, int tblock, int left, int nf) {
     if (tblock <= 0 && plan.deep && nf == 0) {
         // cost of a pass by depth, in units of a depth-6 pass; least-cost split by dynamic programming over `left`
-        static const int depths[] = {8, 6, 4, 3, 2, 1};
-        static const double cost[] = {1.17, 1.00, 0.97, 0.96, 0.95, 0.94};
+        static const int depths[] = {12, 8, 6, 4, 3, 2, 1};
+        static const double cost[] = {1.81, 1.09, 1.00, 0.97, 0.96, 0.95, 0.94};
+        const int k0 = plan.cells >= 500000000L ? 0 : 1;
         constexpr int HORIZON = 48;                     // beyond this many steps the split starts with a depth-8 pass anyway
         if (left > HORIZON) return 8;
         double best[HORIZON + 1];
@@ -592,7 +605,7 @@ inline int next_depth(const Plan &plan, int tblock, int left, int nf) {
         best[0] = 0.0; first[0] = 0;
         for (int n = 1; n <= left; ++n) {
             best[n] = 1e30; first[n] = 1;
-            for (int k = 0; k < 6; ++k) {
+            for (int k = k0; k < 7; ++k) {
                 if (depths[k] > n) continue;
                 const double c = cost[k] + best[n - depths[k]];
                 if (c < best[n] - 1e-9) { best[n] = c; first[n] = depths[k]; }
@@ -700,8 +713,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         const int use = 32 * V - 2 * halo;
         mp.nstrips = (q->ny + use - 1) / use;
         const int rows = mp.out_hi - mp.out_lo;
-        int chunk = g_tune.chunk_rows;
-        if (chunk <= 0) chunk = max(plan.chunk, 4 * T);   // at most ~50 % warm-up/drain recompute on shallow grids
+        int chunk = pass_chunk_rows(plan, T, deep);
         chunk = max(1, min(chunk, rows));
         mp.chunk_rows = chunk;
         mp.nchunks = (rows + chunk - 1) / chunk;
@@ -894,7 +906,7 @@ int fdtd2d_plan(const fdtd2d_problem *q, int nsteps, int tblock, int *depths, in
         left -= T;
     }
     if (vector_width) *vector_width = (q->dtype == FDTD_F64 && first == 8) ? 1 : plan.V;
-    if (chunk_rows) *chunk_rows = g_tune.chunk_rows > 0 ? g_tune.chunk_rows : max(plan.chunk, 4 * max(first, 1));
+    if (chunk_rows) *chunk_rows = pass_chunk_rows(plan, max(first, 1), plan.deep && (first == 8 || first == 12));
     return n;
 }
 

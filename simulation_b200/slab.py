@@ -53,8 +53,9 @@ class SlabFdtd2D:
                 from .fd2d import plan_depths
                 thin = partition(self.nx, self.world, self.world - 1)
                 freqs = engine_kw.get("freqs")
-                ghost = plan_depths(self.nx, self.ny, dtype, 1 << 10, 0, rows=thin, lossy=engine_kw.get("nbz") is not None,
-                                    nf=0 if freqs is None else min(len(freqs), 3))[0]
+                # (the deepest pass any split may start with: a long run's first pass, or the single pass of a 12-step run)
+                ghost = max(plan_depths(self.nx, self.ny, dtype, n, 0, rows=thin, lossy=engine_kw.get("nbz") is not None,
+                                        nf=0 if freqs is None else min(len(freqs), 3))[0] for n in (1 << 10, 12))
             else:
                 ghost = 4
         self.ghost = int(ghost)

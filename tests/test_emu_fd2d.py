@@ -342,10 +342,11 @@ def test_emulated_plan_query(emu):
     """fdtd2d_plan is what advance() does: depths by grid size and step count, without launching anything."""
     from simulation_b200 import fd2d
     before = emu.emu_launches()
-    assert fd2d.plan_depths(32768, 32768, np.float32, 20) == [8, 6, 6]                # the driver's bench call: least-cost split
+    assert fd2d.plan_depths(32768, 32768, np.float32, 20) == [12, 8]                  # the driver's bench call: least-cost split
+    assert fd2d.plan_depths(16384, 16384, np.float32, 20) == [8, 6, 6]                # (depth 12 is offered from 500 M cells up)
     assert fd2d.plan_depths(32768, 32768, np.float32, 96) == [8] * 12
-    assert fd2d.plan_depths(32768, 32768, np.float32, 10) == [6, 4]                   # (a depth-8 pass costs 1.3 depth-6 passes)
-    assert fd2d.plan_depths(32768, 32768, np.float32, 96, tblock=12) == [12] * 8      # depth 12 on explicit request only
+    assert fd2d.plan_depths(32768, 32768, np.float32, 10) == [6, 4]                   # (a depth-8 pass costs 1.09 depth-6 passes)
+    assert fd2d.plan_depths(32768, 32768, np.float32, 96, tblock=12) == [12] * 8
     assert fd2d.plan_depths(32768, 32768, np.float32, 96, tblock=6) == [6] * 16
     assert fd2d.plan_depths(32768, 32768, np.float32, 31, tblock=7) == [6] * 5 + [1]
     assert fd2d.plan_depths(32768, 32768, np.float64, 20) == [6, 6, 6, 2]               # float64: register pipeline only
