@@ -227,8 +227,12 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
                 const int sa = (u - s + 2 * NS) % NS, sh = (u - s - 1 + 2 * NS) % NS;
                 march_stage_pk<CV, false, false>(S[sa], S[sh], negzero, nullptr, nullptr);
             }
-            // ---- give the input slot back: every value read from it has been used by the stages above
-            if (!FIRST) mbar_arrive(in_bar + 16u * u + 8u, leader);
+            // ---- give the input slot back: every value read from it has been used by the stages above (the warp-level
+            // barrier orders the other lanes' reads before the leader's arrive)
+            if (!FIRST) {
+                __syncwarp();
+                mbar_arrive(in_bar + 16u * u + 8u, leader);
+            }
             if (FIRST && !SRING) {
                 if (++rs_row == R) {                 // the box is consumed: refill its slot with the box NSTAGE ahead
                     rs_row = 0;
