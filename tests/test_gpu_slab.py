@@ -23,6 +23,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _torchrun(world, args, env, timeout):
+    """torch.distributed.run on a free local port; the port can be taken between the probe and the rendezvous (or sit
+    in TIME_WAIT from the previous case): retry on EADDRINUSE with another one."""
+    for attempt in range(4):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port())] + args
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        if r.returncode == 0 or "EADDRINUSE" not in (r.stdout + r.stderr):
+            return r
+    return r
+
+
 CASES = [
     ("3_2", 1024, 1536, 40, 61, 6, []),
     ("3_3", 900, 1200, 24, 80, 4, []),       # TFSF: every rank replicates the incident line
@@ -53,10 +65,8 @@ def test_slab_equals_single_device(case, halo, world):
     if world in (3, 8) and (halo != "p2p" or case not in STRESS):
         pytest.skip("3 and 8 ranks run the fused-exchange stress cases")
     prog, nx, ny, npml, ns, tblock, extra = CASES[case]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "slab_nccl_worker.py"), prog, str(nx), str(ny), str(npml), str(ns), str(tblock)] + extra
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, FDTD_SLAB_HALO=halo))
+    r = _torchrun(world, [os.path.join(ROOT, "tests", "slab_nccl_worker.py"), prog, str(nx), str(ny), str(npml), str(ns), str(tblock)] + extra,
+                  dict(os.environ, FDTD_SLAB_HALO=halo), 600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "")
 
@@ -65,9 +75,7 @@ def test_missing_neighbour_is_reported_not_hung():
     """One rank skips an advance() call: its neighbour's pass gives up after the (shortened) bound and the host raises."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "slab_nccl_worker.py"), "3_2", "1024", "1536", "40", "24", "6", "6", "skip"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, FDTD_SLAB_HALO="p2p"))
+    r = _torchrun(2, [os.path.join(ROOT, "tests", "slab_nccl_worker.py"), "3_2", "1024", "1536", "40", "24", "6", "6", "skip"],
+                  dict(os.environ, FDTD_SLAB_HALO="p2p"), 300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "gave up waiting" in r.stdout

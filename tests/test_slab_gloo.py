@@ -16,16 +16,24 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _torchrun(world, args, timeout):
+    """torch.distributed.run on a free local port, retried with another port when the rendezvous finds it taken"""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for attempt in range(4):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port())] + args
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        if r.returncode == 0 or "EADDRINUSE" not in (r.stdout + r.stderr):
+            return r
+    return r
+
+
 @pytest.mark.parametrize("world,nx,ny,npml,ns,ghost,dtype", [
     (2, 51, 36, 5, 41, 3, "float64"),       # uneven split, ghost not dividing the step count
     (3, 64, 32, 6, 44, 4, "float32"),       # a middle rank with two neighbours
 ])                                          # (even splits and the per-step exchange: the emulated-engine cases below)
 def test_slab_equals_monolithic(world, nx, ny, npml, ns, ghost, dtype):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "slab_gloo_worker.py"), str(nx), str(ny), str(npml), str(ns), str(ghost), dtype]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    r = _torchrun(world, [os.path.join(ROOT, "tests", "slab_gloo_worker.py"), str(nx), str(ny), str(npml), str(ns), str(ghost), dtype], 300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
 
 
@@ -39,11 +47,7 @@ def test_slab_of_emulated_engines_equals_monolithic(world, nx, ny, npml, ns, gho
     source on the CPU CTA emulator (tests/emu), ghost rows exchanged by slab.py over gloo."""
     from tests.emu import build_emu
     build_emu.build_library()               # once, before the ranks race for the build directory
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "slab_gloo_worker.py"), str(nx), str(ny), str(npml), str(ns), str(ghost), dtype, "emu"]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    r = _torchrun(world, [os.path.join(ROOT, "tests", "slab_gloo_worker.py"), str(nx), str(ny), str(npml), str(ns), str(ghost), dtype, "emu"], 600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
 
 
