@@ -519,10 +519,10 @@ int opt_in_smem(K kernel, size_t smem, size_t (&configured)[64], std::mutex &gua
 }
 
 template <int V, int MODE>
-int launch_careful2_k(const MarchParams<float> &mp, int T, int items, int all_careful, cudaStream_t st) {
+int launch_careful2_k(const MarchParams<float> &mp, int T, int items, int all_careful, cudaStream_t st, int warps_per_cta) {
     if (items <= 0) return FDTD_OK;
     const size_t per_warp = (size_t)CarefulShape<float, V, MODE>::warp_smem(T);
-    int warps = CAREFUL2_WARPS;
+    int warps = (warps_per_cta >= 1 && warps_per_cta <= CAREFUL2_WARPS) ? warps_per_cta : CAREFUL2_WARPS;
     while (warps > 1 && (size_t)warps * per_warp > 220 * 1024) --warps;
     const size_t smem = (size_t)warps * per_warp;
     static size_t configured[64] = {0};
@@ -557,11 +557,12 @@ namespace fdtd_march {
 
 bool deep_supported(int T, bool lossy) { return (T == 8 || T == 12) && !lossy; }
 
-int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int all_careful, cudaStream_t st, int V) {
+int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int all_careful, cudaStream_t st, int V, int warps_per_cta) {
     if (T < 1 || T > TMAX) { fdtd::set_error("careful kernel: depth %d outside [1, %d]", T, TMAX); return FDTD_EINVAL; }
-    if (V == 2) return lossy ? launch_careful2_k<2, 1>(mp, T, items, all_careful, st) : launch_careful2_k<2, 0>(mp, T, items, all_careful, st);
+    const int w = warps_per_cta;
+    if (V == 2) return lossy ? launch_careful2_k<2, 1>(mp, T, items, all_careful, st, w) : launch_careful2_k<2, 0>(mp, T, items, all_careful, st, w);
     if (V != DV) { fdtd::set_error("ring careful kernel: vector width %d (2 or 4)", V); return FDTD_EUNSUPPORTED; }
-    return lossy ? launch_careful2_k<DV, 1>(mp, T, items, all_careful, st) : launch_careful2_k<DV, 0>(mp, T, items, all_careful, st);
+    return lossy ? launch_careful2_k<DV, 1>(mp, T, items, all_careful, st, w) : launch_careful2_k<DV, 0>(mp, T, items, all_careful, st, w);
 }
 
 int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st) {
@@ -583,7 +584,22 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
     };
     // the careful kernel is small (edges only): fork it onto a side stream so the interior kernel backfills the SMs it
     // leaves idle, and join before the next pass
-    SideStream *side = (pc.n_careful > 0 && pc.n_fast > 0 && g_tune.serial == 2) ? side_stream(st) : nullptr;
+    SideStream *side = (pc.n_careful > 0 && pc.n_fast > 0 && g_tune.serial >= 2) ? side_stream(st) : nullptr;
+    if (side != nullptr && g_tune.serial == 3) {
+        // Backfill: the interior kernel goes first and takes every SM (one CTA each: 184 KB of its shared memory); the
+        // careful kernel follows on a default-priority stream with ONE warp per CTA (39 KB at depth 8), so a careful
+        // CTA fits into what an interior CTA leaves of an SM and its instructions ride in the interior's idle issue
+        // slots -- instead of four-warp careful CTAs owning SMs outright for their latency-bound march.
+        FDTD_CUDA(cudaEventRecord(side->fork, st));
+        int rc = launch_interior();
+        if (rc != FDTD_OK) return rc;
+        FDTD_CUDA(cudaStreamWaitEvent(side->backfill, side->fork, 0));
+        rc = launch_careful2(mp, T, lossy, pc.n_careful, 0, side->backfill, DV, 1);
+        if (rc != FDTD_OK) return rc;
+        FDTD_CUDA(cudaEventRecord(side->join, side->backfill));
+        FDTD_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+        return FDTD_OK;
+    }
     if (side == nullptr) {
         int rc = launch_careful2(mp, T, lossy, pc.n_careful, 0, st);
         if (rc != FDTD_OK) return rc;

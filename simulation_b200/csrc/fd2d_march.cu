@@ -381,6 +381,7 @@ SideStream *side_stream(cudaStream_t launch) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&e.side.stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&e.side.backfill, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&e.side.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&e.side.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     e.dev = dev;
@@ -436,7 +437,7 @@ int launch_march_k(MarchParams<real> &mp, cudaStream_t st) {
     const int n_fast = pc.n_fast, n_careful = pc.n_careful;
     // The careful kernel is small (edges only) and would run alone at a fraction of a wave: fork it onto a side
     // stream so the interior kernel backfills the SMs it leaves idle, and join before the next pass.
-    SideStream *side = (n_careful > 0 && n_fast > 0 && g_tune.serial == 2) ? side_stream(st) : nullptr;
+    SideStream *side = (n_careful > 0 && n_fast > 0 && g_tune.serial >= 2) ? side_stream(st) : nullptr;
     // interior warps: one launch, or -- lossy problem with a lossless-outside promise -- two over the same index space
     // (the lossy kernel keeps the warps that meet the box, the lossless kernel the others)
     auto launch_interior = [&]() -> int {
@@ -864,7 +865,7 @@ int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, 
     g_tune.force_v = force_v;
     g_tune.chunk_rows = chunk_rows;
     g_tune.warps = warps_per_cta;
-    g_tune.serial = (ring_depth == 1) ? 1 : 2;     // (slot reused) 1 = serialise the edge and interior kernels
+    g_tune.serial = (ring_depth == 1) ? 1 : (ring_depth == 3 ? 3 : 2);     // (slot reused) 1 = serialise the edge and interior kernels, 3 = edge kernel backfills
     g_tune.careful = force_careful & 1;            // bit 0: every warp through the careful kernel
     g_tune.split = (force_careful & 2) ? 0 : 1;    // bit 1: ignore the lossless-outside promise
     return FDTD_OK;

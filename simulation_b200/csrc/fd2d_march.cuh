@@ -537,7 +537,8 @@ __device__ __forceinline__ void push_row(const MarchParams<real> &p, const long 
 struct Tuning {
     int force_v = 0, chunk_rows = 0, warps = 0, careful = 0;
     int split = 1;               // 0 = ignore the lossless-outside promise (tests: the lossy kernel everywhere)
-    int serial = 2;              // 2 = fork the edge kernel onto a side stream (measured +2 %); 1 = edge then interior in order
+    int serial = 2;              // 2 = fork the edge kernel onto a side stream (measured +2 %); 1 = edge then interior in order;
+                                 // 3 (deep passes) = interior first, the edge kernel backfills at one warp per CTA
     int variant = 0;             // kernel-shape experiments of the deep passes (0 = the shipped shape)
     int deep = 1;                // 0 = never use the deep passes of fd2d_deep.cu; 2 = the smem-resident careful kernel at every depth
     int edge_chunks = 1;         // 1 = short first / last chunk around the rows that need the careful kernel; 0 = uniform chunks
@@ -545,7 +546,7 @@ struct Tuning {
 };
 extern Tuning g_tune;
 
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; cudaStream_t backfill; };   // backfill: default priority
 // one high-priority side stream + fork/join events per (device, launch stream), created on first use
 SideStream *side_stream(cudaStream_t launch);
 
@@ -627,7 +628,7 @@ PassCounts classify_pass(MarchParams<real> &mp, const int V, const int T) {
 bool deep_supported(int T, bool lossy);
 int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st);
 // the shared-memory-resident careful kernel (any depth <= TMAX), used by the deep passes
-int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int all_careful, cudaStream_t st, int V = 4);
+int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int all_careful, cudaStream_t st, int V = 4, int warps_per_cta = 0);
 void preload_deep(bool lossy);
 // warp-chain passes (fd2d_chain.cu): the interior items of a depth-8 / depth-12 pass as a TMA-fed pipeline of warps
 bool chain_supported(int T, bool lossy);
