@@ -353,7 +353,7 @@ def run_ours(args, emit=print):
     knobs = ("FDTD_FORCE_V", "FDTD_CHUNK_ROWS", "FDTD_WARPS", "FDTD_RING", "FDTD_CAREFUL")
     if any(k in os.environ for k in knobs):                                                 # tuning sweeps only
         _lib.lib().fdtd2d_tune(*[int(os.environ.get(k, "0")) for k in knobs])
-    for key, env in ((_lib.TUNE_DEEP, "FDTD_DEEP"), (_lib.TUNE_VARIANT, "FDTD_VARIANT"), (_lib.TUNE_EDGE_CHUNKS, "FDTD_EDGE_CHUNKS")):
+    for key, env in ((_lib.TUNE_DEEP, "FDTD_DEEP"), (_lib.TUNE_VARIANT, "FDTD_VARIANT"), (_lib.TUNE_EDGE_CHUNKS, "FDTD_EDGE_CHUNKS"), (_lib.TUNE_COL_FAST, "FDTD_COL_FAST")):
         if env in os.environ:
             _lib.lib().fdtd2d_tune2(key, int(os.environ[env]))
     barrier = dist.barrier if world > 1 else (lambda: None)

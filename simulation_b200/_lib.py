@@ -111,7 +111,7 @@ SYMBOLS = {
     "fdtd2d_incident_line": (_I, [C.POINTER(Problem2D), _I, C.POINTER(_D), _P, _P, _P]),
     "fdtd2d_halo_status": (_I, [C.POINTER(Problem2D), C.POINTER(C.c_ulonglong)]),
 }
-TUNE_DEEP, TUNE_HALO_WAIT_MS, TUNE_VARIANT, TUNE_EDGE_CHUNKS = 0, 1, 2, 3
+TUNE_DEEP, TUNE_HALO_WAIT_MS, TUNE_VARIANT, TUNE_EDGE_CHUNKS, TUNE_COL_FAST = 0, 1, 2, 3, 4
 
 _lib = None
 

@@ -138,11 +138,72 @@ __device__ __forceinline__ void sts22(void *dst, const float (&d)[CV]) {
     }
 }
 
+// Column coefficients of a lane for the column variant: the five y-vectors of the PML at its four columns (identity
+// outside the grid), gy2 already halved (gy2 * 0.5 is what the careful stage multiplies the curl by: (gx2*gy2)*0.5 with
+// gx2 = 1), and the two cells whose update is masked: D of column 0 and H of column ny-1.
+struct ColLane {
+    float gy2h[CV], gy3[CV], fy1[CV], fy2[CV], fy3[CV];
+    bool fix_d, fix_h;             // this lane owns column 0 (as its v = 0) / column ny-1 (as its v = CV-1)
+};
+
+// One stage on a strip whose COLUMNS carry PML coefficients while its rows are ordinary (gx2 = gx3 = fx2 = fx3 = 1,
+// fx1 = 0): operation for operation march_stage<float, 4, 0, false> with the row coefficients at those values --
+//   dz = (gy3*dz) + ((gy2*0.5)*curl);  ez = naz*dz
+//   ihx += cm; ihy += cn;  hx = (fy3*hx) + (fy2*((0.5*cm) + (0*ihx)));  hy = hy - ((0.5*cn) + (fy1*ihy))
+// -- in packed arithmetic.  Multiplications by a row coefficient that is exactly 1 are dropped (exact), 0*ihx is kept (it
+// decides the sign of a zero sum).  The two masked cells are computed like the others and put back afterwards.
+__device__ __forceinline__ void march_stage_pk_col(RowSet<float, CV> &A, RowSet<float, CV> &Hd, const ColLane &c, const float2 negzero) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const float2 half2 = make_float2(0.5f, 0.5f), zero2 = make_float2(0.f, 0.f);
+    // ---- D of the arriving row
+    const float keep_dz = A.dz[0];
+    const float hx_left = __shfl_up_sync(FULL, A.hx[CV - 1], 1);
+#pragma unroll
+    for (int v = 0; v < CV; v += 2) {
+        const float2 a1 = pk_sub(make_float2(A.hy[v], A.hy[v + 1]), make_float2(Hd.hy[v], Hd.hy[v + 1]));
+        const float2 a2 = pk_sub(a1, make_float2(A.hx[v], A.hx[v + 1]));
+        const float2 curl = make_float2(a2.x + (v == 0 ? hx_left : A.hx[v == 0 ? 0 : v - 1]), a2.y + A.hx[v]);   // shifted pair: scalar
+        const float2 dn = pk_add(pk_mul(make_float2(c.gy3[v], c.gy3[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero),
+                                 pk_mul(make_float2(c.gy2h[v], c.gy2h[v + 1]), curl, negzero));
+        A.dz[v] = dn.x; A.dz[v + 1] = dn.y;
+    }
+    if (c.fix_d) A.dz[0] = keep_dz;                   // column 0 has no D update
+    // ---- E of the arriving row; the held row's Ez comes from its own trip
+    float ezA[CV], ezH[CV];
+#pragma unroll
+    for (int v = 0; v < CV; v += 2) {
+        const float2 a = pk_mul(make_float2(A.naz[v], A.naz[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
+        A.ez[v] = a.x; A.ez[v + 1] = a.y;
+        ezA[v] = a.x; ezA[v + 1] = a.y; ezH[v] = Hd.ez[v]; ezH[v + 1] = Hd.ez[v + 1];
+    }
+    // ---- H of the held row
+    const float k_ihx = Hd.ihx[CV - 1], k_ihy = Hd.ihy[CV - 1], k_hx = Hd.hx[CV - 1], k_hy = Hd.hy[CV - 1];
+    const float ez_right = __shfl_down_sync(FULL, ezH[0], 1);
+#pragma unroll
+    for (int v = 0; v < CV; v += 2) {
+        const float2 e = make_float2(ezH[v], ezH[v + 1]);
+        const float2 cm = make_float2(ezH[v] - ezH[v + 1], ezH[v + 1] - (v + 2 < CV ? ezH[v + 2 < CV ? v + 2 : v] : ez_right));   // shifted pair: scalar
+        const float2 cn = pk_sub(e, make_float2(ezA[v], ezA[v + 1]));
+        const float2 sx = pk_add(make_float2(Hd.ihx[v], Hd.ihx[v + 1]), cm);
+        const float2 sy = pk_add(make_float2(Hd.ihy[v], Hd.ihy[v + 1]), cn);
+        const float2 tx = pk_add(pk_mul(half2, cm, negzero), pk_mul(zero2, sx, negzero));
+        const float2 ty = pk_add(pk_mul(half2, cn, negzero), pk_mul(make_float2(c.fy1[v], c.fy1[v + 1]), sy, negzero));
+        const float2 hx2 = pk_add(pk_mul(make_float2(c.fy3[v], c.fy3[v + 1]), make_float2(Hd.hx[v], Hd.hx[v + 1]), negzero),
+                                  pk_mul(make_float2(c.fy2[v], c.fy2[v + 1]), tx, negzero));
+        const float2 hy2 = pk_sub(make_float2(Hd.hy[v], Hd.hy[v + 1]), ty);
+        Hd.ihx[v] = sx.x; Hd.ihx[v + 1] = sx.y; Hd.ihy[v] = sy.x; Hd.ihy[v + 1] = sy.y;
+        Hd.hx[v] = hx2.x; Hd.hx[v + 1] = hx2.y; Hd.hy[v] = hy2.x; Hd.hy[v + 1] = hy2.y;
+    }
+    if (c.fix_h) {                                    // column ny-1 has no H update
+        Hd.ihx[CV - 1] = k_ihx; Hd.ihy[CV - 1] = k_ihy; Hd.hx[CV - 1] = k_hx; Hd.hy[CV - 1] = k_hy;
+    }
+}
+
 // One warp of the chain.  FIRST: input from the TMA staging ring; else from the queue behind it.  LAST: output to global
 // memory; else into the queue ahead.  Every warp runs the same number of trips: a warp hands on EVERY row that leaves
 // its last stage, the all-zero sets of the first K sub-iterations included (zero rows stay zero through a stage), so
 // the x-th input of warp g is global row r_begin + x - g*K and nothing in the loop depends on the warp's position.
-template <typename Shape, bool FIRST, bool LAST>
+template <typename Shape, bool FIRST, bool LAST, bool COL>
 __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const ChainMaps &maps, const int strip, const int i0,
                                            const int i1, const int lane, const int wg, unsigned char *const gsm) {
     constexpr int K = Shape::K, NSTAGE = Shape::NSTAGE;
@@ -153,7 +214,25 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
 
     const int c0 = strip * USE - HALO;               // first column of the strip (halo included)
     const int jb = c0 + lane * CV;                   // first column of this lane
-    const bool col_store = (lane * CV >= HALO) && (lane * CV + CV <= W - HALO);
+    const bool col_in = !COL || (jb >= 0 && jb + CV <= p.ny);     // (ordinary strips lie inside the grid)
+    const bool col_store = col_in && (lane * CV >= HALO) && (lane * CV + CV <= W - HALO);
+    ColLane cl;
+    if (COL) {
+#pragma unroll
+        for (int v = 0; v < CV; ++v) { cl.gy2h[v] = 0.5f; cl.gy3[v] = cl.fy2[v] = cl.fy3[v] = 1.f; cl.fy1[v] = 0.f; }
+        if (col_in) {
+            float g2[CV];
+            VecIO<float, CV>::ld(p.gy2 + jb, g2);
+            VecIO<float, CV>::ld(p.gy3 + jb, cl.gy3);
+            VecIO<float, CV>::ld(p.fy1 + jb, cl.fy1);
+            VecIO<float, CV>::ld(p.fy2 + jb, cl.fy2);
+            VecIO<float, CV>::ld(p.fy3 + jb, cl.fy3);
+#pragma unroll
+            for (int v = 0; v < CV; ++v) cl.gy2h[v] = g2[v] * 0.5f;        // (gx2 * gy2) * 0.5 with gx2 = 1
+        }
+        cl.fix_d = jb == 0;
+        cl.fix_h = jb + CV == p.ny;
+    }
     const int r_begin = i0 - T, r_end = i1 + T;      // rows fed to stage 0: [r_begin, r_end)
     const int n_trip = (r_end - r_begin + NS - 1) / NS;   // trips of NS rows (the last one may run past r_end: never stored)
     const int leader = lane == 0;
@@ -225,7 +304,8 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
 #pragma unroll
             for (int s = 0; s < K; ++s) {
                 const int sa = (u - s + 2 * NS) % NS, sh = (u - s - 1 + 2 * NS) % NS;
-                march_stage_pk<CV, false, false>(S[sa], S[sh], negzero, nullptr, nullptr);
+                if (COL) march_stage_pk_col(S[sa], S[sh], cl, negzero);
+                else march_stage_pk<CV, false, false>(S[sa], S[sh], negzero, nullptr, nullptr);
             }
             // ---- give the input slot back: every value read from it has been used by the stages above (the warp-level
             // barrier orders the other lanes' reads before the leader's arrive)
@@ -278,7 +358,16 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
     }
 }
 
-template <typename Shape>
+// (special strip, ordinary chunk) item w of the column variant
+__device__ __forceinline__ bool decode_col_item(const MarchParams<float> &p, const int w, int &strip, int &i0, int &i1) {
+    const int ncf = p.nchunks - p.n_schunks;
+    if (w >= p.n_sstrips * ncf) return false;
+    strip = p.sstrips[w % p.n_sstrips];
+    chunk_span(p, kth_not_in(w / p.n_sstrips, p.schunks, p.n_schunks), i0, i1);
+    return true;
+}
+
+template <typename Shape, bool COL>
 __global__ void __launch_bounds__(Shape::THREADS, 1)
 k_march_chain(const __grid_constant__ MarchParams<float> p, const __grid_constant__ ChainMaps maps) {
     extern __shared__ __align__(1024) unsigned char chain_smem[];
@@ -293,10 +382,11 @@ k_march_chain(const __grid_constant__ MarchParams<float> p, const __grid_constan
     }
     __syncthreads();
     int strip, i0, i1;
-    if (!decode_item<true>(p, blockIdx.x * Shape::GROUPS + grp, 0, CV, Shape::T, false, strip, i0, i1)) return;   // the whole group
-    if (wg == 0) chain_body<Shape, true, false>(p, maps, strip, i0, i1, lane, wg, gsm);
-    else if (wg == Shape::G - 1) chain_body<Shape, false, true>(p, maps, strip, i0, i1, lane, wg, gsm);
-    else chain_body<Shape, false, false>(p, maps, strip, i0, i1, lane, wg, gsm);
+    const int item = blockIdx.x * Shape::GROUPS + grp;
+    if (COL ? !decode_col_item(p, item, strip, i0, i1) : !decode_item<true>(p, item, 0, CV, Shape::T, false, strip, i0, i1)) return;   // the whole group
+    if (wg == 0) chain_body<Shape, true, false, COL>(p, maps, strip, i0, i1, lane, wg, gsm);
+    else if (wg == Shape::G - 1) chain_body<Shape, false, true, COL>(p, maps, strip, i0, i1, lane, wg, gsm);
+    else chain_body<Shape, false, false, COL>(p, maps, strip, i0, i1, lane, wg, gsm);
 }
 
 // ---- host: tensor maps
@@ -330,7 +420,7 @@ int make_map(CUtensorMap *m, const float *base, int ny, int rows, int box_rows) 
     return FDTD_OK;
 }
 
-template <typename Shape>
+template <typename Shape, bool COL = false>
 int launch_chain(const MarchParams<float> &mp, int items, cudaStream_t st) {
     if (items <= 0) return FDTD_OK;
     ChainMaps maps;
@@ -348,12 +438,12 @@ int launch_chain(const MarchParams<float> &mp, int items, cudaStream_t st) {
         FDTD_CUDA(cudaGetDevice(&dev));
         bool &done = configured[dev >= 0 && dev < 64 ? dev : 0];
         if (!done || dev >= 64) {
-            FDTD_CUDA(cudaFuncSetAttribute(k_march_chain<Shape>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape::SMEM));
+            FDTD_CUDA(cudaFuncSetAttribute(k_march_chain<Shape, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape::SMEM));
             done = true;
         }
     }
     const int grid = (items + Shape::GROUPS - 1) / Shape::GROUPS;
-    k_march_chain<Shape><<<grid, Shape::THREADS, Shape::SMEM, st>>>(mp, maps);
+    k_march_chain<Shape, COL><<<grid, Shape::THREADS, Shape::SMEM, st>>>(mp, maps);
     FDTD_LAUNCH_CHECK("k_march_chain");
     return FDTD_OK;
 }
@@ -375,10 +465,14 @@ bool chain_supported(int T, bool lossy) {
     return (T == 8 || T == 12) && !lossy && encoder() != nullptr;
 }
 
-int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items, cudaStream_t st) {
+int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items, cudaStream_t st, bool column_items) {
     if (mp.ny % CV != 0 || (reinterpret_cast<uintptr_t>(mp.in_dz) & 15u) != 0) {
         fdtd::set_error("warp-chain pass: ny must be a multiple of 4 and the arrays 16-byte aligned");
         return FDTD_EINVAL;
+    }
+    if (column_items) {          // (special strip, ordinary chunk) items: the shipped shape with the column-coefficient stage
+        if (T == 8) return launch_chain<Chain8, true>(mp, items, st);
+        if (T == 12) return launch_chain<Chain12, true>(mp, items, st);
     }
     if (T == 8) {
         if (shape == 1) return launch_chain<Chain8b>(mp, items, st);
@@ -397,8 +491,10 @@ int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items
 
 void preload_chain() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, k_march_chain<Chain8>);
-    cudaFuncGetAttributes(&a, k_march_chain<Chain12>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain8, false>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain12, false>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain8, true>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain12, true>);
 }
 
 }  // namespace fdtd_march

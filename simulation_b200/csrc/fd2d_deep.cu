@@ -567,6 +567,9 @@ int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int al
 
 int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st) {
     if (!deep_supported(T, lossy)) { fdtd::set_error("no deep pass of depth %d%s", T, lossy ? " (lossy)" : ""); return FDTD_EUNSUPPORTED; }
+    const bool chain = (g_tune.variant == 0 || g_tune.variant >= 10) && chain_supported(T, lossy);
+    // PML-column strips x ordinary chunks at interior speed (classify_pass withdraws it where it cannot apply)
+    mp.col_fast = chain && g_tune.col_fast && !mp.tfsf ? 1 : 0;
     const PassCounts pc = classify_pass(mp, DV, T);
     if (pc.all_careful) return launch_careful2(mp, T, lossy, pc.n_careful, 1, st);
     auto launch_interior = [&]() -> int {
@@ -574,7 +577,7 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
         // depths; variants 1..3 select the shared-memory-accumulator kernels of this file (also the fallback when the
         // driver has no tensor-map encoder), variants >= 10 the other chain shapes
         const int v = g_tune.variant;
-        if ((v == 0 || v >= 10) && chain_supported(T, lossy)) return launch_march_chain(mp, T, v >= 10 ? v - 10 : 0, pc.n_fast, st);
+        if (chain) return launch_march_chain(mp, T, v >= 10 ? v - 10 : 0, pc.n_fast, st);
         if (T == 12) return launch_deep_interior<12, false, 2, 8, 0>(mp, pc.n_fast, st);
         switch (v) {
             case 1: return launch_deep_interior<8, false, 3, 8, 0>(mp, pc.n_fast, st);
@@ -596,6 +599,10 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
         FDTD_CUDA(cudaStreamWaitEvent(side->backfill, side->fork, 0));
         rc = launch_careful2(mp, T, lossy, pc.n_careful, 0, side->backfill, DV, 1);
         if (rc != FDTD_OK) return rc;
+        if (pc.n_col > 0) {
+            rc = launch_march_chain(mp, T, 0, pc.n_col, side->backfill, true);
+            if (rc != FDTD_OK) return rc;
+        }
         FDTD_CUDA(cudaEventRecord(side->join, side->backfill));
         FDTD_CUDA(cudaStreamWaitEvent(st, side->join, 0));
         return FDTD_OK;
@@ -603,12 +610,20 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
     if (side == nullptr) {
         int rc = launch_careful2(mp, T, lossy, pc.n_careful, 0, st);
         if (rc != FDTD_OK) return rc;
+        if (pc.n_col > 0) {
+            rc = launch_march_chain(mp, T, 0, pc.n_col, st, true);
+            if (rc != FDTD_OK) return rc;
+        }
         return launch_interior();
     }
     FDTD_CUDA(cudaEventRecord(side->fork, st));
     FDTD_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
     int rc = launch_careful2(mp, T, lossy, pc.n_careful, 0, side->stream);
     if (rc != FDTD_OK) return rc;
+    if (pc.n_col > 0) {
+        rc = launch_march_chain(mp, T, 0, pc.n_col, side->stream, true);
+        if (rc != FDTD_OK) return rc;
+    }
     FDTD_CUDA(cudaEventRecord(side->join, side->stream));
     rc = launch_interior();
     if (rc != FDTD_OK) return rc;

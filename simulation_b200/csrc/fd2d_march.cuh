@@ -31,6 +31,11 @@ struct MarchParams {
     // is ordinary chunks of chunk_rows -- see chunk_span.
     int first_rows, last_rows;
     int cchunk_rows, ncchunks;                 // row partition of the SPECIAL strips (careful kernel): finer on small launches
+    // col_fast: the special strips are special only for their COLUMNS (PML y-coefficients, the grid's first / last
+    // column).  Where such a strip crosses an ordinary chunk every row is ordinary, so those items go to the column
+    // variant of the warp-chain kernel (fd2d_chain.cu) and the careful kernel keeps the special strips only inside the
+    // special chunks.
+    int col_fast;
     int tfsf, npml;
     const real *ezi_hist, *hxi_hist;           // [T][ny], [T][2]
     int src_i, src_j, src_hard;                // point source on dz (src_i < 0: none)
@@ -430,11 +435,16 @@ __device__ __forceinline__ bool decode_item(const MarchParams<real> &p, const in
         strip = w % p.nstrips;
         chunk = w / p.nstrips;
     } else {
-        const int na = p.n_sstrips * p.ncchunks;        // special strips: all rows, in their own (finer) row partition
+        // special strips: all rows, in their own (finer) row partition -- or, with col_fast, the special chunks only
+        const int na = p.n_sstrips * (p.col_fast ? p.n_schunks : p.ncchunks);
         if (w < na) {
             strip = p.sstrips[w % p.n_sstrips];
-            chunk = w / p.n_sstrips;
-            own_partition = true;
+            if (p.col_fast) {
+                chunk = p.schunks[w / p.n_sstrips];
+            } else {
+                chunk = w / p.n_sstrips;
+                own_partition = true;
+            }
         } else {
             const int x = w - na, nb = nsf * p.n_schunks;
             if (x < nb) {
@@ -542,6 +552,7 @@ struct Tuning {
     int variant = 0;             // kernel-shape experiments of the deep passes (0 = the shipped shape)
     int deep = 1;                // 0 = never use the deep passes of fd2d_deep.cu; 2 = the smem-resident careful kernel at every depth
     int edge_chunks = 1;         // 1 = short first / last chunk around the rows that need the careful kernel; 0 = uniform chunks
+    int col_fast = 1;            // 1 = PML-column strips x ordinary chunks through the warp-chain kernel's column variant
     unsigned long long spin_ns = HALO_SPIN_NS;
 };
 extern Tuning g_tune;
@@ -550,7 +561,7 @@ struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; cudaStream_t ba
 // one high-priority side stream + fork/join events per (device, launch stream), created on first use
 SideStream *side_stream(cudaStream_t launch);
 
-struct PassCounts { bool all_careful; int n_fast, n_careful; };
+struct PassCounts { bool all_careful; int n_fast, n_careful, n_col; };   // n_col: (special strip, ordinary chunk) items of col_fast
 
 // Classify strips and chunks on the host (same conditions as the kernels rely on): fills the special lists, the single
 // source cells, the careful row partition and total_warps of `mp` for a pass of vector width V and depth T.
@@ -606,7 +617,8 @@ PassCounts classify_pass(MarchParams<real> &mp, const int V, const int T) {
         mp.n_sstrips = mp.n_schunks = 0;
         mp.cchunk_rows = mp.chunk_rows; mp.ncchunks = mp.nchunks;
         mp.total_warps = (unsigned)(mp.nstrips * mp.nchunks);
-        out.all_careful = true; out.n_fast = 0; out.n_careful = mp.nstrips * mp.nchunks;
+        out.all_careful = true; out.n_fast = 0; out.n_careful = mp.nstrips * mp.nchunks; out.n_col = 0;
+        mp.col_fast = 0;
         return out;
     }
     mp.n_sstrips = ns; mp.n_schunks = nc;
@@ -619,7 +631,16 @@ PassCounts classify_pass(MarchParams<real> &mp, const int V, const int T) {
     const bool small_launch = n_fast < 16 * MAX_WARPS * fdtd::sm_count();
     mp.cchunk_rows = small_launch ? max(1, min(mp.chunk_rows, max(4 * T, 32))) : mp.chunk_rows;
     mp.ncchunks = (rows + mp.cchunk_rows - 1) / mp.cchunk_rows;
-    out.all_careful = false; out.n_fast = n_fast; out.n_careful = ns * mp.ncchunks + nsf * nc + np;
+    // col_fast needs a source cell outside the special strips (their items carry no source code)
+    if (mp.col_fast && mp.src_i >= 0)
+        for (int q = 0; q < ns; ++q) {
+            const int c0 = mp.sstrips[q] * USE - HALO;
+            if (mp.src_j >= c0 && mp.src_j < c0 + W) mp.col_fast = 0;
+        }
+    if (ns == 0 || ncf == 0) mp.col_fast = 0;
+    out.all_careful = false; out.n_fast = n_fast;
+    out.n_col = mp.col_fast ? ns * ncf : 0;
+    out.n_careful = (mp.col_fast ? ns * nc : ns * mp.ncchunks) + nsf * nc + np;
     mp.total_warps = (unsigned)out.n_careful;
     return out;
 }
@@ -632,7 +653,7 @@ int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int al
 void preload_deep(bool lossy);
 // warp-chain passes (fd2d_chain.cu): the interior items of a depth-8 / depth-12 pass as a TMA-fed pipeline of warps
 bool chain_supported(int T, bool lossy);
-int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items, cudaStream_t st);
+int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items, cudaStream_t st, bool column_items = false);
 void preload_chain();
 
 }  // namespace fdtd_march
