@@ -185,9 +185,9 @@ def test_emulated_streamed_run(emu, plan, ns, schedule):
     assert b.t == ns and float(host_ez.abs().max()) > 1e-3
 
 
-@pytest.mark.parametrize("prog,plan,ns,tblock", [("3_3", 4, 41, None), ("3_4", [40, 90, 130], 33, None), ("3_3", 3, 29, 8),
-                                                 ("3_4", 2, 50, 4)])
-@pytest.mark.parametrize("schedule", ["skewed", "wavefront"])
+@pytest.mark.parametrize("prog,plan,ns,tblock,schedule", [("3_3", 4, 41, None, "skewed"), ("3_4", [40, 90, 130], 33, None, "skewed"),
+                                                          ("3_4", [40, 90, 130], 33, None, "wavefront"), ("3_3", 3, 29, 8, "skewed"),
+                                                          ("3_3", 3, 29, 8, "wavefront"), ("3_4", 2, 50, 4, "skewed")])
 def test_emulated_streamed_run_tfsf_and_lossy(emu, prog, plan, ns, tblock, schedule):
     """run_streamed with a TFSF plane wave (the incident line advanced once per pass level up front, every block's pass
     reading that level's history) and with the lossy cylinder of program 3_4 (nbz streamed beside naz; iz carried):
