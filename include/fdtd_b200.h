@@ -280,7 +280,7 @@ int fdtd2d_tune(int force_v, int chunk_rows, int warps_per_cta, int ring_depth, 
 #define FDTD_TUNE_DEEP 0
 #define FDTD_TUNE_HALO_WAIT_MS 1
 #define FDTD_TUNE_VARIANT 2
-#define FDTD_TUNE_COL_FAST 4         /* 1 (default) = PML-column strips of a deep pass through the warp-chain kernel's column variant; 0 = edge kernel */
+#define FDTD_TUNE_COL_FAST 4         /* bit 0: PML-column strips, bit 1: PML-row chunks of a deep pass through the warp-chain kernel's column / row variant (default 3); 0 = edge kernel */
 #define FDTD_TUNE_EDGE_CHUNKS 3      /* 1 (default) = short first / last row chunk around the rows that need the edge kernel; 0 = uniform */
 int fdtd2d_tune2(int key, long long value);
 

@@ -45,7 +45,8 @@ constexpr int CLB = CV * 4;           // bytes per lane per array row
 constexpr int CROWB = 32 * CLB;       // bytes per array row of a warp (128 columns)
 constexpr int NARR = 6;               // arrays that travel with a row: dz hx hy ihx ihy naz (ez is recomputed on arrival)
 
-struct ChainMaps { CUtensorMap m[NARR]; };   // in_dz in_hx in_hy in_ihx in_ihy naz: (rows, ny) float, box R x 128
+struct ChainMaps { CUtensorMap m[NARR]; };
+enum { K_INTERIOR = 0, K_COL = 1, K_ROW = 2 };   // what a launch's items are: interior, (special strip, ordinary chunk), (ordinary strip, special chunk)   // in_dz in_hx in_hy in_ihx in_ihy naz: (rows, ny) float, box R x 128
 
 template <int G_, int K_, int GROUPS_, int R_ = K_ + 1, int NSTAGE_ = 2, bool STS_PTX_ = false>
 struct ChainShape {
@@ -199,11 +200,70 @@ __device__ __forceinline__ void march_stage_pk_col(RowSet<float, CV> &A, RowSet<
     }
 }
 
+// One stage on a chunk whose ROWS carry PML coefficients (or are the grid's first / last rows) while its columns are
+// ordinary (gy2 = gy3 = fy2 = fy3 = 1, fy1 = 0): operation for operation march_stage<float, 4, 0, false> with the column
+// coefficients at those values --
+//   dz = (gx3*dz) + ((gx2*0.5)*curl)   where 1 <= rs < nx;   ez = naz*dz
+//   ihx += cm; ihy += cn;  hx = hx + ((0.5*cm) + (fx1*ihx));  hy = (fx3*hy) - (fx2*((0.5*cn) + (0*ihy)))   where 0 <= hr <= nx-2
+// -- in packed arithmetic; the row coefficients and the two row masks are warp-uniform.  rs: global row of the arriving
+// row (the held row is rs - 1); rows outside the stored rows arrive as zeros (the tensor map fills them), exactly what
+// the careful kernel's zero-filling fetch gives.
+__device__ __forceinline__ void march_stage_pk_row(const MarchParams<float> &p, RowSet<float, CV> &A, RowSet<float, CV> &Hd,
+                                                   const int rs, const float2 negzero) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const float2 half2 = make_float2(0.5f, 0.5f), zero2 = make_float2(0.f, 0.f);
+    const int hr = rs - 1;
+    const int rd = min(max(rs, 0), p.nx - 1), rh = min(max(hr, 0), p.nx - 1);
+    const float gx2h = __ldg(p.gx2 + rd) * 0.5f, gx3 = __ldg(p.gx3 + rd);       // (gx2 * gy2) * 0.5 with gy2 = 1
+    const float fx1 = __ldg(p.fx1 + rh), fx2 = __ldg(p.fx2 + rh), fx3 = __ldg(p.fx3 + rh);
+    const bool drow = rs >= 1 && rs < p.nx, hrow = hr >= 0 && hr <= p.nx - 2;
+    // ---- D of the arriving row
+    const float hx_left = __shfl_up_sync(FULL, A.hx[CV - 1], 1);
+    if (drow) {
+        const float2 g3 = make_float2(gx3, gx3), g2 = make_float2(gx2h, gx2h);
+#pragma unroll
+        for (int v = 0; v < CV; v += 2) {
+            const float2 a1 = pk_sub(make_float2(A.hy[v], A.hy[v + 1]), make_float2(Hd.hy[v], Hd.hy[v + 1]));
+            const float2 a2 = pk_sub(a1, make_float2(A.hx[v], A.hx[v + 1]));
+            const float2 curl = make_float2(a2.x + (v == 0 ? hx_left : A.hx[v == 0 ? 0 : v - 1]), a2.y + A.hx[v]);   // shifted pair: scalar
+            const float2 dn = pk_add(pk_mul(g3, make_float2(A.dz[v], A.dz[v + 1]), negzero), pk_mul(g2, curl, negzero));
+            A.dz[v] = dn.x; A.dz[v + 1] = dn.y;
+        }
+    }
+    // ---- E of the arriving row; the held row's Ez comes from its own trip
+    float ezA[CV], ezH[CV];
+#pragma unroll
+    for (int v = 0; v < CV; v += 2) {
+        const float2 a = pk_mul(make_float2(A.naz[v], A.naz[v + 1]), make_float2(A.dz[v], A.dz[v + 1]), negzero);
+        A.ez[v] = a.x; A.ez[v + 1] = a.y;
+        ezA[v] = a.x; ezA[v + 1] = a.y; ezH[v] = Hd.ez[v]; ezH[v + 1] = Hd.ez[v + 1];
+    }
+    // ---- H of the held row
+    const float ez_right = __shfl_down_sync(FULL, ezH[0], 1);
+    if (hrow) {
+        const float2 f1 = make_float2(fx1, fx1), f2 = make_float2(fx2, fx2), f3 = make_float2(fx3, fx3);
+#pragma unroll
+        for (int v = 0; v < CV; v += 2) {
+            const float2 e = make_float2(ezH[v], ezH[v + 1]);
+            const float2 cm = make_float2(ezH[v] - ezH[v + 1], ezH[v + 1] - (v + 2 < CV ? ezH[v + 2 < CV ? v + 2 : v] : ez_right));   // shifted pair: scalar
+            const float2 cn = pk_sub(e, make_float2(ezA[v], ezA[v + 1]));
+            const float2 sx = pk_add(make_float2(Hd.ihx[v], Hd.ihx[v + 1]), cm);
+            const float2 sy = pk_add(make_float2(Hd.ihy[v], Hd.ihy[v + 1]), cn);
+            const float2 tx = pk_add(pk_mul(half2, cm, negzero), pk_mul(f1, sx, negzero));
+            const float2 ty = pk_add(pk_mul(half2, cn, negzero), pk_mul(zero2, sy, negzero));
+            const float2 hx2 = pk_add(make_float2(Hd.hx[v], Hd.hx[v + 1]), tx);
+            const float2 hy2 = pk_sub(pk_mul(f3, make_float2(Hd.hy[v], Hd.hy[v + 1]), negzero), pk_mul(f2, ty, negzero));
+            Hd.ihx[v] = sx.x; Hd.ihx[v + 1] = sx.y; Hd.ihy[v] = sy.x; Hd.ihy[v + 1] = sy.y;
+            Hd.hx[v] = hx2.x; Hd.hx[v + 1] = hx2.y; Hd.hy[v] = hy2.x; Hd.hy[v + 1] = hy2.y;
+        }
+    }
+}
+
 // One warp of the chain.  FIRST: input from the TMA staging ring; else from the queue behind it.  LAST: output to global
 // memory; else into the queue ahead.  Every warp runs the same number of trips: a warp hands on EVERY row that leaves
 // its last stage, the all-zero sets of the first K sub-iterations included (zero rows stay zero through a stage), so
 // the x-th input of warp g is global row r_begin + x - g*K and nothing in the loop depends on the warp's position.
-template <typename Shape, bool FIRST, bool LAST, bool COL>
+template <typename Shape, bool FIRST, bool LAST, int KIND>
 __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const ChainMaps &maps, const int strip, const int i0,
                                            const int i1, const int lane, const int wg, unsigned char *const gsm) {
     constexpr int K = Shape::K, NSTAGE = Shape::NSTAGE;
@@ -214,6 +274,7 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
 
     const int c0 = strip * USE - HALO;               // first column of the strip (halo included)
     const int jb = c0 + lane * CV;                   // first column of this lane
+    constexpr bool COL = KIND == K_COL, ROW = KIND == K_ROW;
     const bool col_in = !COL || (jb >= 0 && jb + CV <= p.ny);     // (ordinary strips lie inside the grid)
     const bool col_store = col_in && (lane * CV >= HALO) && (lane * CV + CV <= W - HALO);
     ColLane cl;
@@ -279,6 +340,7 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
 #pragma unroll 1
     for (int trip = 0; trip < n_trip; ++trip) {
         const unsigned par = (unsigned)trip & 1u;    // queue barriers complete one phase per trip
+        const int row_in = r_begin + trip * NS - wg * K;     // global row of this warp's input at u = 0 (row variant)
         const int sslot = trip & 1;                  // staging slot of this trip's box; its barrier's parity is (trip >> 1) & 1
         const unsigned char *const src_base = (FIRST && SRING) ? in_data + sslot * Shape::STAGE_B : in_data;
         if (FIRST && SRING) mbar_wait(bars + 8u * sslot, ((unsigned)trip >> 1) & 1u);
@@ -305,6 +367,7 @@ __device__ __forceinline__ void chain_body(const MarchParams<float> &p, const Ch
             for (int s = 0; s < K; ++s) {
                 const int sa = (u - s + 2 * NS) % NS, sh = (u - s - 1 + 2 * NS) % NS;
                 if (COL) march_stage_pk_col(S[sa], S[sh], cl, negzero);
+                else if (ROW) march_stage_pk_row(p, S[sa], S[sh], row_in + u - s, negzero);      // stage s: this warp's (x-s)-th input arrives
                 else march_stage_pk<CV, false, false>(S[sa], S[sh], negzero, nullptr, nullptr);
             }
             // ---- give the input slot back: every value read from it has been used by the stages above (the warp-level
@@ -367,7 +430,16 @@ __device__ __forceinline__ bool decode_col_item(const MarchParams<float> &p, con
     return true;
 }
 
-template <typename Shape, bool COL>
+// (ordinary strip, special chunk) item w of the row variant
+__device__ __forceinline__ bool decode_row_item(const MarchParams<float> &p, const int w, int &strip, int &i0, int &i1) {
+    const int nsf = p.nstrips - p.n_sstrips;
+    if (w >= nsf * p.n_schunks) return false;
+    strip = kth_not_in(w % nsf, p.sstrips, p.n_sstrips);
+    chunk_span(p, p.schunks[w / nsf], i0, i1);
+    return true;
+}
+
+template <typename Shape, int KIND>
 __global__ void __launch_bounds__(Shape::THREADS, 1)
 k_march_chain(const __grid_constant__ MarchParams<float> p, const __grid_constant__ ChainMaps maps) {
     extern __shared__ __align__(1024) unsigned char chain_smem[];
@@ -383,10 +455,13 @@ k_march_chain(const __grid_constant__ MarchParams<float> p, const __grid_constan
     __syncthreads();
     int strip, i0, i1;
     const int item = blockIdx.x * Shape::GROUPS + grp;
-    if (COL ? !decode_col_item(p, item, strip, i0, i1) : !decode_item<true>(p, item, 0, CV, Shape::T, false, strip, i0, i1)) return;   // the whole group
-    if (wg == 0) chain_body<Shape, true, false, COL>(p, maps, strip, i0, i1, lane, wg, gsm);
-    else if (wg == Shape::G - 1) chain_body<Shape, false, true, COL>(p, maps, strip, i0, i1, lane, wg, gsm);
-    else chain_body<Shape, false, false, COL>(p, maps, strip, i0, i1, lane, wg, gsm);
+    const bool mine = KIND == K_COL ? decode_col_item(p, item, strip, i0, i1)
+                    : KIND == K_ROW ? decode_row_item(p, item, strip, i0, i1)
+                                    : decode_item<true>(p, item, 0, CV, Shape::T, false, strip, i0, i1);
+    if (!mine) return;                               // the whole group
+    if (wg == 0) chain_body<Shape, true, false, KIND>(p, maps, strip, i0, i1, lane, wg, gsm);
+    else if (wg == Shape::G - 1) chain_body<Shape, false, true, KIND>(p, maps, strip, i0, i1, lane, wg, gsm);
+    else chain_body<Shape, false, false, KIND>(p, maps, strip, i0, i1, lane, wg, gsm);
 }
 
 // ---- host: tensor maps
@@ -420,7 +495,7 @@ int make_map(CUtensorMap *m, const float *base, int ny, int rows, int box_rows) 
     return FDTD_OK;
 }
 
-template <typename Shape, bool COL = false>
+template <typename Shape, int KIND = K_INTERIOR>
 int launch_chain(const MarchParams<float> &mp, int items, cudaStream_t st) {
     if (items <= 0) return FDTD_OK;
     ChainMaps maps;
@@ -438,12 +513,12 @@ int launch_chain(const MarchParams<float> &mp, int items, cudaStream_t st) {
         FDTD_CUDA(cudaGetDevice(&dev));
         bool &done = configured[dev >= 0 && dev < 64 ? dev : 0];
         if (!done || dev >= 64) {
-            FDTD_CUDA(cudaFuncSetAttribute(k_march_chain<Shape, COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape::SMEM));
+            FDTD_CUDA(cudaFuncSetAttribute(k_march_chain<Shape, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape::SMEM));
             done = true;
         }
     }
     const int grid = (items + Shape::GROUPS - 1) / Shape::GROUPS;
-    k_march_chain<Shape, COL><<<grid, Shape::THREADS, Shape::SMEM, st>>>(mp, maps);
+    k_march_chain<Shape, KIND><<<grid, Shape::THREADS, Shape::SMEM, st>>>(mp, maps);
     FDTD_LAUNCH_CHECK("k_march_chain");
     return FDTD_OK;
 }
@@ -465,14 +540,18 @@ bool chain_supported(int T, bool lossy) {
     return (T == 8 || T == 12) && !lossy && encoder() != nullptr;
 }
 
-int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items, cudaStream_t st, bool column_items) {
+int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items, cudaStream_t st, int kind) {
     if (mp.ny % CV != 0 || (reinterpret_cast<uintptr_t>(mp.in_dz) & 15u) != 0) {
         fdtd::set_error("warp-chain pass: ny must be a multiple of 4 and the arrays 16-byte aligned");
         return FDTD_EINVAL;
     }
-    if (column_items) {          // (special strip, ordinary chunk) items: the shipped shape with the column-coefficient stage
-        if (T == 8) return launch_chain<Chain8, true>(mp, items, st);
-        if (T == 12) return launch_chain<Chain12, true>(mp, items, st);
+    if (kind == K_COL) {         // (special strip, ordinary chunk) items: the shipped shape with the column-coefficient stage
+        if (T == 8) return launch_chain<Chain8, K_COL>(mp, items, st);
+        if (T == 12) return launch_chain<Chain12, K_COL>(mp, items, st);
+    }
+    if (kind == K_ROW) {         // (ordinary strip, special chunk) items: ... with the row-coefficient stage
+        if (T == 8) return launch_chain<Chain8, K_ROW>(mp, items, st);
+        if (T == 12) return launch_chain<Chain12, K_ROW>(mp, items, st);
     }
     if (T == 8) {
         if (shape == 1) return launch_chain<Chain8b>(mp, items, st);
@@ -491,10 +570,12 @@ int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items
 
 void preload_chain() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, k_march_chain<Chain8, false>);
-    cudaFuncGetAttributes(&a, k_march_chain<Chain12, false>);
-    cudaFuncGetAttributes(&a, k_march_chain<Chain8, true>);
-    cudaFuncGetAttributes(&a, k_march_chain<Chain12, true>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain8, K_INTERIOR>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain12, K_INTERIOR>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain8, K_COL>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain12, K_COL>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain8, K_ROW>);
+    cudaFuncGetAttributes(&a, k_march_chain<Chain12, K_ROW>);
 }
 
 }  // namespace fdtd_march

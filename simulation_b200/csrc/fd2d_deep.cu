@@ -570,6 +570,9 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
     const bool chain = (g_tune.variant == 0 || g_tune.variant >= 10) && chain_supported(T, lossy);
     // PML-column strips x ordinary chunks at interior speed (classify_pass withdraws it where it cannot apply)
     mp.col_fast = chain && g_tune.col_fast && !mp.tfsf ? 1 : 0;
+    // PML-row chunks x ordinary strips likewise; not on a slab with the fused exchange (its edge chunks read ghost rows
+    // and push rows: the handshake lives in the careful kernel)
+    mp.row_fast = chain && g_tune.row_fast && !mp.tfsf && !mp.halo_on ? 1 : 0;
     const PassCounts pc = classify_pass(mp, DV, T);
     if (pc.all_careful) return launch_careful2(mp, T, lossy, pc.n_careful, 1, st);
     auto launch_interior = [&]() -> int {
@@ -600,7 +603,11 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
         rc = launch_careful2(mp, T, lossy, pc.n_careful, 0, side->backfill, DV, 1);
         if (rc != FDTD_OK) return rc;
         if (pc.n_col > 0) {
-            rc = launch_march_chain(mp, T, 0, pc.n_col, side->backfill, true);
+            rc = launch_march_chain(mp, T, 0, pc.n_col, side->backfill, 1);
+            if (rc != FDTD_OK) return rc;
+        }
+        if (pc.n_row > 0) {
+            rc = launch_march_chain(mp, T, 0, pc.n_row, side->backfill, 2);
             if (rc != FDTD_OK) return rc;
         }
         FDTD_CUDA(cudaEventRecord(side->join, side->backfill));
@@ -611,7 +618,11 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
         int rc = launch_careful2(mp, T, lossy, pc.n_careful, 0, st);
         if (rc != FDTD_OK) return rc;
         if (pc.n_col > 0) {
-            rc = launch_march_chain(mp, T, 0, pc.n_col, st, true);
+            rc = launch_march_chain(mp, T, 0, pc.n_col, st, 1);
+            if (rc != FDTD_OK) return rc;
+        }
+        if (pc.n_row > 0) {
+            rc = launch_march_chain(mp, T, 0, pc.n_row, st, 2);
             if (rc != FDTD_OK) return rc;
         }
         return launch_interior();
@@ -621,7 +632,11 @@ int launch_march_deep(MarchParams<float> &mp, int T, bool lossy, cudaStream_t st
     int rc = launch_careful2(mp, T, lossy, pc.n_careful, 0, side->stream);
     if (rc != FDTD_OK) return rc;
     if (pc.n_col > 0) {
-        rc = launch_march_chain(mp, T, 0, pc.n_col, side->stream, true);
+        rc = launch_march_chain(mp, T, 0, pc.n_col, side->stream, 1);
+        if (rc != FDTD_OK) return rc;
+    }
+    if (pc.n_row > 0) {
+        rc = launch_march_chain(mp, T, 0, pc.n_row, side->stream, 2);
         if (rc != FDTD_OK) return rc;
     }
     FDTD_CUDA(cudaEventRecord(side->join, side->stream));

@@ -719,7 +719,7 @@ int advance(const fdtd2d_problem *q, int cur, int nsteps, const double *src, int
         mp.chunk_rows = chunk;
         mp.nchunks = (rows + chunk - 1) / chunk;
         mp.first_rows = mp.last_rows = 0;
-        mp.col_fast = 0;
+        mp.col_fast = mp.row_fast = 0;
         if (g_tune.edge_chunks && rows >= 3 * chunk) {
             // Short edge chunks: F = the fewest rows (a multiple of 8) after which a chunk starts clear of everything
             // that makes the rows above it special -- the same conditions classify_pass applies to lo = i0 - T - 1 --
@@ -889,7 +889,8 @@ int fdtd2d_tune2(int key, long long value) {
             g_tune.edge_chunks = value != 0;
             return FDTD_OK;
         case FDTD_TUNE_COL_FAST:
-            g_tune.col_fast = value != 0;
+            g_tune.col_fast = (value & 1) != 0;            // bit 0: column variant, bit 1: row variant
+            g_tune.row_fast = (value & 2) != 0;
             return FDTD_OK;
         default:
             fdtd::set_error("fdtd2d_tune2: unknown key %d", key);

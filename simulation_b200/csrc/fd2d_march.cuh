@@ -36,6 +36,10 @@ struct MarchParams {
     // variant of the warp-chain kernel (fd2d_chain.cu) and the careful kernel keeps the special strips only inside the
     // special chunks.
     int col_fast;
+    // row_fast: likewise the special chunks that are special only for their ROWS (PML x-coefficients, the grid's first /
+    // last row): where an ordinary strip crosses one, the item goes to the row variant of the warp-chain kernel and the
+    // careful kernel keeps the corner blocks (special strip x special chunk) and the source cells.
+    int row_fast;
     int tfsf, npml;
     const real *ezi_hist, *hxi_hist;           // [T][ny], [T][2]
     int src_i, src_j, src_hard;                // point source on dz (src_i < 0: none)
@@ -446,7 +450,7 @@ __device__ __forceinline__ bool decode_item(const MarchParams<real> &p, const in
                 own_partition = true;
             }
         } else {
-            const int x = w - na, nb = nsf * p.n_schunks;
+            const int x = w - na, nb = p.row_fast ? 0 : nsf * p.n_schunks;
             if (x < nb) {
                 strip = kth_not_in(x % nsf, p.sstrips, p.n_sstrips);
                 chunk = p.schunks[x / nsf];
@@ -553,6 +557,7 @@ struct Tuning {
     int deep = 1;                // 0 = never use the deep passes of fd2d_deep.cu; 2 = the smem-resident careful kernel at every depth
     int edge_chunks = 1;         // 1 = short first / last chunk around the rows that need the careful kernel; 0 = uniform chunks
     int col_fast = 1;            // 1 = PML-column strips x ordinary chunks through the warp-chain kernel's column variant
+    int row_fast = 1;            // 1 = ordinary strips x PML-row chunks through its row variant
     unsigned long long spin_ns = HALO_SPIN_NS;
 };
 extern Tuning g_tune;
@@ -561,7 +566,7 @@ struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; cudaStream_t ba
 // one high-priority side stream + fork/join events per (device, launch stream), created on first use
 SideStream *side_stream(cudaStream_t launch);
 
-struct PassCounts { bool all_careful; int n_fast, n_careful, n_col; };   // n_col: (special strip, ordinary chunk) items of col_fast
+struct PassCounts { bool all_careful; int n_fast, n_careful, n_col, n_row; };   // n_col / n_row: the items of col_fast / row_fast
 
 // Classify strips and chunks on the host (same conditions as the kernels rely on): fills the special lists, the single
 // source cells, the careful row partition and total_warps of `mp` for a pass of vector width V and depth T.
@@ -617,8 +622,8 @@ PassCounts classify_pass(MarchParams<real> &mp, const int V, const int T) {
         mp.n_sstrips = mp.n_schunks = 0;
         mp.cchunk_rows = mp.chunk_rows; mp.ncchunks = mp.nchunks;
         mp.total_warps = (unsigned)(mp.nstrips * mp.nchunks);
-        out.all_careful = true; out.n_fast = 0; out.n_careful = mp.nstrips * mp.nchunks; out.n_col = 0;
-        mp.col_fast = 0;
+        out.all_careful = true; out.n_fast = 0; out.n_careful = mp.nstrips * mp.nchunks; out.n_col = out.n_row = 0;
+        mp.col_fast = mp.row_fast = 0;
         return out;
     }
     mp.n_sstrips = ns; mp.n_schunks = nc;
@@ -638,9 +643,19 @@ PassCounts classify_pass(MarchParams<real> &mp, const int V, const int T) {
             if (mp.src_j >= c0 && mp.src_j < c0 + W) mp.col_fast = 0;
         }
     if (ns == 0 || ncf == 0) mp.col_fast = 0;
+    // row_fast needs a source cell outside the rows the special chunks touch (their items carry no source code); without
+    // col_fast the special strips run through ALL rows in their own partition, corner blocks included, so nothing else changes
+    if (mp.row_fast && mp.src_i >= 0)
+        for (int q = 0; q < nc; ++q) {
+            int i0, i1;
+            chunk_span(mp, mp.schunks[q], i0, i1);
+            if (mp.src_i >= i0 - T - 1 && mp.src_i < i1 + 2 * T + RING + 2) mp.row_fast = 0;
+        }
+    if (nc == 0 || nsf == 0) mp.row_fast = 0;
     out.all_careful = false; out.n_fast = n_fast;
     out.n_col = mp.col_fast ? ns * ncf : 0;
-    out.n_careful = (mp.col_fast ? ns * nc : ns * mp.ncchunks) + nsf * nc + np;
+    out.n_row = mp.row_fast ? nsf * nc : 0;
+    out.n_careful = (mp.col_fast ? ns * nc : ns * mp.ncchunks) + (mp.row_fast ? 0 : nsf * nc) + np;
     mp.total_warps = (unsigned)out.n_careful;
     return out;
 }
@@ -653,7 +668,7 @@ int launch_careful2(MarchParams<float> &mp, int T, bool lossy, int items, int al
 void preload_deep(bool lossy);
 // warp-chain passes (fd2d_chain.cu): the interior items of a depth-8 / depth-12 pass as a TMA-fed pipeline of warps
 bool chain_supported(int T, bool lossy);
-int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items, cudaStream_t st, bool column_items = false);
+int launch_march_chain(const MarchParams<float> &mp, int T, int shape, int items, cudaStream_t st, int kind = 0);   // kind: 0 interior, 1 column items, 2 row items
 void preload_chain();
 
 }  // namespace fdtd_march

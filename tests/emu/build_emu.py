@@ -47,7 +47,7 @@ CHAIN_STUBS = r'''
 #include "fd2d_march.cuh"
 namespace fdtd_march {
 bool chain_supported(int, bool) { return false; }
-int launch_march_chain(const MarchParams<float> &, int, int, int, cudaStream_t, bool) { fdtd::set_error("the warp-chain passes are not part of the emulated build"); return FDTD_EUNSUPPORTED; }
+int launch_march_chain(const MarchParams<float> &, int, int, int, cudaStream_t, int) { fdtd::set_error("the warp-chain passes are not part of the emulated build"); return FDTD_EUNSUPPORTED; }
 void preload_chain() {}
 }
 '''

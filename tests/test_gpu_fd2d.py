@@ -474,11 +474,11 @@ def test_warp_chain_passes(prog, nx, ny, npml, chunk_rows, tblock, variant):
     _assert_same(sim, g, prog)
 
 
-@pytest.mark.parametrize("variant,col_fast,edge", [(10, 1, 1), (11, 1, 1), (10, 0, 1), (10, 1, 0), (10, 0, 0)])
+@pytest.mark.parametrize("variant,col_fast,edge", [(10, 3, 1), (11, 3, 1), (10, 0, 1), (10, 1, 1), (10, 2, 1), (10, 3, 0), (10, 0, 0)])
 def test_warp_chain_bench_plan_vs_oracle(variant, col_fast, edge):
     """The warp-chain passes on the bench's launch plan (4-wide vectors, tall chunks, depth 8 and 12) forced onto
-    2304 x 4096 with a random medium -- with and without the column variant for the PML-column strips (col_fast) and
-    the short edge chunks: every array bit-for-bit against the numpy oracle."""
+    2304 x 4096 with a random medium -- with and without the column / row variants for the PML-column strips and the
+    PML-row chunks (col_fast bits 0 / 1) and the short edge chunks: every array bit-for-bit against the numpy oracle."""
     from simulation_b200 import _lib
     nx, ny, npml, ns = 2304, 4096, 80, 45
     rng = np.random.default_rng(6)
@@ -495,7 +495,7 @@ def test_warp_chain_bench_plan_vs_oracle(variant, col_fast, edge):
     finally:
         _lib.lib().fdtd2d_tune(0, 0, 0, 0, 0)
         _lib.lib().fdtd2d_tune2(_lib.TUNE_VARIANT, 0)
-        _lib.lib().fdtd2d_tune2(_lib.TUNE_COL_FAST, 1)
+        _lib.lib().fdtd2d_tune2(_lib.TUNE_COL_FAST, 3)
         _lib.lib().fdtd2d_tune2(_lib.TUNE_EDGE_CHUNKS, 1)
     g, src = cases.grid_program("3_2", nx, ny, ns, np.float32, npml=npml, naz=naz.copy())
     orc.advance_2d(g, src)
