@@ -122,10 +122,53 @@ ASM = [  # the kernels' inline PTX, statement by statement -> its emulation (tes
 ]
 
 
+def _asm_operands(stmt: str):
+    """the C expressions of an ``asm volatile("..." : outputs : inputs : clobbers);`` statement, in operand order"""
+    import re
+    ops, pos = [], 0
+    body = re.sub(r'"(?:[^"\\]|\\.)*"\s*(?=["\n])', "", stmt)       # drop the PTX text (adjacent string literals)
+    for m in re.finditer(r'"[=+]?[rlfhd]"\s*\(', stmt):
+        a0 = m.end() - 1
+        ops.append(stmt[a0 + 1:_match(stmt, a0, "(", ")") - 1].strip())
+    return ops
+
+
+# the multi-line PTX blocks of fd2d_chain.cu (mbarrier pipeline, TMA), by the instruction they are built around
+BLOCKS = [
+    ("cp.async.bulk.tensor.2d", lambda o: "emu::tma_issue6(%s);" % ", ".join(o)),
+    ("mbarrier.try_wait.parity", lambda o: "emu::mbar_wait(%s, %s);" % (o[0], o[1])),
+    ("mbarrier.init", lambda o: "emu::mbar_init(%s, %s);" % (o[0], o[1])),
+    ("mbarrier.arrive.shared::cta.b64", lambda o: "emu::mbar_arrive(%s, %s);" % (o[0], o[1])),
+    ("fence.mbarrier_init", lambda o: ";"),
+    ("st.shared.v2.f32 [%0+8]", lambda o: "emu::st_shared_v2(%s + 8, %s, %s);" % (o[0], o[1], o[2])),
+    ("st.shared.v2.f32 [%0]", lambda o: "emu::st_shared_v2(%s, %s, %s);" % (o[0], o[1], o[2])),
+]
+
+
+def rewrite_asm_blocks(src: str) -> str:
+    out, pos = "", 0
+    while True:
+        i = src.find("asm volatile(", pos)
+        if i < 0:
+            return out + src[pos:]
+        a0 = src.index("(", i)
+        a1 = _match(src, a0, "(", ")")
+        end = src.index(";", a1) + 1
+        stmt = src[i:end]
+        for key, make in BLOCKS:
+            if key in stmt:
+                out += src[pos:i] + make(_asm_operands(stmt))
+                break
+        else:
+            out += src[pos:end]                         # left for the single-statement patterns below
+        pos = end
+
+
 def rewrite_device_code(src: str) -> str:
     import re
     for pat, rep in ASM:
         src = re.sub(pat, rep, src)
+    src = rewrite_asm_blocks(src)
     if re.search(r"\basm\b", src):
         raise RuntimeError("inline PTX without an emulation: " + re.search(r"\basm\b.*", src).group(0)[:120])
     # extern __shared__ T name[];  ->  the CTA's dynamic shared memory
@@ -162,7 +205,7 @@ def build(*source_names: str) -> str:
     for n, text in cuh.items():
         with open(os.path.join(inc, n), "w") as f:
             f.write(rewrite_device_code(text).replace('"../../include/fdtd_b200.h"', '"fdtd_b200.h"'))
-    if "fd2d_deep.cu" in srcs:       # fd2d_chain.cu (TMA + mbarrier pipeline) has no emulation: the deep passes keep their own interior kernel
+    if "fd2d_deep.cu" in srcs and "fd2d_chain.cu" not in srcs:      # a partial build without the warp-chain kernel
         stubs += CHAIN_STUBS
     units = {"stubs": '#include "common.cuh"\n' + stubs}
     for n, src in srcs.items():
@@ -188,7 +231,7 @@ def build(*source_names: str) -> str:
     return so
 
 
-ALL_SOURCES = ("fd1d.cu", "fd2d_steps.cu", "fd2d_march.cu", "fd2d_deep.cu")
+ALL_SOURCES = ("fd1d.cu", "fd2d_steps.cu", "fd2d_march.cu", "fd2d_deep.cu", "fd2d_chain.cu")
 
 
 def build_library() -> str:

@@ -8,6 +8,8 @@
 #pragma once
 #include <ucontext.h>
 
+#include "cuda.h"          // the emulated driver-API types (tests/emu/cuda.h)
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -67,6 +69,11 @@ template <typename T> cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)std::m
 inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
+
+// driver entry points: the emulator hands out its own cuTensorMapEncodeTiled (tests/emu/cuda.h)
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+constexpr unsigned long long cudaEnableDefault = 0;
+cudaError_t cudaGetDriverEntryPoint(const char *symbol, void **fn, unsigned long long flags, cudaDriverEntryPointQueryResult *status);
 
 using std::max;
 using std::min;
@@ -239,6 +246,7 @@ void launch(dim3 grid, dim3 block, F body) {
 
 template <typename T> T __shfl_up_sync(unsigned, T v, int d) { return emu::shuffle(v, emu::cur->lane - d); }
 template <typename T> T __shfl_down_sync(unsigned, T v, int d) { return emu::shuffle(v, emu::cur->lane + d); }
+template <typename T> T __shfl_sync(unsigned, T v, int src) { return emu::shuffle(v, src); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::wait(*emu::cur->warp); }
 inline void __syncthreads() { emu::wait(emu::blk->all); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
@@ -309,3 +317,78 @@ inline unsigned long long global_timer_ns() {
 }
 inline void st_release(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 }  // namespace emu
+
+namespace emu {
+// ---- mbarrier and TMA (fd2d_chain.cu).  A barrier is its 8 bytes of CTA shared memory: {phase bit, expected arrivals,
+// pending arrivals} and the transaction bytes still expected.  A phase completes when no arrival and no byte is
+// pending.  try_wait spins by yielding to the CTA's other fibers: the producer warp runs on the same host thread.
+// TMA copies land at issue (the data is there, the barrier says so later): what the emulation checks is the protocol --
+// slot indices, parities, who waits for whom (a wait that can never be satisfied trips the deadlock detector) -- and
+// the arithmetic, not the hardware's asynchrony.
+struct MBar { uint32_t phase : 1, count : 15, pending : 16; int32_t tx; };
+static_assert(sizeof(MBar) == 8, "an mbarrier is 8 bytes");
+inline MBar &mbar_at(unsigned bar) { return *reinterpret_cast<MBar *>(blk->smem + bar); }
+inline void mbar_settle(MBar &b) {
+    if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.count; ++blk->events; }
+}
+inline void mbar_init(unsigned bar, unsigned count) { MBar &b = mbar_at(bar); b.phase = 0; b.count = count; b.pending = count; b.tx = 0; }
+inline void mbar_arrive(unsigned bar, int leader) {
+    if (!leader) return;
+    MBar &b = mbar_at(bar);
+    if (b.pending == 0) { std::fprintf(stderr, "emu: mbarrier over-arrived\n"); std::abort(); }
+    --b.pending;
+    mbar_settle(b);
+}
+inline void mbar_wait(unsigned bar, unsigned parity) {
+    while (mbar_at(bar).phase == parity) yield();     // the phase with this parity has not completed yet
+}
+inline void st_shared_v2(unsigned addr, float x, float y) { float *d = reinterpret_cast<float *>(blk->smem + addr); d[0] = x; d[1] = y; }
+// one box of one array: rows [row, row + box rows) x columns [col, col + box columns), zeros outside the tensor
+inline void tma_box(unsigned dst, const CUtensorMap *m, int col, int row) {
+    unsigned char *d = blk->smem + dst;
+    const size_t row_bytes = (size_t)m->box[0] * m->elem;
+    for (uint32_t r = 0; r < m->box[1]; ++r, d += row_bytes) {
+        std::memset(d, 0, row_bytes);
+        const long long rr = (long long)row + r;
+        if (rr < 0 || rr >= (long long)m->dim[1]) continue;
+        const long long c0 = std::max<long long>(col, 0), c1 = std::min<long long>((long long)col + m->box[0], (long long)m->dim[0]);
+        if (c1 > c0) std::memcpy(d + (c0 - col) * m->elem, m->base + rr * m->row_stride + c0 * m->elem, (size_t)(c1 - c0) * m->elem);
+    }
+}
+// the elected lane arms the barrier with the bytes of six boxes and issues them
+inline void tma_issue6(unsigned dst0, unsigned bar, const CUtensorMap *m0, const CUtensorMap *m1, const CUtensorMap *m2,
+                       const CUtensorMap *m3, const CUtensorMap *m4, const CUtensorMap *m5, int col, int bytes, int row,
+                       unsigned dst1, unsigned dst2, unsigned dst3, unsigned dst4, unsigned dst5) {
+    if (cur->lane != 0) return;                       // elect.sync
+    MBar &b = mbar_at(bar);
+    b.tx += bytes;
+    if (b.pending == 0) { std::fprintf(stderr, "emu: mbarrier over-arrived (expect_tx)\n"); std::abort(); }
+    --b.pending;
+    const CUtensorMap *m[6] = {m0, m1, m2, m3, m4, m5};
+    const unsigned dst[6] = {dst0, dst1, dst2, dst3, dst4, dst5};
+    for (int a = 0; a < 6; ++a) {
+        tma_box(dst[a], m[a], col, row);
+        b.tx -= (int32_t)(m[a]->box[0] * m[a]->box[1] * m[a]->elem);
+    }
+    mbar_settle(b);
+}
+inline CUresult encode_tiled(CUtensorMap *m, CUtensorMapDataType, cuuint32_t rank, void *base, const cuuint64_t *gdim,
+                             const cuuint64_t *gstride, const cuuint32_t *box, const cuuint32_t *, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+    if (rank != 2 || (reinterpret_cast<uintptr_t>(base) & 15u) != 0 || gstride[0] % 16 != 0 || box[0] > 256 || box[1] > 256) return 1;
+    std::memset(m, 0, sizeof(*m));
+    m->base = static_cast<const unsigned char *>(base);
+    m->dim[0] = gdim[0]; m->dim[1] = gdim[1];
+    m->row_stride = gstride[0];
+    m->box[0] = box[0]; m->box[1] = box[1];
+    m->elem = 4;
+    return CUDA_SUCCESS;
+}
+}  // namespace emu
+
+inline cudaError_t cudaGetDriverEntryPoint(const char *symbol, void **fn, unsigned long long, cudaDriverEntryPointQueryResult *status) {
+    const bool known = std::strcmp(symbol, "cuTensorMapEncodeTiled") == 0;
+    *fn = known ? reinterpret_cast<void *>(&emu::encode_tiled) : nullptr;
+    if (status) *status = known ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+    return cudaSuccess;
+}

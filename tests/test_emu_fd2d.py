@@ -25,11 +25,14 @@ def emu(monkeypatch):
     return device.install(monkeypatch)
 
 
-def _run(emu, prog, nx, ny, npml, ns, dtype, tblock=None, radius=0.12, tune=(0, 0, 0, 0, 0), parts=None, deep=1, edge=1):
+def _run(emu, prog, nx, ny, npml, ns, dtype, tblock=None, radius=0.12, tune=(0, 0, 0, 0, 0), parts=None, deep=1, edge=1,
+         variant=0, fast=3):
     before = emu.emu_launches()
     emu.fdtd2d_tune(*tune)
     emu.fdtd2d_tune2(0, deep)
     emu.fdtd2d_tune2(3, edge)
+    emu.fdtd2d_tune2(2, variant)
+    emu.fdtd2d_tune2(4, fast)
     try:
         sim = _sim_for(prog, nx, ny, dtype, npml=npml, radius=radius, device="cpu")
         for part in (parts or (ns,)):
@@ -38,6 +41,8 @@ def _run(emu, prog, nx, ny, npml, ns, dtype, tblock=None, radius=0.12, tune=(0, 
         emu.fdtd2d_tune(0, 0, 0, 0, 0)
         emu.fdtd2d_tune2(0, 1)
         emu.fdtd2d_tune2(3, 1)
+        emu.fdtd2d_tune2(2, 0)
+        emu.fdtd2d_tune2(4, 3)
     assert sim.t == ns and emu.emu_launches() > before
     g, src = cases.grid_program(prog, nx, ny, ns, dtype, npml=npml, radius=radius, dft=False)
     orc.advance_2d(g, src)
@@ -65,7 +70,10 @@ def test_emulated_interior_and_careful_kernels(emu, prog, nx, ny, npml, force_v,
     # 3_4 (lossy cylinder in free space): two interior kernels per pass -- lossy for the warps that meet the cylinder's
     # box, lossless for the others -- and one more setup check (the lossless-outside promise)
     per_pass = {"3_2": 2, "3_3": 3, "3_4": 4}[prog]
-    assert emu.emu_launches() - before == 3 * per_pass + (3 if prog == "3_4" else 2), "an interior kernel did not run in every pass"
+    # the two depth-8 passes at 4-wide vectors are deep passes: without TFSF / loss the column and the row variant of the
+    # warp-chain kernel launch beside the interior one
+    extra = 2 * 2 if (prog == "3_2" and force_v == 4 and tblock == 8) else 0
+    assert emu.emu_launches() - before == 3 * per_pass + extra + (3 if prog == "3_4" else 2), "an interior kernel did not run in every pass"
 
 
 def test_emulated_interior_kernel_equals_careful_kernel(emu):
@@ -288,9 +296,9 @@ def test_emulated_fused_halo_exchange(emu, prog, nslab, order):
 @pytest.mark.parametrize("tblock,chunk_rows", [(12, 40), (8, 40), (12, 0), (8, 64)])
 @pytest.mark.parametrize("prog,nx,ny,npml", [("3_2", 300, 1100, 8), ("3_3", 280, 1000, 12)])
 def test_emulated_deep_passes(emu, prog, nx, ny, npml, tblock, chunk_rows):
-    """Depth 8 and 12: the interior kernel with shared-memory-resident accumulators (dz, hx, hy in registers; ihx, ihy,
-    naz in each lane's own shared-memory column; Ez re-evaluated) + the shared-memory-ring careful kernel, on grids with
-    a true interior; ragged last strips and chunks, a remainder pass of the register-pipeline kernels at the end."""
+    """Depth 8 and 12: the warp-chain interior kernel (TMA boxes, mbarrier hand-off between the warps of a group; its
+    column and row variants for the PML strips / chunks) + the shared-memory-ring careful kernel, on grids with a true
+    interior; ragged last strips and chunks, a remainder pass of the register-pipeline kernels at the end."""
     before = emu.emu_launches()
     sim = _run(emu, prog, nx, ny, npml, 2 * tblock + 3, np.float32, tblock, radius=0.3, tune=(4, chunk_rows, 0, 0, 0))
     emu.fdtd2d_tune(4, chunk_rows, 0, 0, 0)
@@ -299,8 +307,10 @@ def test_emulated_deep_passes(emu, prog, nx, ny, npml, tblock, chunk_rows):
     finally:
         emu.fdtd2d_tune(0, 0, 0, 0, 0)
     assert sim.max_tblock == 12
-    if chunk_rows:       # 3 passes x (careful + interior [+ incident line]) + the two identity checks of the setup
-        assert emu.emu_launches() - before == 3 * (3 if prog == "3_3" else 2) + 2, "an interior kernel did not run in every pass"
+    if chunk_rows:       # the two identity checks of the setup + 3 passes x (careful + interior [+ incident line]); the two deep
+        # passes of a problem without TFSF also launch the column and the row variant of the warp-chain kernel
+        want = 2 + (3 * 3 if prog == "3_3" else 3 * 2 + 2 * 2)
+        assert emu.emu_launches() - before == want, "an interior kernel did not run in every pass"
 
 
 @pytest.mark.parametrize("prog,nx,ny,npml,vec,chunk,tblock", [("3_2", 420, 600, 8, 4, 64, 6), ("3_3", 400, 560, 12, 4, 96, 8),
@@ -314,6 +324,17 @@ def test_emulated_short_edge_chunks(emu, prog, nx, ny, npml, vec, chunk, tblock)
     b = _run(emu, prog, nx, ny, npml, ns, np.float32, tblock, radius=0.3, tune=(vec, chunk, 0, 0, 0), edge=0)
     for name in ("dz", "ez", "hx", "hy", "ihx", "ihy"):
         assert a.get(name).tobytes() == b.get(name).tobytes(), name
+
+
+@pytest.mark.parametrize("variant,fast,tblock", [(3, 3, 8), (1, 3, 8), (2, 3, 8), (3, 3, 12),          # shared-memory-accumulator kernels
+                                                 (11, 3, 8), (12, 3, 8), (13, 3, 8), (11, 3, 12), (12, 3, 12),   # other warp-chain shapes
+                                                 (0, 0, 8), (0, 1, 12), (0, 2, 8)])                      # chain without / with one of its variants
+def test_emulated_deep_kernel_variants(emu, variant, fast, tblock):
+    """Every interior kernel of the deep passes on the CTA emulator: the shared-memory-accumulator kernels of
+    fd2d_deep.cu (variants 1..3: the fallback without a tensor-map encoder), the warp-chain shapes that are not shipped
+    (run-time staging ring with 2- and 3-row TMA boxes, 64-bit queue stores spelled in PTX, four warps of two stages, ...)
+    and the shipped shape with its column / row variants switched off one by one -- the oracle's bits each time."""
+    _run(emu, "3_2", 300, 1100, 8, 2 * tblock + 3, np.float32, tblock, tune=(4, 40, 0, 0, 0), variant=variant, fast=fast)
 
 
 def test_emulated_deep_equals_register_pipeline(emu):
