@@ -35,13 +35,44 @@ while time.time() < t_end:
     edge = int(rng.choice([1, 1, 0]))
     deep = int(rng.choice([1, 1, 2]))
     ns = int(rng.integers(8, 40))
-    cfg = dict(prog=prog, nx=nx, ny=ny, npml=npml, tblock=tblock, chunk=chunk, variant=variant, fast=fast, edge=edge, deep=deep, ns=ns)
+    slabbed = prog != "3_1" and rng.random() < 0.35
+    cfg = dict(prog=prog, nx=nx, ny=ny, npml=npml, tblock=tblock, chunk=chunk, variant=variant, fast=fast, edge=edge, deep=deep, ns=ns,
+               slabbed=slabbed)
     try:
         emu.fdtd2d_tune(4, chunk, 0, 0, 0)
         emu.fdtd2d_tune2(0, deep)
         emu.fdtd2d_tune2(2, variant)
         emu.fdtd2d_tune2(3, edge)
         emu.fdtd2d_tune2(4, fast)
+        if slabbed:
+            # the halo exchange fused into the pass: every "GPU" a slab in this process, peers wired by raw pointers,
+            # the ring careful kernel carrying the handshake around deep interior passes
+            from simulation_b200 import fd2d
+            T = tblock or 8
+            nslab = int(rng.integers(2, 5))
+            if nx // nslab < 2 * T + 2:
+                continue
+            nblocks = int(rng.integers(1, 4))
+            cfg.update(T=T, nslab=nslab, nblocks=nblocks)
+            cuts = np.linspace(0, nx, nslab + 1).astype(int)
+            slabs = [_sim_for(prog, nx, ny, np.float32, npml=npml, rows=(int(lo), int(hi)), ghost=T, tblock=T, device="cpu")
+                     for lo, hi in zip(cuts[:-1], cuts[1:])]
+            names = [k for k in fd2d.FIELD_NAMES if k not in ("ez", "iz")]
+            words = [np.zeros(8, dtype=np.int64) for _ in slabs]
+            for r, sl in enumerate(slabs):
+                peer = lambda q: None if q is None else {"row_base": slabs[q].row_base, "sync": words[q].ctypes.data,
+                                                         "sets": [{k: slabs[q]._sets[i][k].data_ptr() for k in names} for i in range(2)]}
+                sl.p2p = {"halo": T, "sync": type("W", (), {"ptr": words[r].ctypes.data})(),
+                          "up": peer(r - 1 if r > 0 else None), "dn": peer(r + 1 if r < nslab - 1 else None)}
+            for epoch in range(1, nblocks + 1):
+                for r in rng.permutation(nslab):
+                    slabs[int(r)].advance(T, tblock=T, lazy_ez=epoch < nblocks, epoch=epoch)
+            g, src = cases.grid_program(prog, nx, ny, nblocks * T, np.float32, npml=npml, dft=False)
+            orc.advance_2d(g, src)
+            for k in names + ["ez"]:
+                assert np.concatenate([sl.get(k) for sl in slabs]).tobytes() == getattr(g, k).tobytes(), k
+            n += 1
+            continue
         sim = _sim_for(prog, nx, ny, np.float32, npml=npml, device="cpu")
         parts = [ns] if rng.random() < 0.5 else [ns // 3, ns - ns // 3]
         for part in parts:
