@@ -22,7 +22,8 @@ seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 rng = np.random.default_rng(seed)
 mp = pytest.MonkeyPatch()
 emu = device.install(mp)
-t_end, n, bad = time.time() + budget, 0, 0
+t_end, n, bad, n_slab = time.time() + budget, 0, 0, 0
+slab_share = float(os.environ.get("FUZZ_SLAB_SHARE", "0.35"))
 while time.time() < t_end:
     prog = str(rng.choice(["3_2", "3_2", "3_3", "3_1"]))
     nx = int(rng.integers(40, 520))
@@ -35,7 +36,7 @@ while time.time() < t_end:
     edge = int(rng.choice([1, 1, 0]))
     deep = int(rng.choice([1, 1, 2]))
     ns = int(rng.integers(8, 40))
-    slabbed = prog != "3_1" and rng.random() < 0.35
+    slabbed = prog != "3_1" and rng.random() < slab_share
     cfg = dict(prog=prog, nx=nx, ny=ny, npml=npml, tblock=tblock, chunk=chunk, variant=variant, fast=fast, edge=edge, deep=deep, ns=ns,
                slabbed=slabbed)
     try:
@@ -72,6 +73,7 @@ while time.time() < t_end:
             for k in names + ["ez"]:
                 assert np.concatenate([sl.get(k) for sl in slabs]).tobytes() == getattr(g, k).tobytes(), k
             n += 1
+            n_slab += 1
             continue
         sim = _sim_for(prog, nx, ny, np.float32, npml=npml, device="cpu")
         parts = [ns] if rng.random() < 0.5 else [ns // 3, ns - ns // 3]
@@ -91,5 +93,5 @@ while time.time() < t_end:
         emu.fdtd2d_tune2(3, 1)
         emu.fdtd2d_tune2(4, 3)
     n += 1
-print(f"{n} random configurations, {bad} failures (seed {seed})")
+print(f"{n} random configurations ({n_slab} of them slab runs with the fused halo exchange), {bad} failures (seed {seed})")
 mp.undo()
